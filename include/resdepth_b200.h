@@ -1,0 +1,114 @@
+/*
+ * resdepth_b200.h -- C ABI of the B200-native ResDepth hot path.
+ *
+ * The reference (prs-eth/ResDepth) has no FFI of its own: its hot path is reached through two
+ * Python classes, lib.UNet.UNet (lib/UNet.py:104-246) and lib.Trainer.Trainer
+ * (lib/Trainer.py:13-318), plus lib.evaluation.predict_linear_blend (lib/evaluation.py:460-513).
+ * Each entry point below names the reference statement(s) it replaces.  The Python mirror
+ * classes in resdepth_b200/lib/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; rd_last_error() gives the text
+ *     of the last failure on the calling thread.  Nothing throws across the ABI.
+ *   - all pointers except handles are DEVICE pointers borrowed from the caller (PyTorch owns
+ *     parameters, gradients, optimizer state, inputs and outputs); the library owns only its
+ *     workspace (activations, packed weights, partial sums, TMA descriptors).
+ *   - all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     a handle is bound to one device and is not re-entrant.
+ *   - activations are fp32; the external tensor layout is the reference's (NCHW contiguous).
+ */
+#ifndef RESDEPTH_B200_H_
+#define RESDEPTH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_ABI_VERSION 1
+
+typedef struct rd_handle rd_handle;
+
+enum { RD_ACT_RELU = 0, RD_ACT_LRELU = 1, RD_ACT_PRELU = 2 };      /* lib/UNet.py:27-33 */
+enum { RD_MATH_FP32 = 0, RD_MATH_TF32 = 1 };  /* CUDA-core fp32 FMA | tcgen05 kind::tf32 */
+
+/* Constructor arguments of lib.UNet.UNet (lib/UNet.py:105-107) + execution knobs. */
+typedef struct rd_config {
+  int32_t n_input_channels;   /* 1..8 */
+  int32_t start_kernel;       /* multiple of 16 */
+  int32_t max_filter_depth;
+  int32_t depth;              /* 1..8 */
+  int32_t act_encoder, act_decoder, act_bottleneck;   /* RD_ACT_* */
+  int32_t do_bn;
+  int32_t bias_conv_layer;    /* bias of last_layer, lib/UNet.py:184 */
+  int32_t outer_skip;
+  int32_t outer_skip_bn;      /* not supported by the CUDA path yet: rd_create fails */
+  int32_t math_mode;          /* RD_MATH_* for the GEMM-shaped layers */
+} rd_config;
+
+int rd_abi_version(void);
+const char* rd_last_error(void);
+
+/* UNet.__init__ (lib/UNet.py:104-194): builds the layer plan; no device memory yet. */
+int rd_create(const rd_config* cfg, int device, rd_handle** out);
+int rd_destroy(rd_handle* h);
+
+/* Flat parameter arena layout, in nn.Module.named_parameters() order.
+ * rd_param_info: name (<=63 chars), element count and float offset of parameter `index`.
+ * rd_buffer_info: same for the fp32 BatchNorm buffers (running_mean, running_var). */
+int rd_num_params(const rd_handle* h);
+int rd_param_info(const rd_handle* h, int index, char* name64, int64_t* numel, int64_t* offset);
+int64_t rd_param_arena_size(const rd_handle* h);
+int rd_num_buffers(const rd_handle* h);
+int rd_buffer_info(const rd_handle* h, int index, char* name64, int64_t* numel, int64_t* offset);
+int64_t rd_buffer_arena_size(const rd_handle* h);
+
+/* Borrow the caller's arenas (replaces nn.Module parameter/buffer storage and param.grad). */
+int rd_bind(rd_handle* h, float* params, float* grads, float* bn_buffers);
+
+/* Grow the workspace for batches of up to `batch` tiles of `tile` x `tile` pixels. */
+int rd_reserve(rd_handle* h, int batch, int tile, int with_backward);
+int64_t rd_workspace_bytes(const rd_handle* h);
+
+/* UNet.forward (lib/UNet.py:196-246).  x: [B,C,T,T] fp32 NCHW, y: [B,1,T,T].
+ * training != 0: BatchNorm uses batch statistics, updates running stats in the bound buffer
+ * arena (num_batches_tracked is the caller's job) and keeps activations for rd_backward. */
+int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int training, void* stream);
+
+/* Trainer._compute_denormalized_loss (lib/Trainer.py:87-100) + the seed of loss.backward()
+ * (lib/Trainer.py:179).  mask: uint8 [B,1,T,T]; mean/std: [B]; loss_out: device scalar;
+ * dy_out (may be NULL): d loss / d y_pred, [B,1,T,T]. */
+int rd_loss(rd_handle* h, const float* y_pred, const float* target, const uint8_t* mask,
+            const float* mean, const float* std, float* loss_out, float* dy_out,
+            int batch, int tile, void* stream);
+
+/* loss.backward() through the network (lib/Trainer.py:179): dy [B,1,T,T] -> gradients of all
+ * parameters, written (not accumulated) into the bound gradient arena. */
+int rd_backward(rd_handle* h, const float* dy, void* stream);
+
+/* torch.optim.Adam.step / SGD.step as built by lib/utils.py:329-334 (coupled L2 decay), over
+ * flat arenas of n floats.  step >= 1 is the Adam time step after the increment. */
+int rd_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                 float grad_scale, void* stream);
+int rd_sgd_step(float* params, const float* grads, int64_t n, float lr, float weight_decay,
+                float grad_scale, void* stream);
+
+/* Accumulation loop of predict_linear_blend (lib/evaluation.py:484-511) with
+ * denormalize_numpy (lib/data_normalization.py:41-53) and _get_blend_weights
+ * (lib/evaluation.py:516-567).  tiles: [n,1,T,T] fp32 predictions; mean/std: [n];
+ * geom: int32 [n,6] = (y, x, uly, ulx, lry, lrx); raster: float64 [rows, cols], accumulated. */
+int rd_blend_accumulate(const float* tiles, const float* mean, const float* std, const int32_t* geom,
+                        int n, int tile, int stride, double* raster, int rows, int cols, void* stream);
+
+/* Number of kernels launched by this library since the last call with reset != 0. */
+int64_t rd_launch_count(int reset);
+
+/* Debug/profiling: name of the math path actually compiled for the GEMM-shaped layers. */
+const char* rd_math_mode_name(const rd_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* RESDEPTH_B200_H_ */

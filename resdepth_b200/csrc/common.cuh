@@ -1,0 +1,142 @@
+// Shared declarations of the resdepth_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace rd {
+
+extern thread_local std::string g_last_error;
+extern long long g_launch_count;
+
+int fail(const char* fmt, ...);
+
+#define RD_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return ::rd::fail("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+#define RD_TRY(expr)            \
+  do {                          \
+    int r__ = (expr);           \
+    if (r__ != 0) return r__;   \
+  } while (0)
+
+// count + check a kernel launch (no sync)
+#define RD_LAUNCHED()                                                                      \
+  do {                                                                                     \
+    ++::rd::g_launch_count;                                                                \
+    cudaError_t e__ = cudaGetLastError();                                                  \
+    if (e__ != cudaSuccess)                                                                \
+      return ::rd::fail("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Tensor views (NHWC fp32 unless stated otherwise)
+// ---------------------------------------------------------------------------------------------
+struct Act {           // per-layer activation parameters
+  int kind;            // RD_ACT_*
+  const float* slope;  // device pointer to the negative slope (0 for relu, 0.01 lrelu, alpha prelu)
+};
+
+// ---- direct (CUDA-core) kernels for the two thin ends of the network -------------------------
+// first conv: x NCHW [B,Cin,H,W] (Cin<=8) -> z NHWC [B,H,W,Cout]; per-block channel sums for BN
+int launch_conv_first_fwd(const float* x, const float* w_oihw, float* z, float* partials, int* n_partials,
+                          int B, int Cin, int H, int W, int Cout, cudaStream_t s);
+// wgrad of the first conv: dW[co][ci][r][s] (OIHW, written) from x NCHW and dz NHWC
+int launch_conv_first_wgrad(const float* x, const float* dz, float* dw_oihw, float* scratch, size_t scratch_floats,
+                            int B, int Cin, int H, int W, int Cout, cudaStream_t s);
+// last conv C->1 (+bias +residual x[:,0]):  u NHWC [B,H,W,C] -> y [B,H,W]
+int launch_conv_last_fwd(const float* u, const float* w_oihw, const float* bias, const float* x_nchw, int x_cstride_b,
+                         float* y, int B, int H, int W, int C, cudaStream_t s);
+// backward of the last conv: du NHWC (written), dW (OIHW [1,C,3,3], written), dbias (written if non-null)
+int launch_conv_last_bwd(const float* u, const float* dy, const float* w_oihw, float* du, float* dw, float* dbias,
+                         float* scratch, size_t scratch_floats, int B, int H, int W, int C, cudaStream_t s);
+
+// ---- elementwise / reduction kernels -----------------------------------------------------------
+struct BnLayer {
+  int C;
+  const float* gamma;   // params (null when !do_bn)
+  const float* beta;
+  const float* conv_bias;  // used when !do_bn
+  float* running_mean;  // buffers (null when !do_bn)
+  float* running_var;
+  float* mean;          // saved batch stats [C]
+  float* invstd;        // [C]
+  float* scale;         // [C] fused affine:  a = act(z*scale + shift)
+  float* shift;         // [C]
+};
+// partials: [nparts][C][2] (sum, sumsq) -> mean/invstd/scale/shift (+ running stats when training)
+int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int training,
+                       int do_bn, cudaStream_t s);
+// a = act(z*scale+shift)  (+ 2x2 max-pool into p when p != null).  round_tf32: store TF32-rounded values.
+int launch_bn_act_pool(const float* z, const float* scale, const float* shift, Act act, float* a, float* p,
+                       int B, int H, int W, int C, int round_tf32, cudaStream_t s);
+// backward pass 1:  gA = unpool(g_pool, a) + g_full ; gY = gA*act'(a) -> gy_out ; partial sums
+//   partials [nblk][C][4] = (sum gY, sum gY*z, sum gA*neg(a) (prelu), unused)
+int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* a, const float* z, Act act,
+                         float* gy_out, float* partials, int* n_partials, int B, int H, int W, int C,
+                         cudaStream_t s);
+// finalize: dgamma, dbeta (or dbias) -> grads; coefficients for pass 2
+int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int do_bn,
+                           float* dgamma, float* dbeta, float* dslope, float* coef /*[C][2]*/, cudaStream_t s);
+// pass 2 (in place on gy):  dz = scale*(gy - c1 - (z-mean)*c2)    [round_bf16 unused for now]
+int launch_bn_bwd_apply(float* gy, const float* z, const BnLayer& L, const float* coef, long long npix, int C,
+                        cudaStream_t s);
+
+int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
+                float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s);
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                float wd, long long step, float gscale, cudaStream_t s);
+int launch_sgd(float* p, const float* g, long long n, float lr, float wd, float gscale, cudaStream_t s);
+int launch_blend(const float* tiles, const float* mean, const float* std, const int32_t* geom, int n, int T,
+                 int stride, double* raster, int rows, int cols, cudaStream_t s);
+int launch_fill(float* p, float v, long long n, cudaStream_t s);
+
+// weight packing ------------------------------------------------------------------------------
+// conv3x3 OIHW [Co,Ci,3,3] -> forward GEMM B matrix  Wf[(t,ci)][co]  and dgrad matrix Wd[(t,co)][ci]
+//   (dgrad tap t uses the 180-degree rotated filter).  round_tf32 rounds to nearest TF32.
+int launch_pack_conv3x3(const float* w, float* wf, float* wd, int Co, int Ci, int round_tf32, cudaStream_t s);
+// convT 2x2 [Ci,Co,2,2] -> Wm[ci][(a,b,co)] and WmT[(a,b,co)][ci]
+int launch_pack_convt(const float* w, float* wm, float* wmt, int Ci, int Co, int round_tf32, cudaStream_t s);
+// reduce split partials and un-pack to the PyTorch layouts
+//   conv: part [S][(t,ci)][co] -> dW OIHW ;  convT: part [S][(a,b,co)][ci] -> dW [ci][co][2][2]
+int launch_unpack_conv3x3_grad(const float* part, int S, float* dw, int Co, int Ci, cudaStream_t s);
+int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co, cudaStream_t s);
+// column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)
+int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,
+                       cudaStream_t s);
+
+// ---- GEMM-shaped layers, CUDA-core fp32 path ("exact" mode) ------------------------------------
+struct Gather {      // how GEMM rows (output pixels) map to source pixels per tap
+  int ntaps;         // 9 (conv3x3), 1 (plain), 4 (2x2 stride-2 gather)
+  int ups;           // 1 or 2: source pixel = ups*(h,w) + (dh,dw)
+  int Hs, Ws;        // source spatial size
+  int Ho, Wo;        // GEMM-row spatial size
+  int C;             // channels per tap (source tensor channel count)
+  signed char dh[9], dw[9];
+};
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_CONVT = 2 };
+struct Epilogue {
+  int mode;
+  float* out;             // PLAIN/STATS: [M][N] ; CONVT: u NHWC [B,2Ho,2Wo,N/4]
+  float* partials;        // STATS: [m_tiles][N][2]
+  const float* bias;      // CONVT: [N/4]
+  const float* skip;      // CONVT: NHWC same shape as out (may be null)
+  int round_tf32;         // CONVT: round the stored sum
+};
+// C[M=B*Ho*Wo][N] = gather(src)[M][ntaps*C] * Bm[ntaps*C][N]
+int launch_gemm_rows_simt(const float* src, const Gather& g, const float* Bm, int B, int N, const Epilogue& e,
+                          int* m_tiles_out, cudaStream_t s);
+// part[split][tap][Ca][N] = sum over pixels  gather(src)[p][tap][Ca] * G[p][N]
+int launch_gemm_reduce_simt(const float* src, const Gather& g, const float* G, int B, int N, float* part,
+                            size_t part_floats, int* splits_out, cudaStream_t s);
+
+// ---- GEMM-shaped layers, tcgen05 path ------------------------------------------------------------
+bool tc_available();
+
+}  // namespace rd

@@ -1,0 +1,461 @@
+// Direct (CUDA-core) kernels for the two thin ends of the U-Net, where the contraction is too
+// narrow for tensor cores and the layer is HBM-bound (enc0 AI~10, last AI~4):
+//   * first conv  Cin(<=8) -> Cout, NCHW input -> NHWC output, + BatchNorm partial sums
+//       replaces nn.Conv2d of encoder[0]            (reference lib/UNet.py:158-162, 4-5)
+//   * last  conv  C -> 1 (+bias, +outer residual)     (reference lib/UNet.py:184,227,229-244)
+//   * their weight/input gradients (autograd of the above, reference lib/Trainer.py:179)
+#include "common.cuh"
+
+namespace rd {
+
+static constexpr int TH = 8, TW = 32;          // pixel tile of one block
+static constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
+
+// ----------------------------------------------------------------------------------------------
+// first conv forward
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z,
+                      float* __restrict__ partials, int B, int Cin, int H, int W, int Cout,
+                      int tiles_x, int tiles_y) {
+  extern __shared__ float smem[];
+  float* xs = smem;                                   // [Cin][HALO_H][HALO_W]
+  float* ws = xs + Cin * HALO_H * HALO_W;             // [Cin*9][Cout]
+  float* red = ws + Cin * 9 * Cout;                   // [PG][Cout][2]
+  const int tid = threadIdx.x;
+  const int Q = Cout >> 2;
+  const int PG = 256 / Q;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int h0 = ty * TH, w0 = tx * TW;
+
+  for (int i = tid; i < Cin * 9 * Cout; i += 256) {   // w[co][ci][r][s] -> ws[(ci*9+r*3+s)][co]
+    int co = i % Cout, k = i / Cout;
+    ws[i] = w[(size_t)co * Cin * 9 + k];
+  }
+  for (int i = tid; i < Cin * HALO_H * HALO_W; i += 256) {
+    int ww = i % HALO_W, hh = (i / HALO_W) % HALO_H, ci = i / (HALO_W * HALO_H);
+    int gh = h0 + hh - 1, gw = w0 + ww - 1;
+    float v = 0.f;
+    if (gh >= 0 && gh < H && gw >= 0 && gw < W) v = x[(((size_t)b * Cin + ci) * H + gh) * W + gw];
+    xs[i] = v;
+  }
+  __syncthreads();
+
+  const int q = tid % Q, pg = tid / Q;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+  if (pg < PG) {
+    for (int g = pg; g < (TH * TW) / 4; g += PG) {
+      const int lh = g / (TW / 4), lw = (g % (TW / 4)) * 4;
+      float acc[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+      for (int ci = 0; ci < Cin; ++ci) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float* row = xs + (ci * HALO_H + lh + r) * HALO_W + lw;
+          float in[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) in[i] = row[i];
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const float4 wv = *reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * Cout + q * 4);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              acc[p][0] = fmaf(in[p + s], wv.x, acc[p][0]);
+              acc[p][1] = fmaf(in[p + s], wv.y, acc[p][1]);
+              acc[p][2] = fmaf(in[p + s], wv.z, acc[p][2]);
+              acc[p][3] = fmaf(in[p + s], wv.w, acc[p][3]);
+            }
+          }
+        }
+      }
+      const int gh = h0 + lh;
+      if (gh < H) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int gw = w0 + lw + p;
+          if (gw < W) {
+            *reinterpret_cast<float4*>(z + (((size_t)b * H + gh) * W + gw) * Cout + q * 4) =
+                make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { s1[c] += acc[p][c]; s2[c] = fmaf(acc[p][c], acc[p][c], s2[c]); }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      red[(pg * Cout + q * 4 + c) * 2 + 0] = s1[c];
+      red[(pg * Cout + q * 4 + c) * 2 + 1] = s2[c];
+    }
+  }
+  __syncthreads();
+  if (partials != nullptr) {
+    for (int i = tid; i < Cout * 2; i += 256) {
+      float a = 0.f;
+      for (int p = 0; p < PG; ++p) a += red[p * Cout * 2 + i];
+      partials[(size_t)blockIdx.x * Cout * 2 + i] = a;
+    }
+  }
+}
+
+int launch_conv_first_fwd(const float* x, const float* w, float* z, float* partials, int* n_partials, int B,
+                          int Cin, int H, int W, int Cout, cudaStream_t s) {
+  if (Cout % 4 || Cout > 1024 || Cin > 8) return fail("conv_first: unsupported Cin=%d Cout=%d", Cin, Cout);
+  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
+  const int grid = tiles_x * tiles_y * B;
+  const int Q = Cout / 4, PG = 256 / Q;
+  size_t smem = sizeof(float) * ((size_t)Cin * HALO_H * HALO_W + (size_t)Cin * 9 * Cout + (size_t)PG * Cout * 2);
+  if (smem > 48 * 1024)
+    RD_CUDA(cudaFuncSetAttribute(conv_first_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  conv_first_fwd_kernel<<<grid, 256, smem, s>>>(x, w, z, partials, B, Cin, H, W, Cout, tiles_x, tiles_y);
+  RD_LAUNCHED();
+  if (n_partials) *n_partials = grid;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// first conv wgrad:  dW[co][ci][r][s] = sum_p x[b,ci,h+r-1,w+s-1] * dz[p,co]
+// ----------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(256)
+conv_first_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ part,
+                        int B, int Cin, int H, int W, int Cout, int tiles_x, int tiles_y, int ntiles) {
+  extern __shared__ float smem[];
+  float* xs = smem;                                   // [Cin][HALO_H][HALO_W]
+  const int tid = threadIdx.x;
+  const int Q = Cout >> 2;
+  const int NS = 256 / (Q * 4);                       // pixel streams per block
+  const int q = tid % Q, tg = (tid / Q) % 4, st = tid / (Q * 4);
+  const int ntaps = Cin * 9;
+  int off[NT];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    int k = tg * NT + i;
+    if (k >= ntaps) k = 0;
+    const int ci = k / 9, r = (k % 9) / 3, sx = k % 3;
+    off[i] = (ci * HALO_H + r) * HALO_W + sx;
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int h0 = ty * TH, w0 = tx * TW;
+    __syncthreads();
+    for (int i = tid; i < Cin * HALO_H * HALO_W; i += 256) {
+      int ww = i % HALO_W, hh = (i / HALO_W) % HALO_H, ci = i / (HALO_W * HALO_H);
+      int gh = h0 + hh - 1, gw = w0 + ww - 1;
+      float v = 0.f;
+      if (gh >= 0 && gh < H && gw >= 0 && gw < W) v = x[(((size_t)b * Cin + ci) * H + gh) * W + gw];
+      xs[i] = v;
+    }
+    __syncthreads();
+    if (st < NS) {
+      for (int p = st; p < TH * TW; p += NS) {
+        const int lh = p / TW, lw = p % TW;
+        const int gh = h0 + lh, gw = w0 + lw;
+        if (gh >= H || gw >= W) continue;
+        const float4 g = *reinterpret_cast<const float4*>(dz + (((size_t)b * H + gh) * W + gw) * Cout + q * 4);
+        const float* base = xs + lh * HALO_W + lw;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          const float xv = base[off[i]];
+          acc[i][0] = fmaf(xv, g.x, acc[i][0]);
+          acc[i][1] = fmaf(xv, g.y, acc[i][1]);
+          acc[i][2] = fmaf(xv, g.z, acc[i][2]);
+          acc[i][3] = fmaf(xv, g.w, acc[i][3]);
+        }
+      }
+    }
+  }
+  // reduce the NS streams through shared memory, then write the block partial [Cout][ntaps]
+  __syncthreads();
+  float* red = smem;                                  // [NS][Cout*ntaps]  (re-uses xs; sized by host)
+  if (st < NS) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int k = tg * NT + i;
+      if (k < ntaps) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) red[(size_t)st * Cout * ntaps + (q * 4 + c) * ntaps + k] = acc[i][c];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < Cout * ntaps; i += 256) {
+    float a = 0.f;
+    for (int s2 = 0; s2 < NS; ++s2) a += red[(size_t)s2 * Cout * ntaps + i];
+    part[(size_t)blockIdx.x * Cout * ntaps + i] = a;
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += (double)part[(size_t)p * n + i];
+  out[i] = (float)a;
+}
+
+int launch_conv_first_wgrad(const float* x, const float* dz, float* dw, float* scratch, size_t scratch_floats,
+                            int B, int Cin, int H, int W, int Cout, cudaStream_t s) {
+  const int Q = Cout / 4;
+  if (Cout % 4 || Q * 4 > 256 || Cin > 8) return fail("conv_first_wgrad: unsupported Cin=%d Cout=%d", Cin, Cout);
+  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
+  const int ntiles = tiles_x * tiles_y * B;
+  const int ntaps = Cin * 9;
+  int grid = ntiles < 296 ? ntiles : 296;
+  while ((size_t)grid * Cout * ntaps > scratch_floats && grid > 1) grid /= 2;
+  if ((size_t)grid * Cout * ntaps > scratch_floats) return fail("conv_first_wgrad: scratch too small");
+  const int NS = 256 / (Q * 4);
+  size_t smem_x = (size_t)Cin * HALO_H * HALO_W, smem_r = (size_t)NS * Cout * ntaps;
+  size_t smem = sizeof(float) * (smem_x > smem_r ? smem_x : smem_r);
+  const int NT = (ntaps + 3) / 4;
+#define RD_WG(NTV)                                                                                            \
+  {                                                                                                           \
+    RD_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel<NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                 (int)smem));                                                                 \
+    conv_first_wgrad_kernel<NTV><<<grid, 256, smem, s>>>(x, dz, scratch, B, Cin, H, W, Cout, tiles_x, tiles_y, \
+                                                         ntiles);                                             \
+  }
+  if (NT <= 3) RD_WG(3)
+  else if (NT <= 5) RD_WG(5)
+  else if (NT <= 7) RD_WG(7)
+  else if (NT <= 9) RD_WG(9)
+  else if (NT <= 14) RD_WG(14)
+  else RD_WG(18)
+#undef RD_WG
+  RD_LAUNCHED();
+  const int n = Cout * ntaps;
+  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(scratch, grid, n, dw);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// last conv forward:  y[b,h,w] = sum_{c,r,s} u[b,h+r-1,w+s-1,c] W[c,r,s] + bias + x[b,0,h,w]
+//   phase 1: per input pixel, 9 partial dot products over channels (each u element read once)
+//   phase 2: per output pixel, gather the 9 partials of its 3x3 neighbourhood
+// ----------------------------------------------------------------------------------------------
+template <int QPL>
+__global__ void __launch_bounds__(256)
+conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
+                     const float* __restrict__ x0, long long x_bstride, float* __restrict__ y, int B, int H,
+                     int W, int C, int tiles_x, int tiles_y) {
+  __shared__ float ts[HALO_H * HALO_W][9];
+  const int tid = threadIdx.x;
+  const int lane16 = tid & 15, grp = tid >> 4;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int h0 = ty * TH, w0 = tx * TW;
+  float4 wr[QPL][9];
+#pragma unroll
+  for (int j = 0; j < QPL; ++j) {
+    const int c = (lane16 + 16 * j) * 4;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (c < C) wr[j][k] = make_float4(w[(c + 0) * 9 + k], w[(c + 1) * 9 + k], w[(c + 2) * 9 + k], w[(c + 3) * 9 + k]);
+      else wr[j][k] = make_float4(0, 0, 0, 0);
+    }
+  }
+  for (int p = grp; p < HALO_H * HALO_W; p += 16) {
+    const int hh = p / HALO_W, ww = p % HALO_W;
+    const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    if (gh >= 0 && gh < H && gw >= 0 && gw < W) {
+      const float* up = u + (((size_t)b * H + gh) * W + gw) * C;
+#pragma unroll
+      for (int j = 0; j < QPL; ++j) {
+        const int c = (lane16 + 16 * j) * 4;
+        if (c < C) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(up + c));
+#pragma unroll
+          for (int k = 0; k < 9; ++k)
+            acc[k] += v.x * wr[j][k].x + v.y * wr[j][k].y + v.z * wr[j][k].z + v.w * wr[j][k].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float a = acc[k];
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      acc[k] = a;
+    }
+    if (lane16 == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) ts[p][k] = acc[k];
+    }
+  }
+  __syncthreads();
+  {
+    const int lh = tid / TW, lw = tid % TW;
+    const int gh = h0 + lh, gw = w0 + lw;
+    if (gh < H && gw < W) {
+      float a = bias ? bias[0] : 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) a += ts[(lh + r) * HALO_W + lw + s][r * 3 + s];
+      const size_t o = ((size_t)b * H + gh) * W + gw;
+      if (x0) a += x0[(size_t)b * x_bstride + (size_t)gh * W + gw];
+      y[o] = a;
+    }
+  }
+}
+
+int launch_conv_last_fwd(const float* u, const float* w, const float* bias, const float* x, int x_bstride,
+                         float* y, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 4 || C > 128) return fail("conv_last: unsupported C=%d (needs C%%4==0, C<=128)", C);
+  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
+  const int grid = tiles_x * tiles_y * B;
+  if (C <= 64)
+    conv_last_fwd_kernel<1><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, y, B, H, W, C, tiles_x, tiles_y);
+  else
+    conv_last_fwd_kernel<2><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, y, B, H, W, C, tiles_x, tiles_y);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// last conv backward: for input pixel q and channel c, with n[r][s] = dy[q - (r-1, s-1)]:
+//   du[q,c] = sum_{r,s} n[r][s] W[c,r,s];   dW[c,r,s] += u[q,c] n[r][s];   db += dy[q]
+// ----------------------------------------------------------------------------------------------
+template <int QPL>
+__global__ void __launch_bounds__(256)
+conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ w,
+                     float* __restrict__ du, float* __restrict__ part, int B, int H, int W, int C, int tiles_x,
+                     int tiles_y, int ntiles) {
+  __shared__ float dys[HALO_H * HALO_W];
+  extern __shared__ float red_dyn[];                  // [16][RS]
+  constexpr int RS = 9 * 4 * 16 * QPL + 1;
+  const int tid = threadIdx.x;
+  const int lane16 = tid & 15, grp = tid >> 4;
+  float4 wr[QPL][9], dwacc[QPL][9];
+  float dbacc = 0.f;
+#pragma unroll
+  for (int j = 0; j < QPL; ++j) {
+    const int c = (lane16 + 16 * j) * 4;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      if (c < C) wr[j][k] = make_float4(w[(c + 0) * 9 + k], w[(c + 1) * 9 + k], w[(c + 2) * 9 + k], w[(c + 3) * 9 + k]);
+      else wr[j][k] = make_float4(0, 0, 0, 0);
+      dwacc[j][k] = make_float4(0, 0, 0, 0);
+    }
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int h0 = ty * TH, w0 = tx * TW;
+    __syncthreads();
+    for (int i = tid; i < HALO_H * HALO_W; i += 256) {
+      const int hh = i / HALO_W, ww = i % HALO_W;
+      const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+      dys[i] = (gh >= 0 && gh < H && gw >= 0 && gw < W) ? dy[((size_t)b * H + gh) * W + gw] : 0.f;
+    }
+    __syncthreads();
+    for (int p = grp; p < TH * TW; p += 16) {
+      const int lh = p / TW, lw = p % TW;
+      const int gh = h0 + lh, gw = w0 + lw;
+      if (gh >= H || gw >= W) continue;
+      float n[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * HALO_W + (lw + 1 - (s2 - 1))];
+      if (lane16 == 0) dbacc += n[4];
+      const size_t o = (((size_t)b * H + gh) * W + gw) * C;
+#pragma unroll
+      for (int j = 0; j < QPL; ++j) {
+        const int c = (lane16 + 16 * j) * 4;
+        if (c < C) {
+          const float4 uv = __ldg(reinterpret_cast<const float4*>(u + o + c));
+          float4 d = make_float4(0, 0, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) {
+            d.x = fmaf(n[k], wr[j][k].x, d.x); d.y = fmaf(n[k], wr[j][k].y, d.y);
+            d.z = fmaf(n[k], wr[j][k].z, d.z); d.w = fmaf(n[k], wr[j][k].w, d.w);
+            dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
+            dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
+          }
+          *reinterpret_cast<float4*>(du + o + c) = d;
+        }
+      }
+    }
+  }
+  // block reduction over the 16 pixel groups -> part[blk][C*9 + 1]
+#pragma unroll
+  for (int j = 0; j < QPL; ++j)
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int base = ((j * 16 + lane16) * 9 + k) * 4;
+      float* rr = red_dyn + grp * RS + base;
+      rr[0] = dwacc[j][k].x; rr[1] = dwacc[j][k].y; rr[2] = dwacc[j][k].z; rr[3] = dwacc[j][k].w;
+    }
+  if (lane16 == 0) red_dyn[grp * RS + RS - 1] = dbacc;
+  __syncthreads();
+  for (int i = tid; i < 9 * 4 * 16 * QPL + 1; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) a += red_dyn[g * RS + i];
+    if (i == 9 * 4 * 16 * QPL) {
+      part[(size_t)blockIdx.x * (C * 9 + 1) + C * 9] = a;
+    } else {
+      const int cc = i & 3, k = (i >> 2) % 9, ql = (i >> 2) / 9;   // ql = j*16 + lane16 = channel quad
+      const int c = ql * 4 + cc;
+      if (c < C) part[(size_t)blockIdx.x * (C * 9 + 1) + c * 9 + k] = a;
+    }
+  }
+}
+
+__global__ void last_bwd_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ dw,
+                                       float* __restrict__ dbias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = C * 9 + 1;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += (double)part[(size_t)p * n + i];
+  if (i < C * 9) dw[i] = (float)a;
+  else if (dbias) dbias[0] = (float)a;
+}
+
+int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float* du, float* dw, float* dbias,
+                         float* scratch, size_t scratch_floats, int B, int H, int W, int C, cudaStream_t s) {
+  if (C % 4 || C > 128) return fail("conv_last_bwd: unsupported C=%d", C);
+  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
+  const int ntiles = tiles_x * tiles_y * B;
+  int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
+  if ((size_t)grid * (C * 9 + 1) > scratch_floats) return fail("conv_last_bwd: scratch too small");
+  if (C <= 64) {
+    const int smem = 16 * (9 * 4 * 16 * 1 + 1) * (int)sizeof(float);
+    conv_last_bwd_kernel<1><<<grid, 256, smem, s>>>(u, dy, w, du, scratch, B, H, W, C, tiles_x, tiles_y, ntiles);
+  } else {
+    const int smem = 16 * (9 * 4 * 16 * 2 + 1) * (int)sizeof(float);
+    RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_last_bwd_kernel<2><<<grid, 256, smem, s>>>(u, dy, w, du, scratch, B, H, W, C, tiles_x, tiles_y, ntiles);
+  }
+  RD_LAUNCHED();
+  last_bwd_finish_kernel<<<cdiv(C * 9 + 1, 128), 128, 0, s>>>(scratch, grid, C, dw, dbias);
+  RD_LAUNCHED();
+  return 0;
+}
+
+}  // namespace rd
