@@ -32,6 +32,8 @@ typedef struct rd_handle rd_handle;
 
 enum { RD_ACT_RELU = 0, RD_ACT_LRELU = 1, RD_ACT_PRELU = 2 };      /* lib/UNet.py:27-33 */
 enum { RD_MATH_FP32 = 0, RD_MATH_TF32 = 1 };  /* CUDA-core fp32 FMA | tcgen05 kind::tf32 */
+/* rd_forward modes: model.eval() under no_grad | model.train() | model.eval() with autograd recording */
+enum { RD_FWD_EVAL = 0, RD_FWD_TRAIN = 1, RD_FWD_EVAL_SAVE = 2 };
 
 /* Constructor arguments of lib.UNet.UNet (lib/UNet.py:105-107) + execution knobs. */
 typedef struct rd_config {
@@ -72,9 +74,10 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward);
 int64_t rd_workspace_bytes(const rd_handle* h);
 
 /* UNet.forward (lib/UNet.py:196-246).  x: [B,C,T,T] fp32 NCHW, y: [B,1,T,T].
- * training != 0: BatchNorm uses batch statistics, updates running stats in the bound buffer
- * arena (num_batches_tracked is the caller's job) and keeps activations for rd_backward. */
-int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int training, void* stream);
+ * mode RD_FWD_TRAIN: BatchNorm uses batch statistics, updates running stats in the bound buffer
+ * arena (num_batches_tracked is the caller's job) and keeps activations for rd_backward.
+ * RD_FWD_EVAL_SAVE: running statistics, activations kept.  RD_FWD_EVAL: inference only. */
+int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int mode, void* stream);
 
 /* Trainer._compute_denormalized_loss (lib/Trainer.py:87-100) + the seed of loss.backward()
  * (lib/Trainer.py:179).  mask: uint8 [B,1,T,T]; mean/std: [B]; loss_out: device scalar;
@@ -84,8 +87,9 @@ int rd_loss(rd_handle* h, const float* y_pred, const float* target, const uint8_
             int batch, int tile, void* stream);
 
 /* loss.backward() through the network (lib/Trainer.py:179): dy [B,1,T,T] -> gradients of all
- * parameters, written (not accumulated) into the bound gradient arena. */
-int rd_backward(rd_handle* h, const float* dy, void* stream);
+ * parameters, written (not accumulated) into the bound gradient arena.  x is the input of the
+ * matching rd_forward call (needed for the first layer's weight gradient). */
+int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream);
 
 /* torch.optim.Adam.step / SGD.step as built by lib/utils.py:329-334 (coupled L2 decay), over
  * flat arenas of n floats.  step >= 1 is the Adam time step after the increment. */
@@ -101,6 +105,22 @@ int rd_sgd_step(float* params, const float* grads, int64_t n, float lr, float we
  * geom: int32 [n,6] = (y, x, uly, ulx, lry, lrx); raster: float64 [rows, cols], accumulated. */
 int rd_blend_accumulate(const float* tiles, const float* mean, const float* std, const int32_t* geom,
                         int n, int tile, int stride, double* raster, int rows, int cols, void* stream);
+
+/* Per-category device timing (CUDA events on the launching stream around the library's own launches).
+ * rd_profile_enable(h, 1) starts recording; rd_profile_collect synchronises the recorded events and folds
+ * them into per-category totals; rd_profile_read returns one category: total milliseconds, algorithmic
+ * FLOPs and algorithmic HBM bytes of the bracketed launches, number of kernel launches and of brackets.
+ * rd_profile_enable(h, 0) stops recording and clears the totals. */
+enum {
+  RD_PROF_CONV_FWD = 0, RD_PROF_CONV_DGRAD, RD_PROF_CONV_WGRAD, RD_PROF_CONVT_FWD, RD_PROF_CONVT_DGRAD,
+  RD_PROF_CONVT_WGRAD, RD_PROF_FIRST_FWD, RD_PROF_FIRST_WGRAD, RD_PROF_LAST_FWD, RD_PROF_LAST_BWD,
+  RD_PROF_BN_FINALIZE, RD_PROF_BN_ACT_POOL, RD_PROF_BN_BWD_REDUCE, RD_PROF_BN_BWD_APPLY, RD_PROF_PACK,
+  RD_PROF_UNPACK, RD_PROF_BIAS_GRAD, RD_PROF_LOSS, RD_PROF_NUM
+};
+int rd_profile_enable(rd_handle* h, int on);
+int rd_profile_collect(rd_handle* h);
+int rd_profile_read(const rd_handle* h, int category, char* name64, double* ms, double* flops, double* bytes,
+                    int64_t* launches, int64_t* calls);
 
 /* Number of kernels launched by this library since the last call with reset != 0. */
 int64_t rd_launch_count(int reset);

@@ -1,0 +1,706 @@
+// C ABI of the B200-native ResDepth hot path (see include/resdepth_b200.h): the layer plan of
+// lib.UNet.UNet (reference lib/UNet.py:104-246), workspace management, and the forward / backward schedules.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/resdepth_b200.h"
+#include "common.cuh"
+
+namespace rd {
+
+thread_local std::string g_last_error;
+long long g_launch_count = 0;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return 1;
+}
+
+struct ParamInfo {
+  std::string name;
+  long long numel;
+  long long offset;   // in floats, 16-byte aligned
+};
+
+struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottleneck / decoder conv (lib/UNet.py:36-93)
+  int Cin = 0, Cout = 0;
+  int act = RD_ACT_RELU;
+  bool pool = false;
+  long long w = -1, bias = -1, gamma = -1, beta = -1, slope = -1;   // param arena offsets
+  long long rm = -1, rv = -1;                                       // buffer arena offsets
+  // workspace
+  float *z = nullptr, *a = nullptr, *p = nullptr;
+  float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
+  float *w_kn = nullptr, *w_nk = nullptr, *wd_kn = nullptr, *wd_nk = nullptr;
+  bool tc = false;     // GEMMs of this block run on tcgen05
+};
+
+struct UpConv {        // ConvTranspose2d(C, C, 2, 2) (lib/UNet.py:17-24)
+  int C = 0;
+  long long w = -1, bias = -1;
+  float *u = nullptr;
+  float *w_kn = nullptr, *w_nk = nullptr;
+  bool tc = false;
+};
+
+}  // namespace rd
+
+using namespace rd;
+
+struct rd_handle {
+  rd_config cfg;
+  int device = 0;
+  int depth = 0;
+  std::vector<int> widths;
+  std::vector<ConvBlock> enc, dec;   // dec has depth-1 entries
+  ConvBlock bott;
+  std::vector<UpConv> ups;           // depth entries
+  long long last_w = -1, last_b = -1;
+  std::vector<ParamInfo> params, buffers;
+  long long param_floats = 0, buffer_floats = 0;
+  float *P = nullptr, *G = nullptr, *BUF = nullptr;   // bound arenas
+
+  // workspace
+  void* slab = nullptr;
+  size_t slab_bytes = 0;
+  int res_batch = 0, res_tile = 0, res_bwd = 0;
+  float *partials = nullptr, *scratch = nullptr, *part = nullptr, *coef = nullptr, *consts = nullptr;
+  size_t partials_floats = 0, scratch_floats = 0, part_floats = 0;
+  std::vector<float*> g_skip;
+  float *gy = nullptr, *gh = nullptr, *gp = nullptr;
+  // state of the last forward
+  int fwd_batch = 0, fwd_tile = 0, fwd_mode = -1;
+  bool tf32() const { return cfg.math_mode == RD_MATH_TF32; }
+
+  // per-category CUDA-event timing (rd_profile_*): off by default
+  bool profiling = false;
+  struct ProfRec { int cat; cudaEvent_t e0, e1; double flops, bytes; int launches; };
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[RD_PROF_NUM] = {0}, prof_flops[RD_PROF_NUM] = {0}, prof_bytes[RD_PROF_NUM] = {0};
+  long long prof_launches[RD_PROF_NUM] = {0}, prof_calls[RD_PROF_NUM] = {0};
+};
+
+namespace {
+const char* const kProfNames[RD_PROF_NUM] = {
+    "conv3x3_fwd", "conv3x3_dgrad", "conv3x3_wgrad", "convT_fwd", "convT_dgrad", "convT_wgrad",
+    "first_conv_fwd", "first_conv_wgrad", "last_conv_fwd", "last_conv_bwd", "bn_finalize", "bn_act_pool",
+    "bn_bwd_reduce", "bn_bwd_apply", "pack_weights", "unpack_grads", "bias_grad", "loss"};
+
+// brackets the launches of one category with events on the launching stream when profiling is on
+struct ProfScope {
+  rd_handle* h;
+  cudaStream_t s;
+  size_t idx = (size_t)-1;
+  long long launches0 = 0;
+  ProfScope(rd_handle* h_, int cat, double flops, double bytes, cudaStream_t s_) : h(h_), s(s_) {
+    if (!h->profiling) return;
+    cudaEvent_t ev[2];
+    for (auto& e : ev) {
+      if (!h->event_pool.empty()) { e = h->event_pool.back(); h->event_pool.pop_back(); }
+      else if (cudaEventCreate(&e) != cudaSuccess) return;
+    }
+    cudaEventRecord(ev[0], s);
+    launches0 = rd::g_launch_count;
+    h->prof.push_back({cat, ev[0], ev[1], flops, bytes, 0});
+    idx = h->prof.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx == (size_t)-1) return;
+    cudaEventRecord(h->prof[idx].e1, s);
+    h->prof[idx].launches = (int)(rd::g_launch_count - launches0);
+  }
+};
+}  // namespace
+
+
+namespace {
+
+long long align4(long long v) { return (v + 3) & ~3LL; }
+
+void add_param(rd_handle* h, const std::string& name, long long numel, long long* off_out) {
+  ParamInfo p{name, numel, h->param_floats};
+  if (off_out) *off_out = p.offset;
+  h->param_floats = align4(h->param_floats + numel);
+  h->params.push_back(p);
+}
+void add_buffer(rd_handle* h, const std::string& name, long long numel, long long* off_out) {
+  ParamInfo p{name, numel, h->buffer_floats};
+  if (off_out) *off_out = p.offset;
+  h->buffer_floats = align4(h->buffer_floats + numel);
+  h->buffers.push_back(p);
+}
+
+// registers the parameters of one conv block under `prefix` in nn.Module registration order
+void plan_block(rd_handle* h, ConvBlock& b, const std::string& prefix, int Cin, int Cout, int act, bool pool) {
+  b.Cin = Cin; b.Cout = Cout; b.act = act; b.pool = pool;
+  add_param(h, prefix + ".0.weight", (long long)Cout * Cin * 9, &b.w);
+  int idx = 1;
+  if (h->cfg.do_bn) {
+    add_param(h, prefix + ".1.weight", Cout, &b.gamma);
+    add_param(h, prefix + ".1.bias", Cout, &b.beta);
+    add_buffer(h, prefix + ".1.running_mean", Cout, &b.rm);
+    add_buffer(h, prefix + ".1.running_var", Cout, &b.rv);
+    idx = 2;
+  } else {
+    add_param(h, prefix + ".0.bias", Cout, &b.bias);
+  }
+  if (act == RD_ACT_PRELU) add_param(h, prefix + "." + std::to_string(idx) + ".weight", 1, &b.slope);
+}
+
+Gather gather_conv3x3(int H, int W, int C) {
+  Gather g{};
+  g.ntaps = 9; g.ups = 1; g.Hs = g.Ho = H; g.Ws = g.Wo = W; g.C = C;
+  for (int t = 0; t < 9; ++t) { g.dh[t] = (signed char)(t / 3 - 1); g.dw[t] = (signed char)(t % 3 - 1); }
+  return g;
+}
+Gather gather_plain(int H, int W, int C) {
+  Gather g{};
+  g.ntaps = 1; g.ups = 1; g.Hs = g.Ho = H; g.Ws = g.Wo = W; g.C = C;
+  return g;
+}
+Gather gather_up2(int Hin, int Win, int C) {      // rows = input pixels, 4 taps into the 2x-upsampled tensor
+  Gather g{};
+  g.ntaps = 4; g.ups = 2; g.Hs = 2 * Hin; g.Ws = 2 * Win; g.Ho = Hin; g.Wo = Win; g.C = C;
+  for (int t = 0; t < 4; ++t) { g.dh[t] = (signed char)(t >> 1); g.dw[t] = (signed char)(t & 1); }
+  return g;
+}
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(reinterpret_cast<char*>(b)) {}
+  float* take(size_t floats) {
+    float* p = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += (floats * sizeof(float) + 255) & ~size_t(255);
+    return p;
+  }
+};
+
+// lays out the workspace; with base == nullptr only measures it
+size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
+  Carver c(base);
+  const int D = h->depth;
+  const bool tf = h->tf32();
+  size_t max_out = 0, max_pool = 0;
+  auto block = [&](ConvBlock& b, int H, bool first) {
+    const size_t n = (size_t)B * H * H * b.Cout;
+    b.z = c.take(n);
+    b.a = c.take(n);
+    b.p = b.pool ? c.take(n / 4) : nullptr;
+    b.mean = c.take(b.Cout); b.invstd = c.take(b.Cout); b.scale = c.take(b.Cout); b.shift = c.take(b.Cout);
+    if (!first) {
+      const size_t wn = (size_t)9 * b.Cin * b.Cout;
+      b.w_kn = c.take(wn);
+      b.wd_kn = c.take(wn);
+      b.w_nk = tf ? c.take(wn) : nullptr;
+      b.wd_nk = tf ? c.take(wn) : nullptr;
+    }
+    if (n > max_out) max_out = n;
+    if (b.pool && n / 4 > max_pool) max_pool = n / 4;
+  };
+  for (int i = 0; i < D; ++i) block(h->enc[i], T >> i, i == 0);
+  block(h->bott, T >> D, false);
+  for (int j = 0; j < D; ++j) {
+    UpConv& u = h->ups[j];
+    const int Hout = T >> (D - 1 - j);
+    u.u = c.take((size_t)B * Hout * Hout * u.C);
+    u.w_kn = c.take((size_t)4 * u.C * u.C);
+    u.w_nk = c.take((size_t)4 * u.C * u.C);
+    if (j < D - 1) block(h->dec[j], Hout, false);
+  }
+  h->partials_floats = (size_t)2 << 20;
+  h->partials = c.take(h->partials_floats);
+  h->scratch_floats = (size_t)1 << 20;
+  h->scratch = c.take(h->scratch_floats);
+  h->coef = c.take(4 * 2048);
+  h->consts = c.take(64);
+  if (bwd) {
+    h->part_floats = (size_t)8 << 20;
+    h->part = c.take(h->part_floats);
+    h->g_skip.resize(D);
+    for (int i = 0; i < D; ++i) h->g_skip[i] = c.take((size_t)B * (T >> i) * (T >> i) * h->enc[i].Cout);
+    h->gy = c.take(max_out);
+    h->gh = c.take(max_out);
+    h->gp = c.take(max_pool);
+  } else {
+    h->part = nullptr; h->part_floats = 0;
+    h->g_skip.assign(D, nullptr);
+    h->gy = h->gh = h->gp = nullptr;
+  }
+  return c.off;
+}
+
+int check_shape(const rd_handle* h, int B, int T) {
+  if (B < 1) return fail("batch must be >= 1 (got %d)", B);
+  const int D = h->depth;
+  if (T < (1 << D) || T % (1 << D)) return fail("tile size %d is not a positive multiple of 2^depth = %d", T, 1 << D);
+  return 0;
+}
+
+BnLayer bn_view(const rd_handle* h, const ConvBlock& b) {
+  BnLayer L{};
+  L.C = b.Cout;
+  L.gamma = b.gamma >= 0 ? h->P + b.gamma : nullptr;
+  L.beta = b.beta >= 0 ? h->P + b.beta : nullptr;
+  L.conv_bias = b.bias >= 0 ? h->P + b.bias : nullptr;
+  L.running_mean = b.rm >= 0 ? h->BUF + b.rm : nullptr;
+  L.running_var = b.rv >= 0 ? h->BUF + b.rv : nullptr;
+  L.mean = b.mean; L.invstd = b.invstd; L.scale = b.scale; L.shift = b.shift;
+  return L;
+}
+
+Act act_view(const rd_handle* h, const ConvBlock& b) {
+  Act a{};
+  a.kind = b.act;
+  if (b.act == RD_ACT_PRELU) a.slope = h->P + b.slope;
+  else a.slope = h->consts + (b.act == RD_ACT_LRELU ? 1 : 0);
+  return a;
+}
+
+int pack_weights(rd_handle* h, bool for_backward, cudaStream_t s) {
+  const int rnd = h->tf32() ? 1 : 0;
+  ProfScope ps(h, RD_PROF_PACK, 0.0, 4.0 * 3.0 * (double)h->param_floats, s);
+  auto block = [&](ConvBlock& b) -> int {
+    if (!b.w_kn) return 0;
+    return launch_pack_conv3x3(h->P + b.w, b.w_kn, b.w_nk, for_backward ? b.wd_kn : nullptr,
+                               for_backward ? b.wd_nk : nullptr, b.Cout, b.Cin, rnd && b.tc, s);
+  };
+  for (auto& b : h->enc) RD_TRY(block(b));
+  RD_TRY(block(h->bott));
+  for (auto& b : h->dec) RD_TRY(block(b));
+  for (auto& u : h->ups) RD_TRY(launch_pack_convt(h->P + u.w, u.w_kn, u.w_nk, u.C, u.C, rnd && u.tc, s));
+  return 0;
+}
+
+// conv3x3 of one block: src NHWC [B,H,W,Cin] -> z (+ statistics partials)
+int conv_block_forward(rd_handle* h, ConvBlock& b, const float* src, int B, int H, bool batch_stats, int* np,
+                       cudaStream_t s) {
+  Gather g = gather_conv3x3(H, H, b.Cin);
+  Epilogue e{};
+  e.mode = batch_stats ? EPI_STATS : EPI_PLAIN;
+  e.out = b.z;
+  e.partials = h->partials;
+  *np = 0;
+  const double px = (double)B * H * H;
+  ProfScope ps(h, RD_PROF_CONV_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+  return launch_gemm_rows_simt(src, g, b.w_kn, B, b.Cout, e, np, s);
+}
+
+// BN statistics finalize + fused normalise/activation(/pool) pass of one block
+int bn_act_forward(rd_handle* h, ConvBlock& b, int np, int B, int H, bool train, int round_a, int round_p,
+                   cudaStream_t s) {
+  BnLayer L = bn_view(h, b);
+  {
+    ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
+    RD_TRY(launch_bn_finalize(L, h->partials, np, (long long)B * H * H, train, h->cfg.do_bn, s));
+  }
+  const double n = (double)B * H * H * b.Cout;
+  ProfScope ps(h, RD_PROF_BN_ACT_POOL, 0.0, 4.0 * n * (b.pool ? 2.25 : 2.0), s);
+  return launch_bn_act_pool(b.z, b.scale, b.shift, act_view(h, b), b.a, b.pool ? b.p : nullptr, B, H, H, b.Cout,
+                            round_a, round_p, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int rd_abi_version(void) { return RD_ABI_VERSION; }
+const char* rd_last_error(void) { return g_last_error.c_str(); }
+
+int rd_create(const rd_config* cfg, int device, rd_handle** out) {
+  if (!cfg || !out) return fail("rd_create: null argument");
+  *out = nullptr;
+  if (cfg->n_input_channels < 1 || cfg->n_input_channels > 8)
+    return fail("n_input_channels=%d outside the supported range 1..8", cfg->n_input_channels);
+  if (cfg->depth < 1 || cfg->depth > 8) return fail("depth=%d outside the supported range 1..8", cfg->depth);
+  if (cfg->start_kernel < 32 || cfg->start_kernel % 32)
+    return fail("start_kernel=%d must be a positive multiple of 32", cfg->start_kernel);
+  if (cfg->start_kernel > 128) return fail("start_kernel=%d > 128 is not supported by the full-resolution kernels", cfg->start_kernel);
+  if (cfg->max_filter_depth % 32 || cfg->max_filter_depth < cfg->start_kernel || cfg->max_filter_depth > 1024)
+    return fail("max_filter_depth=%d must be a multiple of 32 in [start_kernel, 1024]", cfg->max_filter_depth);
+  if (cfg->outer_skip_bn) return fail("outer_skip_BN=True is not supported by the CUDA path");
+  for (int a : {cfg->act_encoder, cfg->act_decoder, cfg->act_bottleneck})
+    if (a < RD_ACT_RELU || a > RD_ACT_PRELU) return fail("unknown activation id %d", a);
+  if (cfg->math_mode != RD_MATH_FP32 && cfg->math_mode != RD_MATH_TF32) return fail("unknown math mode %d", cfg->math_mode);
+
+  rd_handle* h = new rd_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  const int D = h->depth = cfg->depth;
+  for (int i = 0; i < D; ++i) {
+    long long w = (long long)cfg->start_kernel << i;
+    h->widths.push_back((int)(w > cfg->max_filter_depth ? cfg->max_filter_depth : w));   // lib/UNet.py:152-155
+  }
+  h->enc.resize(D);
+  h->dec.resize(D - 1);
+  h->ups.resize(D);
+  for (int i = 0; i < D; ++i)
+    plan_block(h, h->enc[i], "encoder." + std::to_string(i) + ".0", i == 0 ? cfg->n_input_channels : h->widths[i - 1],
+               h->widths[i], cfg->act_encoder, true);
+  plan_block(h, h->bott, "bottleneck", h->widths[D - 1], h->widths[D - 1], cfg->act_bottleneck, false);
+  for (int j = 0; j < D; ++j) {
+    const int C = h->widths[D - 1 - j];
+    h->ups[j].C = C;
+    if (j < D - 1) {
+      const std::string p = "decoder." + std::to_string(j);
+      add_param(h, p + ".0.weight", (long long)C * C * 4, &h->ups[j].w);
+      add_param(h, p + ".0.bias", C, &h->ups[j].bias);
+      plan_block(h, h->dec[j], p + ".1", C, h->widths[D - 2 - j], cfg->act_decoder, false);
+    } else {
+      const std::string p = "decoder." + std::to_string(j);
+      add_param(h, p + ".weight", (long long)C * C * 4, &h->ups[j].w);
+      add_param(h, p + ".bias", C, &h->ups[j].bias);
+    }
+  }
+  add_param(h, "last_layer.weight", (long long)cfg->start_kernel * 9, &h->last_w);
+  if (cfg->bias_conv_layer) add_param(h, "last_layer.bias", 1, &h->last_b);
+  *out = h;
+  return 0;
+}
+
+int rd_destroy(rd_handle* h) {
+  if (!h) return 0;
+  if (h->slab) {
+    cudaSetDevice(h->device);
+    cudaFree(h->slab);
+  }
+  for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  for (auto& e : h->event_pool) cudaEventDestroy(e);
+  delete h;
+  return 0;
+}
+
+int rd_num_params(const rd_handle* h) { return (int)h->params.size(); }
+int rd_num_buffers(const rd_handle* h) { return (int)h->buffers.size(); }
+int64_t rd_param_arena_size(const rd_handle* h) { return h->param_floats; }
+int64_t rd_buffer_arena_size(const rd_handle* h) { return h->buffer_floats; }
+
+static int info(const std::vector<ParamInfo>& v, int index, char* name64, int64_t* numel, int64_t* offset) {
+  if (index < 0 || index >= (int)v.size()) return fail("index %d out of range", index);
+  if (name64) {
+    std::strncpy(name64, v[index].name.c_str(), 63);
+    name64[63] = 0;
+  }
+  if (numel) *numel = v[index].numel;
+  if (offset) *offset = v[index].offset;
+  return 0;
+}
+int rd_param_info(const rd_handle* h, int index, char* name64, int64_t* numel, int64_t* offset) {
+  return info(h->params, index, name64, numel, offset);
+}
+int rd_buffer_info(const rd_handle* h, int index, char* name64, int64_t* numel, int64_t* offset) {
+  return info(h->buffers, index, name64, numel, offset);
+}
+
+int rd_bind(rd_handle* h, float* params, float* grads, float* bn_buffers) {
+  if (!h) return fail("rd_bind: null handle");
+  if (!params) return fail("rd_bind: null parameter arena");
+  if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)bn_buffers) & 15) return fail("rd_bind: arenas must be 16-byte aligned");
+  h->P = params; h->G = grads; h->BUF = bn_buffers;
+  return 0;
+}
+
+int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
+  if (!h) return fail("rd_reserve: null handle");
+  RD_TRY(check_shape(h, batch, tile));
+  RD_CUDA(cudaSetDevice(h->device));
+  if (h->slab && batch == h->res_batch && tile == h->res_tile && (h->res_bwd || !with_backward)) return 0;
+  const size_t need = carve(h, nullptr, batch, tile, with_backward);
+  if (need > h->slab_bytes) {
+    if (h->slab) {
+      RD_CUDA(cudaDeviceSynchronize());
+      RD_CUDA(cudaFree(h->slab));
+      h->slab = nullptr; h->slab_bytes = 0;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return fail("workspace allocation of %.1f MB failed: %s", need / 1048576.0, cudaGetErrorString(e));
+    }
+    h->slab = p; h->slab_bytes = need;
+  } else {
+    RD_CUDA(cudaDeviceSynchronize());   // re-carving a live slab: wait for in-flight work
+  }
+  carve(h, h->slab, batch, tile, with_backward);
+  const float consts[4] = {0.f, 0.01f, 1.f, 0.f};          // relu slope, LeakyReLU default slope (lib/UNet.py:30)
+  RD_CUDA(cudaMemcpy(h->consts, consts, sizeof(consts), cudaMemcpyHostToDevice));
+  h->res_batch = batch; h->res_tile = tile; h->res_bwd = with_backward;
+  h->fwd_mode = -1;
+  return 0;
+}
+
+int64_t rd_workspace_bytes(const rd_handle* h) { return h ? (int64_t)h->slab_bytes : 0; }
+
+int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int mode, void* stream) {
+  if (!h || !x || !y) return fail("rd_forward: null argument");
+  if (!h->P) return fail("rd_forward: parameters not bound (rd_bind)");
+  if (mode < RD_FWD_EVAL || mode > RD_FWD_EVAL_SAVE) return fail("rd_forward: bad mode %d", mode);
+  if (h->cfg.do_bn && !h->BUF) return fail("rd_forward: BatchNorm buffers not bound");
+  RD_CUDA(cudaSetDevice(h->device));
+  const int save = mode != RD_FWD_EVAL;
+  RD_TRY(rd_reserve(h, batch, tile, save));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int B = batch, T = tile, D = h->depth;
+  const bool train = mode == RD_FWD_TRAIN;
+  const bool stats = train && h->cfg.do_bn;
+  const int tf = h->tf32() ? 1 : 0;
+  h->fwd_mode = -1;
+  RD_TRY(pack_weights(h, save, s));
+
+  int np = 0;
+  for (int i = 0; i < D; ++i) {
+    ConvBlock& b = h->enc[i];
+    const int H = T >> i;
+    if (i == 0) {
+      const double px = (double)B * H * H;
+      ProfScope ps(h, RD_PROF_FIRST_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+      RD_TRY(launch_conv_first_fwd(x, h->P + b.w, b.z, stats ? h->partials : nullptr, &np, B, b.Cin, H, H, b.Cout, s));
+    } else {
+      RD_TRY(conv_block_forward(h, b, h->enc[i - 1].p, B, H, stats, &np, s));
+    }
+    RD_TRY(bn_act_forward(h, b, np, B, H, train, 0, tf, s));
+  }
+  {
+    ConvBlock& b = h->bott;
+    const int H = T >> D;
+    RD_TRY(conv_block_forward(h, b, h->enc[D - 1].p, B, H, stats, &np, s));
+    RD_TRY(bn_act_forward(h, b, np, B, H, train, tf, 0, s));
+  }
+  const float* cur = h->bott.a;
+  int Hc = T >> D;
+  for (int j = 0; j < D; ++j) {
+    UpConv& u = h->ups[j];
+    Gather g = gather_plain(Hc, Hc, u.C);
+    Epilogue e{};
+    e.mode = EPI_CONVT;
+    e.out = u.u;
+    e.bias = h->P + u.bias;
+    e.skip = h->enc[D - 1 - j].a;                       // additive skip, lib/UNet.py:96-101,220,224
+    e.round_tf32 = (j < D - 1) ? tf : 0;
+    {
+      const double px = (double)B * Hc * Hc;
+      ProfScope ps(h, RD_PROF_CONVT_FWD, 2.0 * 4.0 * u.C * u.C * px, 4.0 * px * u.C * (1.0 + 4.0 + 4.0), s);
+      RD_TRY(launch_gemm_rows_simt(cur, g, u.w_kn, B, 4 * u.C, e, nullptr, s));
+    }
+    Hc *= 2;
+    if (j < D - 1) {
+      ConvBlock& b = h->dec[j];
+      RD_TRY(conv_block_forward(h, b, u.u, B, Hc, stats, &np, s));
+      RD_TRY(bn_act_forward(h, b, np, B, Hc, train, tf, 0, s));
+      cur = b.a;
+    }
+  }
+  const int C0 = h->cfg.start_kernel;
+  {
+    const double px = (double)B * T * T;
+    ProfScope ps(h, RD_PROF_LAST_FWD, 2.0 * 9.0 * C0 * px, 4.0 * px * (C0 + 2.0), s);
+    RD_TRY(launch_conv_last_fwd(h->ups[D - 1].u, h->P + h->last_w, h->last_b >= 0 ? h->P + h->last_b : nullptr,
+                                h->cfg.outer_skip ? x : nullptr, h->cfg.n_input_channels * T * T, y, B, T, T, C0, s));
+  }
+  if (save) { h->fwd_batch = B; h->fwd_tile = T; h->fwd_mode = mode; }
+  return 0;
+}
+
+int rd_loss(rd_handle* h, const float* y_pred, const float* target, const uint8_t* mask, const float* mean,
+            const float* std, float* loss_out, float* dy_out, int batch, int tile, void* stream) {
+  if (!h || !y_pred || !target || !mask || !mean || !std || !loss_out) return fail("rd_loss: null argument");
+  RD_CUDA(cudaSetDevice(h->device));
+  if (!h->slab) RD_TRY(rd_reserve(h, batch, tile, 0));
+  ProfScope ps(h, RD_PROF_LOSS, 0.0, (double)batch * tile * tile * (4.0 + 4.0 + 1.0 + (dy_out ? 13.0 : 0.0)),
+               reinterpret_cast<cudaStream_t>(stream));
+  return launch_loss(y_pred, target, mask, mean, std, loss_out, dy_out, h->scratch, batch, tile * tile,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+namespace {
+
+// backward of one conv block.  g_full: gradient at the (un-pooled) block output, g_pool: gradient at the pooled
+// output; src_in: the block's input (NHWC) or, for the first encoder block, the network input x (NCHW).
+int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float* g_pool, int B, int H,
+                   const float* src_in, bool first, float* dgrad_out, cudaStream_t s) {
+  BnLayer L = bn_view(h, b);
+  Act act = act_view(h, b);
+  const int do_bn = h->cfg.do_bn;
+  int np = 0;
+  const double px = (double)B * H * H, n = px * b.Cout;
+  const double gin = (g_full ? 1.0 : 0.0) + (g_pool ? 0.25 : 0.0);
+  {
+    ProfScope ps(h, RD_PROF_BN_BWD_REDUCE, 0.0, 4.0 * n * (1.0 + gin), s);
+    RD_TRY(launch_bn_bwd_reduce(g_full, g_pool, b.z, L, act, h->partials, &np, B, H, H, s));
+    RD_TRY(launch_bn_bwd_finalize(L, h->partials, np, (long long)B * H * H, do_bn, h->fwd_mode == RD_FWD_TRAIN,
+                                  do_bn ? h->G + b.gamma : nullptr, h->G + (do_bn ? b.beta : b.bias),
+                                  b.slope >= 0 ? h->G + b.slope : nullptr, h->scratch, h->coef, s));
+  }
+  {
+    ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (2.0 + gin), s);
+    RD_TRY(launch_bn_bwd_apply(g_full, g_pool, b.z, L, act, h->coef, h->gy, B, H, H, h->tf32() && b.tc, s));
+  }
+  if (first) {
+    ProfScope ps(h, RD_PROF_FIRST_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+    RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
+  } else {
+    Gather g = gather_conv3x3(H, H, b.Cin);
+    int S = 0;
+    {
+      ProfScope ps(h, RD_PROF_CONV_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+      RD_TRY(launch_gemm_reduce_simt(src_in, g, h->gy, B, b.Cout, h->part, h->part_floats, &S, s));
+    }
+    ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), s);
+    RD_TRY(launch_unpack_conv3x3_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, s));
+  }
+  if (dgrad_out) {
+    Gather g = gather_conv3x3(H, H, b.Cout);
+    Epilogue e{};
+    e.mode = EPI_PLAIN;
+    e.out = dgrad_out;
+    ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+    RD_TRY(launch_gemm_rows_simt(h->gy, g, b.wd_kn, B, b.Cin, e, nullptr, s));
+  }
+  return 0;
+}
+
+}  // namespace
+
+int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
+  if (!h || !dy || !x) return fail("rd_backward: null argument");
+  if (!h->G) return fail("rd_backward: gradient arena not bound (rd_bind)");
+  if (h->fwd_mode != RD_FWD_TRAIN && h->fwd_mode != RD_FWD_EVAL_SAVE)
+    return fail("rd_backward: no saved forward pass (call rd_forward with RD_FWD_TRAIN or RD_FWD_EVAL_SAVE first)");
+  RD_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int B = h->fwd_batch, T = h->fwd_tile, D = h->depth;
+  const int C0 = h->cfg.start_kernel;
+
+  // last_layer (lib/UNet.py:184,227): du -> gradient at u_{D-1}, which is also the skip gradient of level 0
+  {
+    const double px = (double)B * T * T;
+    ProfScope ps(h, RD_PROF_LAST_BWD, 2.0 * 2.0 * 9.0 * C0 * px, 4.0 * px * (2.0 * C0 + 1.0), s);
+    RD_TRY(launch_conv_last_bwd(h->ups[D - 1].u, dy, h->P + h->last_w, h->g_skip[0], h->G + h->last_w,
+                                h->last_b >= 0 ? h->G + h->last_b : nullptr, h->scratch, h->scratch_floats, B, T, T, C0, s));
+  }
+  for (int j = D - 1; j >= 0; --j) {
+    UpConv& u = h->ups[j];
+    const int Hin = T >> (D - j);
+    const float* Gu = h->g_skip[D - 1 - j];                  // gradient at u_j (and at skip a_{D-1-j})
+    const float* X = j == 0 ? h->bott.a : h->dec[j - 1].a;   // input of the transposed conv
+    const double px = (double)B * Hin * Hin, cc = (double)u.C * u.C;
+    {
+      ProfScope ps(h, RD_PROF_BIAS_GRAD, 0.0, 4.0 * 4.0 * px * u.C, s);
+      RD_TRY(launch_channel_sum(Gu, (long long)B * 4 * Hin * Hin, u.C, h->G + u.bias, h->scratch, h->scratch_floats, s));
+    }
+    Gather g4 = gather_up2(Hin, Hin, u.C);
+    int S = 0;
+    {
+      ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
+      RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, s));
+    }
+    {
+      ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 4.0 * cc * (S + 1.0), s);
+      RD_TRY(launch_unpack_convt_grad(h->part, S, h->G + u.w, u.C, u.C, s));
+    }
+    Epilogue e{};
+    e.mode = EPI_PLAIN;
+    e.out = h->gh;
+    {
+      ProfScope ps(h, RD_PROF_CONVT_DGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
+      RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
+    }
+    if (j == 0) {
+      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, s));
+    } else {
+      RD_TRY(block_backward(h, h->dec[j - 1], h->gh, nullptr, B, Hin, h->ups[j - 1].u, false, h->g_skip[D - j], s));
+    }
+  }
+  for (int i = D - 1; i >= 0; --i) {
+    const int H = T >> i;
+    RD_TRY(block_backward(h, h->enc[i], h->g_skip[i], h->gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
+                          i == 0 ? nullptr : h->gp, s));
+  }
+  return 0;
+}
+
+int rd_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                 float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("rd_adam_step: null argument");
+  if (step < 1) return fail("rd_adam_step: step must be >= 1");
+  return launch_adam(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_sgd_step(float* params, const float* grads, int64_t n, float lr, float weight_decay, float grad_scale,
+                void* stream) {
+  if (!params || !grads) return fail("rd_sgd_step: null argument");
+  return launch_sgd(params, grads, n, lr, weight_decay, grad_scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_blend_accumulate(const float* tiles, const float* mean, const float* std, const int32_t* geom, int n, int tile,
+                        int stride, double* raster, int rows, int cols, void* stream) {
+  if (!tiles || !mean || !std || !geom || !raster) return fail("rd_blend_accumulate: null argument");
+  return launch_blend(tiles, mean, std, geom, n, tile, stride, raster, rows, cols, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_profile_enable(rd_handle* h, int on) {
+  if (!h) return fail("rd_profile_enable: null handle");
+  RD_CUDA(cudaSetDevice(h->device));
+  if (!on) RD_TRY(rd_profile_collect(h));
+  h->profiling = on != 0;
+  for (int i = 0; i < RD_PROF_NUM; ++i) {
+    h->prof_ms[i] = h->prof_flops[i] = h->prof_bytes[i] = 0.0;
+    h->prof_launches[i] = h->prof_calls[i] = 0;
+  }
+  return 0;
+}
+
+int rd_profile_collect(rd_handle* h) {
+  if (!h) return fail("rd_profile_collect: null handle");
+  RD_CUDA(cudaSetDevice(h->device));
+  for (auto& r : h->prof) {
+    RD_CUDA(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    RD_CUDA(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    h->prof_ms[r.cat] += ms;
+    h->prof_flops[r.cat] += r.flops;
+    h->prof_bytes[r.cat] += r.bytes;
+    h->prof_launches[r.cat] += r.launches;
+    h->prof_calls[r.cat] += 1;
+    h->event_pool.push_back(r.e0);
+    h->event_pool.push_back(r.e1);
+  }
+  h->prof.clear();
+  return 0;
+}
+
+int rd_profile_read(const rd_handle* h, int category, char* name64, double* ms, double* flops, double* bytes,
+                    int64_t* launches, int64_t* calls) {
+  if (!h || category < 0 || category >= RD_PROF_NUM) return fail("rd_profile_read: bad argument");
+  if (name64) { std::strncpy(name64, kProfNames[category], 63); name64[63] = 0; }
+  if (ms) *ms = h->prof_ms[category];
+  if (flops) *flops = h->prof_flops[category];
+  if (bytes) *bytes = h->prof_bytes[category];
+  if (launches) *launches = h->prof_launches[category];
+  if (calls) *calls = h->prof_calls[category];
+  return 0;
+}
+
+int64_t rd_launch_count(int reset) {
+  const long long v = g_launch_count;
+  if (reset) g_launch_count = 0;
+  return v;
+}
+
+const char* rd_math_mode_name(const rd_handle* h) {
+  if (!h) return "none";
+  return h->tf32() ? "tf32 (tcgen05 kind::tf32, fp32 accumulate)" : "fp32 (CUDA-core FMA)";
+}
+
+}  // extern "C"

@@ -73,23 +73,24 @@ struct BnLayer {
 // partials: [nparts][C][2] (sum, sumsq) -> mean/invstd/scale/shift (+ running stats when training)
 int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int training,
                        int do_bn, cudaStream_t s);
-// a = act(z*scale+shift)  (+ 2x2 max-pool into p when p != null).  round_tf32: store TF32-rounded values.
+// a = act(z*scale+shift)  (+ 2x2 max-pool into p when p != null).  round_*: store TF32-rounded values.
 int launch_bn_act_pool(const float* z, const float* scale, const float* shift, Act act, float* a, float* p,
-                       int B, int H, int W, int C, int round_tf32, cudaStream_t s);
-// backward pass 1:  gA = unpool(g_pool, a) + g_full ; gY = gA*act'(a) -> gy_out ; partial sums
-//   partials [nblk][C][4] = (sum gY, sum gY*z, sum gA*neg(a) (prelu), unused)
-int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* a, const float* z, Act act,
-                         float* gy_out, float* partials, int* n_partials, int B, int H, int W, int C,
-                         cudaStream_t s);
-// finalize: dgamma, dbeta (or dbias) -> grads; coefficients for pass 2
+                       int B, int H, int W, int C, int round_a, int round_p, cudaStream_t s);
+// backward pass 1:  gA = unpool(g_pool, a) + g_full ; gY = gA*act'(y) ; per-block partial sums
+//   partials [nblk][C][3] = (sum gY, sum gY*(z-mean), sum gA*min(y,0))
+int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
+                         float* partials, int* n_partials, int B, int H, int W, cudaStream_t s);
+// finalize: dgamma, dbeta (or conv dbias) -> grads, PReLU slope gradient, coefficients for pass 2 (coef: 4*C floats)
 int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int do_bn,
-                           float* dgamma, float* dbeta, float* dslope, float* coef /*[C][2]*/, cudaStream_t s);
-// pass 2 (in place on gy):  dz = scale*(gy - c1 - (z-mean)*c2)    [round_bf16 unused for now]
-int launch_bn_bwd_apply(float* gy, const float* z, const BnLayer& L, const float* coef, long long npix, int C,
-                        cudaStream_t s);
+                           int batch_stats, float* dgamma, float* dbeta, float* dslope, float* dslope_scratch, void* coef,
+                           cudaStream_t s);
+// pass 2:  dz = cs*(gY - c1 - (z-mean)*c2), gY recomputed from the same inputs as pass 1
+int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
+                        const void* coef, float* dz, int B, int H, int W, int round_out, cudaStream_t s);
 
 int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
                 float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s);
+static constexpr size_t LOSS_SCRATCH_FLOATS = 2 * 2 * 256 + 4;
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, long long step, float gscale, cudaStream_t s);
 int launch_sgd(float* p, const float* g, long long n, float lr, float wd, float gscale, cudaStream_t s);
@@ -97,12 +98,10 @@ int launch_blend(const float* tiles, const float* mean, const float* std, const 
                  int stride, double* raster, int rows, int cols, cudaStream_t s);
 int launch_fill(float* p, float v, long long n, cudaStream_t s);
 
-// weight packing ------------------------------------------------------------------------------
-// conv3x3 OIHW [Co,Ci,3,3] -> forward GEMM B matrix  Wf[(t,ci)][co]  and dgrad matrix Wd[(t,co)][ci]
-//   (dgrad tap t uses the 180-degree rotated filter).  round_tf32 rounds to nearest TF32.
-int launch_pack_conv3x3(const float* w, float* wf, float* wd, int Co, int Ci, int round_tf32, cudaStream_t s);
-// convT 2x2 [Ci,Co,2,2] -> Wm[ci][(a,b,co)] and WmT[(a,b,co)][ci]
-int launch_pack_convt(const float* w, float* wm, float* wmt, int Ci, int Co, int round_tf32, cudaStream_t s);
+// weight packing (see kernels_elementwise.cu for the layouts); null outputs are skipped
+int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, int Co, int Ci, int round_tf32,
+                        cudaStream_t s);
+int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int round_tf32, cudaStream_t s);
 // reduce split partials and un-pack to the PyTorch layouts
 //   conv: part [S][(t,ci)][co] -> dW OIHW ;  convT: part [S][(a,b,co)][ci] -> dW [ci][co][2][2]
 int launch_unpack_conv3x3_grad(const float* part, int S, float* dw, int Co, int Ci, cudaStream_t s);

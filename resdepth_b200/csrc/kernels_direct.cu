@@ -17,7 +17,7 @@ static constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
 __global__ void __launch_bounds__(256)
 conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z,
                       float* __restrict__ partials, int B, int Cin, int H, int W, int Cout,
-                      int tiles_x, int tiles_y) {
+                      int tiles_x, int tiles_y, int ntiles) {
   extern __shared__ float smem[];
   float* xs = smem;                                   // [Cin][HALO_H][HALO_W]
   float* ws = xs + Cin * HALO_H * HALO_W;             // [Cin*9][Cout]
@@ -25,69 +25,73 @@ conv_first_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, 
   const int tid = threadIdx.x;
   const int Q = Cout >> 2;
   const int PG = 256 / Q;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int h0 = ty * TH, w0 = tx * TW;
-
   for (int i = tid; i < Cin * 9 * Cout; i += 256) {   // w[co][ci][r][s] -> ws[(ci*9+r*3+s)][co]
     int co = i % Cout, k = i / Cout;
     ws[i] = w[(size_t)co * Cin * 9 + k];
   }
-  for (int i = tid; i < Cin * HALO_H * HALO_W; i += 256) {
-    int ww = i % HALO_W, hh = (i / HALO_W) % HALO_H, ci = i / (HALO_W * HALO_H);
-    int gh = h0 + hh - 1, gw = w0 + ww - 1;
-    float v = 0.f;
-    if (gh >= 0 && gh < H && gw >= 0 && gw < W) v = x[(((size_t)b * Cin + ci) * H + gh) * W + gw];
-    xs[i] = v;
-  }
-  __syncthreads();
-
   const int q = tid % Q, pg = tid / Q;
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-  if (pg < PG) {
-    for (int g = pg; g < (TH * TW) / 4; g += PG) {
-      const int lh = g / (TW / 4), lw = (g % (TW / 4)) * 4;
-      float acc[4][4];
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    const int b = t / tiles_y;
+    const int h0 = ty * TH, w0 = tx * TW;
+    __syncthreads();
+    for (int i = tid; i < Cin * HALO_H * HALO_W; i += 256) {
+      int ww = i % HALO_W, hh = (i / HALO_W) % HALO_H, ci = i / (HALO_W * HALO_H);
+      int gh = h0 + hh - 1, gw = w0 + ww - 1;
+      float v = 0.f;
+      if (gh >= 0 && gh < H && gw >= 0 && gw < W) v = x[(((size_t)b * Cin + ci) * H + gh) * W + gw];
+      xs[i] = v;
+    }
+    __syncthreads();
+    if (pg < PG) {
+      for (int g = pg; g < (TH * TW) / 4; g += PG) {
+        const int lh = g / (TW / 4), lw = (g % (TW / 4)) * 4;
+        float acc[4][4];
 #pragma unroll
-      for (int p = 0; p < 4; ++p)
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
-      for (int ci = 0; ci < Cin; ++ci) {
+          for (int c = 0; c < 4; ++c) acc[p][c] = 0.f;
+        for (int ci = 0; ci < Cin; ++ci) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          const float* row = xs + (ci * HALO_H + lh + r) * HALO_W + lw;
-          float in[6];
+          for (int r = 0; r < 3; ++r) {
+            const float* row = xs + (ci * HALO_H + lh + r) * HALO_W + lw;
+            float in[6];
 #pragma unroll
-          for (int i = 0; i < 6; ++i) in[i] = row[i];
+            for (int i = 0; i < 6; ++i) in[i] = row[i];
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const float4 wv = *reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * Cout + q * 4);
+            for (int s = 0; s < 3; ++s) {
+              const float4 wv = *reinterpret_cast<const float4*>(ws + ((ci * 3 + r) * 3 + s) * Cout + q * 4);
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              acc[p][0] = fmaf(in[p + s], wv.x, acc[p][0]);
-              acc[p][1] = fmaf(in[p + s], wv.y, acc[p][1]);
-              acc[p][2] = fmaf(in[p + s], wv.z, acc[p][2]);
-              acc[p][3] = fmaf(in[p + s], wv.w, acc[p][3]);
+              for (int p = 0; p < 4; ++p) {
+                acc[p][0] = fmaf(in[p + s], wv.x, acc[p][0]);
+                acc[p][1] = fmaf(in[p + s], wv.y, acc[p][1]);
+                acc[p][2] = fmaf(in[p + s], wv.z, acc[p][2]);
+                acc[p][3] = fmaf(in[p + s], wv.w, acc[p][3]);
+              }
+            }
+          }
+        }
+        const int gh = h0 + lh;
+        if (gh < H) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int gw = w0 + lw + p;
+            if (gw < W) {
+              *reinterpret_cast<float4*>(z + (((size_t)b * H + gh) * W + gw) * Cout + q * 4) =
+                  make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) { s1[c] += acc[p][c]; s2[c] = fmaf(acc[p][c], acc[p][c], s2[c]); }
             }
           }
         }
       }
-      const int gh = h0 + lh;
-      if (gh < H) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int gw = w0 + lw + p;
-          if (gw < W) {
-            *reinterpret_cast<float4*>(z + (((size_t)b * H + gh) * W + gw) * Cout + q * 4) =
-                make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { s1[c] += acc[p][c]; s2[c] = fmaf(acc[p][c], acc[p][c], s2[c]); }
-          }
-        }
-      }
     }
+  }
+  if (pg < PG) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       red[(pg * Cout + q * 4 + c) * 2 + 0] = s1[c];
@@ -108,12 +112,13 @@ int launch_conv_first_fwd(const float* x, const float* w, float* z, float* parti
                           int Cin, int H, int W, int Cout, cudaStream_t s) {
   if (Cout % 4 || Cout > 1024 || Cin > 8) return fail("conv_first: unsupported Cin=%d Cout=%d", Cin, Cout);
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
-  const int grid = tiles_x * tiles_y * B;
+  const int ntiles = tiles_x * tiles_y * B;
+  const int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
   const int Q = Cout / 4, PG = 256 / Q;
   size_t smem = sizeof(float) * ((size_t)Cin * HALO_H * HALO_W + (size_t)Cin * 9 * Cout + (size_t)PG * Cout * 2);
   if (smem > 48 * 1024)
     RD_CUDA(cudaFuncSetAttribute(conv_first_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  conv_first_fwd_kernel<<<grid, 256, smem, s>>>(x, w, z, partials, B, Cin, H, W, Cout, tiles_x, tiles_y);
+  conv_first_fwd_kernel<<<grid, 256, smem, s>>>(x, w, z, partials, B, Cin, H, W, Cout, tiles_x, tiles_y, ntiles);
   RD_LAUNCHED();
   if (n_partials) *n_partials = grid;
   return 0;

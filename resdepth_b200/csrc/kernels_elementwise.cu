@@ -1,0 +1,756 @@
+// Memory-bound kernels of the ResDepth hot path (NHWC fp32, 128-bit accesses):
+//   * BatchNorm statistics finalize + running-stat update       (nn.BatchNorm2d, lib/UNet.py:45,66,86)
+//   * fused BN-apply + activation (+ 2x2 max-pool dual write)   (lib/UNet.py:27-33,161,167)
+//   * block backward: un-pool + skip-grad add + act' + BN backward (two passes)
+//   * masked denormalised L1 loss + gradient seed               (lib/Trainer.py:87-100,179)
+//   * Adam / SGD over a flat arena                              (lib/utils.py:329-334, lib/Trainer.py:218)
+//   * linear-blend accumulation                                 (lib/evaluation.py:484-567)
+//   * weight packing / gradient un-packing for the GEMM-shaped layers
+#include "common.cuh"
+#include "../../include/resdepth_b200.h"
+
+namespace rd {
+
+static constexpr int EW_THREADS = 256;
+static constexpr float BN_EPS = 1e-5f;
+static constexpr float BN_MOMENTUM = 0.1f;
+
+__device__ __forceinline__ float tf32_rn(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) {
+  return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+}
+__device__ __forceinline__ float act1(float y, float slope) { return y > 0.f ? y : y * slope; }
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+static int ew_grid(long long work_items) {
+  long long g = (work_items + EW_THREADS - 1) / EW_THREADS;
+  const long long cap = 148LL * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ----------------------------------------------------------------------------------------------
+// BN finalize: partials [nparts][C][2] (sum, sumsq) -> mean / invstd / scale / shift
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, int training, int do_bn,
+                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ conv_bias, float* __restrict__ running_mean,
+                   float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                   float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double red[8][32][2];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s1 = 0.0, s2 = 0.0;
+  if (do_bn && training && c < C) {
+    for (int p = pl; p < nparts; p += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2);
+      s1 += (double)v.x;
+      s2 += (double)v.y;
+    }
+  }
+  red[pl][cl][0] = s1;
+  red[pl][cl][1] = s2;
+  __syncthreads();
+  if (pl != 0 || c >= C) return;
+  if (!do_bn) {
+    scale[c] = 1.f;
+    shift[c] = conv_bias ? conv_bias[c] : 0.f;
+    return;
+  }
+  float mean, invstd;
+  if (training) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s1 += red[i][cl][0]; s2 += red[i][cl][1]; }
+    const double m = s1 / count;
+    double var = s2 / count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)BN_EPS));
+    const double unbiased = count > 1.0 ? var * (count / (count - 1.0)) : var;
+    running_mean[c] = (1.f - BN_MOMENTUM) * running_mean[c] + BN_MOMENTUM * mean;
+    running_var[c] = (1.f - BN_MOMENTUM) * running_var[c] + BN_MOMENTUM * (float)unbiased;
+  } else {
+    mean = running_mean[c];
+    invstd = 1.f / sqrtf(running_var[c] + BN_EPS);
+  }
+  mean_out[c] = mean;
+  invstd_out[c] = invstd;
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+}
+
+int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int training,
+                       int do_bn, cudaStream_t s) {
+  bn_finalize_kernel<<<cdiv(L.C, 32), 256, 0, s>>>(partials, nparts, L.C, (double)count, training, do_bn, L.gamma,
+                                                   L.beta, L.conv_bias, L.running_mean, L.running_var, L.mean,
+                                                   L.invstd, L.scale, L.shift);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// a = act(z*scale + shift), optional 2x2 max-pool (first-max-wins is irrelevant in the forward)
+// ----------------------------------------------------------------------------------------------
+template <bool POOL>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_act_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ slope_p, float* __restrict__ a, float* __restrict__ p, int B, int H,
+                   int W, int C, int round_a, int round_p) {
+  const int Q = C >> 2;
+  const float slope = *slope_p;
+  if (POOL) {
+    const int Hp = H >> 1, Wp = W >> 1;
+    const long long total = (long long)B * Hp * Wp * Q;
+    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
+         i += (long long)gridDim.x * EW_THREADS) {
+      const int q = (int)(i % Q);
+      long long w_ = i / Q;
+      const int wp = (int)(w_ % Wp); w_ /= Wp;
+      const int hp = (int)(w_ % Hp);
+      const int b = (int)(w_ / Hp);
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + q);
+      const size_t base = (((size_t)b * H + 2 * hp) * W + 2 * wp) * C + q * 4;
+      float4 m;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const size_t o = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+        const float4 v = ld4(z + o);
+        float4 r;
+        r.x = act1(fmaf(v.x, sc.x, sh.x), slope);
+        r.y = act1(fmaf(v.y, sc.y, sh.y), slope);
+        r.z = act1(fmaf(v.z, sc.z, sh.z), slope);
+        r.w = act1(fmaf(v.w, sc.w, sh.w), slope);
+        st4(a + o, round_a ? tf32_rn4(r) : r);
+        if (k == 0) m = r;
+        else { m.x = fmaxf(m.x, r.x); m.y = fmaxf(m.y, r.y); m.z = fmaxf(m.z, r.z); m.w = fmaxf(m.w, r.w); }
+      }
+      st4(p + (((size_t)b * Hp + hp) * Wp + wp) * C + q * 4, round_p ? tf32_rn4(m) : m);
+    }
+  } else {
+    const long long total = (long long)B * H * W * Q;
+    for (long long i = blockIdx.x * (long long)EW_THREADS + threadIdx.x; i < total;
+         i += (long long)gridDim.x * EW_THREADS) {
+      const int q = (int)(i % Q);
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + q);
+      const float4 v = ld4(z + i * 4);
+      float4 r;
+      r.x = act1(fmaf(v.x, sc.x, sh.x), slope);
+      r.y = act1(fmaf(v.y, sc.y, sh.y), slope);
+      r.z = act1(fmaf(v.z, sc.z, sh.z), slope);
+      r.w = act1(fmaf(v.w, sc.w, sh.w), slope);
+      st4(a + i * 4, round_a ? tf32_rn4(r) : r);
+    }
+  }
+}
+
+int launch_bn_act_pool(const float* z, const float* scale, const float* shift, Act act, float* a, float* p, int B,
+                       int H, int W, int C, int round_a, int round_p, cudaStream_t s) {
+  if (C % 4) return fail("bn_act_pool: C=%d not a multiple of 4", C);
+  if (p) {
+    if ((H | W) & 1) return fail("bn_act_pool: odd size %dx%d cannot be pooled", H, W);
+    const long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
+    bn_act_pool_kernel<true><<<ew_grid(total), EW_THREADS, 0, s>>>(z, scale, shift, act.slope, a, p, B, H, W, C,
+                                                                    round_a, round_p);
+  } else {
+    const long long total = (long long)B * H * W * (C / 4);
+    bn_act_pool_kernel<false><<<ew_grid(total), EW_THREADS, 0, s>>>(z, scale, shift, act.slope, a, p, B, H, W, C,
+                                                                     round_a, round_p);
+  }
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Block backward.  With y = z*scale+shift, a = act(y):
+//   gA = unpool_first_max(g_pool, a) + g_full ;  gY = gA * act'(y)
+//   pass 1 (reduce): per-channel  S1 = sum gY,  S2 = sum gY*(z-mean),  S3 = sum gA*min(y,0)   (PReLU slope grad)
+//   pass 2 (apply) : dz = cs * (gY - c1 - (z-mean)*c2)
+// Threads keep a fixed channel quad so the sums stay in registers; one thread handles one 2x2 window (pooled
+// layers) or one pixel (others) per iteration.
+// ----------------------------------------------------------------------------------------------
+struct BwdCoef {            // per channel, built by bn_bwd_finalize
+  float mean, cs, c1, c2;
+};
+
+template <bool POOL, bool APPLY>
+__global__ void __launch_bounds__(EW_THREADS)
+bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool, const float* __restrict__ z,
+              const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ slope_p,
+              const float* __restrict__ mean, const BwdCoef* __restrict__ coef, float* __restrict__ dz,
+              float* __restrict__ partials, int B, int H, int W, int C, int round_out) {
+  extern __shared__ float red[];                       // reduce: [PL][C][3]
+  const int Q = C >> 2;
+  const int PL = EW_THREADS / Q;                       // pixel lanes per block
+  const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
+  const float slope = *slope_p;
+  float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
+  if (pl < PL) {
+    const float4 sc4 = ld4(scale + q * 4), sh4 = ld4(shift + q * 4);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+    float mu[4], cs[4], c1[4], c2[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (APPLY) {
+        const BwdCoef k = coef[q * 4 + c];
+        mu[c] = k.mean; cs[c] = k.cs; c1[c] = k.c1; c2[c] = k.c2;
+      } else {
+        mu[c] = mean[q * 4 + c]; cs[c] = c1[c] = c2[c] = 0.f;
+      }
+    }
+    const int Hw = POOL ? (H >> 1) : H, Ww = POOL ? (W >> 1) : W;
+    const long long nwin = (long long)B * Hw * Ww;
+    for (long long wi = (long long)blockIdx.x * PL + pl; wi < nwin; wi += (long long)gridDim.x * PL) {
+      if (POOL) {
+        const int wp = (int)(wi % Ww);
+        const int hp = (int)((wi / Ww) % Hw);
+        const int b = (int)(wi / ((long long)Ww * Hw));
+        const size_t base = (((size_t)b * H + 2 * hp) * W + 2 * wp) * C + q * 4;
+        float zz[4][4], yy[4][4], gf[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const size_t o = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+          const float4 v = ld4(z + o);
+          zz[k][0] = v.x; zz[k][1] = v.y; zz[k][2] = v.z; zz[k][3] = v.w;
+          if (g_full) {
+            const float4 g = ld4(g_full + o);
+            gf[k][0] = g.x; gf[k][1] = g.y; gf[k][2] = g.z; gf[k][3] = g.w;
+          } else {
+            gf[k][0] = gf[k][1] = gf[k][2] = gf[k][3] = 0.f;
+          }
+        }
+        const float4 gp4 = ld4(g_pool + (size_t)wi * C + q * 4);
+        const float gp[4] = {gp4.x, gp4.y, gp4.z, gp4.w};
+        float out[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int arg = 0;
+          float best = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            yy[k][c] = fmaf(zz[k][c], sc[c], sh[c]);
+            const float av = act1(yy[k][c], slope);
+            if (k == 0 || av > best) { best = av; arg = k; }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float gA = gf[k][c] + (k == arg ? gp[c] : 0.f);
+            const float y = yy[k][c];
+            const float gY = y > 0.f ? gA : gA * slope;
+            const float zc = zz[k][c] - mu[c];
+            if (APPLY) {
+              out[k][c] = cs[c] * (gY - c1[c] - zc * c2[c]);
+            } else {
+              s1[c] += gY;
+              s2[c] = fmaf(gY, zc, s2[c]);
+              s3[c] += y > 0.f ? 0.f : gA * y;
+            }
+          }
+        }
+        if (APPLY) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const size_t o = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
+            float4 r = make_float4(out[k][0], out[k][1], out[k][2], out[k][3]);
+            st4(dz + o, round_out ? tf32_rn4(r) : r);
+          }
+        }
+      } else {
+        const size_t o = (size_t)wi * C + q * 4;
+        const float4 v = ld4(z + o), g = ld4(g_full + o);
+        const float zz[4] = {v.x, v.y, v.z, v.w}, gA[4] = {g.x, g.y, g.z, g.w};
+        float out[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float y = fmaf(zz[c], sc[c], sh[c]);
+          const float gY = y > 0.f ? gA[c] : gA[c] * slope;
+          const float zc = zz[c] - mu[c];
+          if (APPLY) {
+            out[c] = cs[c] * (gY - c1[c] - zc * c2[c]);
+          } else {
+            s1[c] += gY;
+            s2[c] = fmaf(gY, zc, s2[c]);
+            s3[c] += y > 0.f ? 0.f : gA[c] * y;
+          }
+        }
+        if (APPLY) {
+          float4 r = make_float4(out[0], out[1], out[2], out[3]);
+          st4(dz + o, round_out ? tf32_rn4(r) : r);
+        }
+      }
+    }
+  }
+  if (!APPLY) {
+    if (pl < PL) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float* r = red + ((size_t)pl * C + q * 4 + c) * 3;
+        r[0] = s1[c]; r[1] = s2[c]; r[2] = s3[c];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 3; i += EW_THREADS) {
+      float acc = 0.f;
+      for (int p = 0; p < PL; ++p) acc += red[(size_t)p * C * 3 + i];
+      partials[(size_t)blockIdx.x * C * 3 + i] = acc;
+    }
+  }
+}
+
+static int bwd_grid(long long nwin, int PL) {
+  long long g = (nwin + PL - 1) / PL;
+  if (g > 148 * 4) g = 148 * 4;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
+                         float* partials, int* n_partials, int B, int H, int W, cudaStream_t s) {
+  const int C = L.C, Q = C / 4;
+  if (C % 4 || Q > EW_THREADS) return fail("bn_bwd: unsupported C=%d", C);
+  const int PL = EW_THREADS / Q;
+  const size_t smem = (size_t)PL * C * 3 * sizeof(float);
+  int grid;
+  if (g_pool) {
+    grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL);
+    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    bn_bwd_kernel<true, false><<<grid, EW_THREADS, smem, s>>>(g_full, g_pool, z, L.scale, L.shift, act.slope, L.mean,
+                                                              nullptr, nullptr, partials, B, H, W, C, 0);
+  } else {
+    if (!g_full) return fail("bn_bwd: no incoming gradient");
+    grid = bwd_grid((long long)B * H * W, PL);
+    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    bn_bwd_kernel<false, false><<<grid, EW_THREADS, smem, s>>>(g_full, nullptr, z, L.scale, L.shift, act.slope,
+                                                               L.mean, nullptr, nullptr, partials, B, H, W, C, 0);
+  }
+  RD_LAUNCHED();
+  *n_partials = grid;
+  return 0;
+}
+
+// partials [nparts][C][3] -> dgamma/dbeta (or conv dbias), PReLU slope grad partial, pass-2 coefficients
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, int do_bn,
+                       int batch_stats, const float* __restrict__ gamma, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                       float* __restrict__ dslope_part, BwdCoef* __restrict__ coef) {
+  __shared__ double red[8][32][3];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (c < C) {
+    for (int p = pl; p < nparts; p += 8) {
+      const float* v = partials + ((size_t)p * C + c) * 3;
+      s1 += (double)v[0]; s2 += (double)v[1]; s3 += (double)v[2];
+    }
+  }
+  red[pl][cl][0] = s1; red[pl][cl][1] = s2; red[pl][cl][2] = s3;
+  __syncthreads();
+  if (pl != 0) return;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) { s1 += red[i][cl][0]; s2 += red[i][cl][1]; s3 += red[i][cl][2]; }
+  if (c < C) {
+    BwdCoef k;
+    if (do_bn) {
+      const double is = (double)invstd[c];
+      const double dg = s2 * is;                     // sum gY * xhat
+      dgamma[c] = (float)dg;
+      dbeta[c] = (float)s1;
+      k.mean = mean[c];
+      k.cs = gamma[c] * invstd[c];
+      k.c1 = (float)(s1 / count);
+      k.c2 = (float)(is * is * s2 / count);          // xhat*dgamma/N = (z-mean)*invstd^2*S2/N
+      if (!batch_stats) k.c1 = k.c2 = 0.f;           // eval-mode BN: statistics are constants
+    } else {
+      dbeta[c] = (float)s1;                          // gradient of the conv bias
+      k.mean = 0.f; k.cs = 1.f; k.c1 = 0.f; k.c2 = 0.f;
+    }
+    coef[c] = k;
+  }
+  // slope gradient: sum over channels of S3 (one value per block; reduced by the caller-side kernel below)
+  if (dslope_part) {
+    double v = c < C ? s3 : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (cl == 0) dslope_part[blockIdx.x] = (float)v;
+  }
+}
+
+__global__ void sum_small_kernel(const float* __restrict__ in, int n, float* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0;
+    for (int i = 0; i < n; ++i) a += (double)in[i];
+    out[0] = (float)a;
+  }
+}
+
+int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int do_bn,
+                           int batch_stats, float* dgamma, float* dbeta, float* dslope, float* dslope_scratch, void* coef,
+                           cudaStream_t s) {
+  const int nb = cdiv(L.C, 32);
+  bn_bwd_finalize_kernel<<<nb, 256, 0, s>>>(partials, nparts, L.C, (double)count, do_bn, batch_stats, L.gamma, L.mean,
+                                            L.invstd, dgamma, dbeta, dslope ? dslope_scratch : nullptr,
+                                            reinterpret_cast<BwdCoef*>(coef));
+  RD_LAUNCHED();
+  if (dslope) {
+    sum_small_kernel<<<1, 32, 0, s>>>(dslope_scratch, nb, dslope);
+    RD_LAUNCHED();
+  }
+  return 0;
+}
+
+int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
+                        const void* coef, float* dz, int B, int H, int W, int round_out, cudaStream_t s) {
+  const int C = L.C, Q = C / 4;
+  const int PL = EW_THREADS / Q;
+  if (g_pool) {
+    const int grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL) * 2;
+    bn_bwd_kernel<true, true><<<grid, EW_THREADS, 0, s>>>(g_full, g_pool, z, L.scale, L.shift, act.slope, L.mean,
+                                                          reinterpret_cast<const BwdCoef*>(coef), dz, nullptr, B, H,
+                                                          W, C, round_out);
+  } else {
+    const int grid = bwd_grid((long long)B * H * W, PL) * 2;
+    bn_bwd_kernel<false, true><<<grid, EW_THREADS, 0, s>>>(g_full, nullptr, z, L.scale, L.shift, act.slope, L.mean,
+                                                           reinterpret_cast<const BwdCoef*>(coef), dz, nullptr, B, H,
+                                                           W, C, round_out);
+  }
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Loss (lib/Trainer.py:87-100 with lib/data_normalization.py:29-38 and L1Loss(mean)):
+//   yp = y_pred*std_i + mean_i ; yt = y*std_i + mean_i   (separate fp32 multiply and add, as torch does)
+//   loss = mean(|yp - yt| over ALL pixels, masked ones zeroed) * numel / sum(mask)
+//   d loss / d y_pred = sign(yp - yt) * mask * std_i / sum(mask)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+loss_partial_kernel(const float* __restrict__ y_pred, const float* __restrict__ target,
+                    const uint8_t* __restrict__ mask, const float* __restrict__ mean, const float* __restrict__ std,
+                    double* __restrict__ part, int B, int HW) {
+  __shared__ double r1[256], r2[256];
+  double a = 0.0, m = 0.0;
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int b = (int)(i / HW);
+    if (mask[i]) {
+      const float sd = std[b], mu = mean[b];
+      const float yp = __fadd_rn(__fmul_rn(y_pred[i], sd), mu);
+      const float yt = __fadd_rn(__fmul_rn(target[i], sd), mu);
+      a += (double)fabsf(__fsub_rn(yp, yt));
+      m += 1.0;
+    }
+  }
+  r1[threadIdx.x] = a; r2[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { part[blockIdx.x * 2] = r1[0]; part[blockIdx.x * 2 + 1] = r2[0]; }
+}
+
+__global__ void loss_finalize_kernel(const double* __restrict__ part, int nparts, float* __restrict__ loss_out,
+                                     float* __restrict__ inv_count) {
+  if (threadIdx.x != 0) return;
+  double a = 0.0, m = 0.0;
+  for (int i = 0; i < nparts; ++i) { a += part[i * 2]; m += part[i * 2 + 1]; }
+  loss_out[0] = (float)(a / m);
+  inv_count[0] = (float)(1.0 / m);
+}
+
+__global__ void __launch_bounds__(256)
+loss_grad_kernel(const float* __restrict__ y_pred, const float* __restrict__ target, const uint8_t* __restrict__ mask,
+                 const float* __restrict__ mean, const float* __restrict__ std, const float* __restrict__ inv_count,
+                 float* __restrict__ dy, int B, int HW) {
+  const float ic = inv_count[0];
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int b = (int)(i / HW);
+    float g = 0.f;
+    if (mask[i]) {
+      const float sd = std[b], mu = mean[b];
+      const float d = __fsub_rn(__fadd_rn(__fmul_rn(y_pred[i], sd), mu), __fadd_rn(__fmul_rn(target[i], sd), mu));
+      g = d > 0.f ? sd * ic : (d < 0.f ? -sd * ic : 0.f);
+    }
+    dy[i] = g;
+  }
+}
+
+int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
+                float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s) {
+  // scratch: >= 2*LOSS_BLOCKS doubles + 2 floats
+  const int nb = 256;
+  double* part = reinterpret_cast<double*>(scratch);
+  float* inv_count = scratch + 2 * 2 * nb;
+  loss_partial_kernel<<<nb, 256, 0, s>>>(y_pred, target, mask, mean, std, part, B, HW);
+  RD_LAUNCHED();
+  loss_finalize_kernel<<<1, 32, 0, s>>>(part, nb, loss_out, inv_count);
+  RD_LAUNCHED();
+  if (dy_out) {
+    loss_grad_kernel<<<ew_grid((long long)B * HW), 256, 0, s>>>(y_pred, target, mask, mean, std, inv_count, dy_out, B,
+                                                                HW);
+    RD_LAUNCHED();
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Optimizers over a flat arena (torch.optim.Adam / SGD with coupled L2 decay, lib/utils.py:329-334)
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float b1, float b2, float eps, float wd, float step_size, float inv_bc2_sqrt, float gscale) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += gridDim.x * 256LL) {
+    float4 pp = ld4(p + i * 4), gg = ld4(g + i * 4), mm = ld4(m + i * 4), vv = ld4(v + i * 4);
+    float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gr = fmaf(wd, P[k], G[k] * gscale);
+      M[k] = M[k] + (1.f - b1) * (gr - M[k]);
+      V[k] = b2 * V[k] + (1.f - b2) * gr * gr;
+      const float denom = sqrtf(V[k]) * inv_bc2_sqrt + eps;
+      P[k] = P[k] - step_size * (M[k] / denom);
+    }
+    st4(p + i * 4, pp); st4(m + i * 4, mm); st4(v + i * 4, vv);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    const float gr = fmaf(wd, p[i], g[i] * gscale);
+    const float mk = m[i] + (1.f - b1) * (gr - m[i]);
+    const float vk = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mk; v[i] = vk;
+    p[i] = p[i] - step_size * (mk / (sqrtf(vk) * inv_bc2_sqrt + eps));
+  }
+}
+
+int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                float wd, long long step, float gscale, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) return fail("adam: arenas must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)b1, (double)step);
+  const double bc2 = 1.0 - pow((double)b2, (double)step);
+  adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, s>>>(p, g, m, v, n, b1, b2, eps, wd, (float)((double)lr / bc1),
+                                                 (float)(1.0 / sqrt(bc2)), gscale);
+  RD_LAUNCHED();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, float lr, float wd, float gscale) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL)
+    p[i] = p[i] - lr * fmaf(wd, p[i], g[i] * gscale);
+}
+
+int launch_sgd(float* p, const float* g, long long n, float lr, float wd, float gscale, cudaStream_t s) {
+  if (n <= 0) return 0;
+  sgd_kernel<<<ew_grid(n), 256, 0, s>>>(p, g, n, lr, wd, gscale);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Linear blending (lib/evaluation.py:484-567, denormalize_numpy lib/data_normalization.py:41-53)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ramp_weight(int c, int lo_edge, int hi_edge, int T, int overlap, double step) {
+  // lo_edge = ulx (or uly), hi_edge = lrx (or lry); follows _get_blend_weights for one axis
+  double w = 1.0;
+  if (lo_edge > 0) {
+    if (c < lo_edge - overlap) return 0.0;
+    if (c < lo_edge) {
+      const int k = c - (lo_edge - overlap);
+      w *= (k == overlap - 1) ? 1.0 : (double)k * step;
+    }
+  }
+  if (hi_edge < T - 1 && c > hi_edge) {
+    const int k = overlap - 1 - (c - (hi_edge + 1));
+    if (k >= 0 && k < overlap) w *= (k == overlap - 1) ? 1.0 : (double)k * step;
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(256)
+blend_kernel(const float* __restrict__ tiles, const float* __restrict__ mean, const float* __restrict__ std,
+             const int32_t* __restrict__ geom, int T, int stride, double* __restrict__ raster, int rows, int cols) {
+  const int t = blockIdx.y;
+  const int y0 = geom[t * 6 + 0], x0 = geom[t * 6 + 1];
+  const int uly = geom[t * 6 + 2], ulx = geom[t * 6 + 3], lry = geom[t * 6 + 4], lrx = geom[t * 6 + 5];
+  const int overlap = T - stride;
+  const double step = overlap > 1 ? 1.0 / (double)(overlap - 1) : 0.0;
+  const float sd = std[t], mu = mean[t];
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < T * T; i += gridDim.x * 256) {
+    const int r = i / T, c = i % T;
+    const int gy = y0 + r, gx = x0 + c;
+    if (gy < 0 || gy >= rows || gx < 0 || gx >= cols) continue;
+    const double w = ramp_weight(c, ulx, lrx, T, overlap, step) * ramp_weight(r, uly, lry, T, overlap, step);
+    const float den = __fadd_rn(__fmul_rn(tiles[(size_t)t * T * T + i], sd), mu);
+    atomicAdd(raster + (size_t)gy * cols + gx, (double)den * w);
+  }
+}
+
+int launch_blend(const float* tiles, const float* mean, const float* std, const int32_t* geom, int n, int T,
+                 int stride, double* raster, int rows, int cols, cudaStream_t s) {
+  if (n <= 0) return 0;
+  if (stride <= 0 || stride > T) return fail("blend: bad stride %d for tile %d", stride, T);
+  dim3 grid(cdiv((long long)T * T, 256 * 4), n);
+  blend_kernel<<<grid, 256, 0, s>>>(tiles, mean, std, geom, T, stride, raster, rows, cols);
+  RD_LAUNCHED();
+  return 0;
+}
+
+__global__ void fill_kernel(float* p, float v, long long n) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) p[i] = v;
+}
+int launch_fill(float* p, float v, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  fill_kernel<<<ew_grid(n), 256, 0, s>>>(p, v, n);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Weight packing (every forward in training: the optimizer rewrites the weights each step)
+//   conv3x3 OIHW [Co,Ci,3,3]:  kn[(t,ci)][co]  = W[co,ci,t]         (forward, K rows x N)
+//                              nk[co][(t,ci)]  = W[co,ci,t]         (forward, N rows x K: tcgen05 K-major B)
+//                              dkn[(t,co)][ci] = W[co,ci,8-t]       (dgrad: taps rotated by 180 degrees)
+//                              dnk[ci][(t,co)] = W[co,ci,8-t]
+//   convT [Ci,Co,2,2]:         kn[ci][(ab,co)] = W[ci,co,ab]        (forward)     nk[(ab,co)][ci] (its transpose)
+//     the transpose is also the K x N matrix of the dgrad GEMM (K = (ab,co), N = ci), and kn its N x K form.
+// ----------------------------------------------------------------------------------------------
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, float* __restrict__ kn, float* __restrict__ nk,
+                                    float* __restrict__ dkn, float* __restrict__ dnk, int Co, int Ci, int rnd) {
+  const long long total = (long long)Co * Ci * 9;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int t = (int)(i % 9);
+    const int ci = (int)((i / 9) % Ci);
+    const int co = (int)(i / (9LL * Ci));
+    float v = w[i];
+    if (rnd) v = tf32_rn(v);
+    if (kn) kn[((size_t)t * Ci + ci) * Co + co] = v;
+    if (nk) nk[(size_t)co * 9 * Ci + (size_t)t * Ci + ci] = v;
+    const int tr = 8 - t;
+    if (dkn) dkn[((size_t)tr * Co + co) * Ci + ci] = v;
+    if (dnk) dnk[(size_t)ci * 9 * Co + (size_t)tr * Co + co] = v;
+  }
+}
+int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, int Co, int Ci, int rnd,
+                        cudaStream_t s) {
+  pack_conv3x3_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(w, kn, nk, dkn, dnk, Co, Ci, rnd);
+  RD_LAUNCHED();
+  return 0;
+}
+
+__global__ void pack_convt_kernel(const float* __restrict__ w, float* __restrict__ kn, float* __restrict__ nk, int Ci,
+                                  int Co, int rnd) {
+  const long long total = (long long)Ci * Co * 4;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int ab = (int)(i % 4);
+    const int co = (int)((i / 4) % Co);
+    const int ci = (int)(i / (4LL * Co));
+    float v = w[i];
+    if (rnd) v = tf32_rn(v);
+    if (kn) kn[(size_t)ci * 4 * Co + (size_t)ab * Co + co] = v;
+    if (nk) nk[((size_t)ab * Co + co) * Ci + ci] = v;
+  }
+}
+int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int rnd, cudaStream_t s) {
+  pack_convt_kernel<<<ew_grid((long long)Ci * Co * 4), 256, 0, s>>>(w, kn, nk, Ci, Co, rnd);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// gradient un-packing: part [S][(t,ci)][co] summed over S -> dW OIHW
+__global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co,
+                                           int Ci) {
+  const long long total = (long long)Co * Ci * 9;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    // i indexes the packed layout (coalesced reads); scatter to OIHW
+    const int co = (int)(i % Co);
+    const int ci = (int)((i / Co) % Ci);
+    const int t = (int)(i / ((long long)Co * Ci));
+    float a = 0.f;
+    for (int sp = 0; sp < S; ++sp) a += part[(size_t)sp * total + i];
+    dw[((size_t)co * Ci + ci) * 9 + t] = a;
+  }
+}
+int launch_unpack_conv3x3_grad(const float* part, int S, float* dw, int Co, int Ci, cudaStream_t s) {
+  unpack_conv3x3_grad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(part, S, dw, Co, Ci);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// part [S][(ab,co)][ci] summed over S -> dW [ci][co][2][2]
+__global__ void unpack_convt_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Ci,
+                                         int Co) {
+  const long long total = (long long)Ci * Co * 4;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int ci = (int)(i % Ci);
+    const int co = (int)((i / Ci) % Co);
+    const int ab = (int)(i / ((long long)Ci * Co));
+    float a = 0.f;
+    for (int sp = 0; sp < S; ++sp) a += part[(size_t)sp * total + i];
+    dw[((size_t)ci * Co + co) * 4 + ab] = a;
+  }
+}
+int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co, cudaStream_t s) {
+  unpack_convt_grad_kernel<<<ew_grid((long long)Ci * Co * 4), 256, 0, s>>>(part, S, dw, Ci, Co);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// out[c] = sum over pixels of g[p][c]
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const float* __restrict__ g, long long npix, int C, float* __restrict__ part) {
+  extern __shared__ float red[];                        // [PL][C]
+  const int Q = C >> 2, PL = 256 / Q;
+  const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
+  float4 a = make_float4(0, 0, 0, 0);
+  if (pl < PL) {
+    for (long long p = (long long)blockIdx.x * PL + pl; p < npix; p += (long long)gridDim.x * PL) {
+      const float4 v = ld4(g + (size_t)p * C + q * 4);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    st4(red + (size_t)pl * C + q * 4, a);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) {
+    float acc = 0.f;
+    for (int p = 0; p < PL; ++p) acc += red[(size_t)p * C + i];
+    part[(size_t)blockIdx.x * C + i] = acc;
+  }
+}
+__global__ void channel_sum_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0;
+  for (int p = 0; p < nparts; ++p) a += (double)part[(size_t)p * C + c];
+  out[c] = (float)a;
+}
+int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,
+                       cudaStream_t s) {
+  const int Q = C / 4;
+  if (C % 4 || Q > 256) return fail("channel_sum: unsupported C=%d", C);
+  const int PL = 256 / Q;
+  int grid = bwd_grid(npix, PL);
+  while ((size_t)grid * C > scratch_floats && grid > 1) grid /= 2;
+  if ((size_t)grid * C > scratch_floats) return fail("channel_sum: scratch too small");
+  channel_sum_kernel<<<grid, 256, (size_t)PL * C * sizeof(float), s>>>(g, npix, C, scratch);
+  RD_LAUNCHED();
+  channel_sum_finish_kernel<<<cdiv(C, 128), 128, 0, s>>>(scratch, grid, C, out);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// NCHW [B,1,H,W] BatchNorm on channel 0 of the input for outer_skip_BN is handled by the host wrapper (1 channel).
+
+}  // namespace rd

@@ -1,0 +1,366 @@
+"""GPU parity tests (run with ``-m gpu`` on the B200 box): the CUDA path, called through the C ABI, against
+(a) the committed golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances.  fp32 math mode (CUDA-core FMA): y within 1e-4 absolute of the reference output (fp32 summation
+order only).  TF32 math mode (tcgen05 kind::tf32): the bar of BASELINE.json -- relative L2 error of the height
+residual r = y - x0 at most 1e-3, identical argmax|r| per tile, height MAE within 1e-3 m at sigma = 3.5 m.
+"""
+import copy
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_oracle as O
+from tests.cases import CASES, NATIVE_CASES, batch_of, load_golden, spec_of
+
+pytestmark = pytest.mark.gpu
+
+DEV = 'cuda:0'
+
+
+def _model(kwargs):
+    from resdepth_b200.lib.UNet import UNet
+    torch.manual_seed(0)
+    return UNet(**kwargs)
+
+
+def _cuda_batch(batch):
+    return {k: v.to(DEV) for k, v in batch.items()}
+
+
+def _train_step(model, batch, opt=None):
+    """Forward(train) + fused loss + backward through the C ABI; returns (y, loss, grads by name)."""
+    from resdepth_b200 import _native
+    b = _cuda_batch(batch)
+    model.train()
+    with torch.no_grad():
+        y = model._forward_native(b['input'], _native.FWD_TRAIN)
+        h = model.native_handle(torch.device(DEV))
+        loss = torch.empty(1, device=DEV)
+        dy = torch.empty_like(y)
+        h.loss(y.data_ptr(), b['target'].data_ptr(), b['loss_mask'].view(torch.uint8).data_ptr(),
+               b['dsm_mean'].data_ptr(), b['dsm_std'].data_ptr(), loss.data_ptr(), dy.data_ptr(),
+               y.shape[0], y.shape[2], torch.cuda.current_stream().cuda_stream)
+        grads = model._backward_native(b['input'], dy, detach_copy=True)
+    named = {n: g for (n, _), g in zip(model.named_parameters(), grads)}
+    if opt is not None:
+        for p, g in zip(model.parameters(), grads):
+            p.grad = g
+        opt.step()
+    return y, float(loss.item()), named, dy
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+@pytest.fixture(params=['fp32', 'tf32'])
+def math_mode(request, monkeypatch):
+    monkeypatch.setenv('RESDEPTH_MATH', request.param)
+    return request.param
+
+
+@pytest.mark.parametrize('name', NATIVE_CASES)
+def test_train_step_and_eval_against_reference_golden(name, math_mode):
+    from resdepth_b200.lib.optim import Adam
+    kwargs, B, T = CASES[name]
+    g = load_golden(name)
+    model = _model(kwargs).to(DEV)
+    batch = batch_of(name)
+    opt = Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
+    y, loss, grads, _ = _train_step(model, batch, opt)
+    y_ref = torch.from_numpy(g['y_train'])
+    x0 = batch['input'][:, :1]
+    y_cpu = y.cpu()
+    if math_mode == 'fp32':
+        np.testing.assert_allclose(y_cpu.numpy(), g['y_train'], rtol=0, atol=1e-4)
+        assert abs(loss - float(g['loss_train'])) < 1e-5 * abs(float(g['loss_train']))
+        gtol = 5e-3
+    else:
+        if kwargs.get('outer_skip', True):
+            rel, same, mae = O.residual_metrics(y_cpu, y_ref, x0)
+            assert rel <= 1e-3, rel
+            assert same
+            assert mae <= 1e-3, mae
+        else:
+            assert _rel(y_cpu, y_ref) <= 1e-3
+        assert abs(loss - float(g['loss_train'])) < 2e-3 * abs(float(g['loss_train']))
+        gtol = 3e-2
+    pkeys = [str(k) for k in g['param_keys']]
+    gn = np.array([float(grads[k].double().norm()) for k in pkeys])
+    np.testing.assert_allclose(gn, g['grad_norm'], rtol=gtol, atol=1e-5)
+    for k in g.files:
+        if k.startswith('grad::'):
+            assert _rel(grads[k[6:]].cpu(), torch.from_numpy(g[k])) <= (2e-3 if math_mode == 'fp32' else 3e-2), k
+    # running statistics and the step counter moved exactly once
+    sd = model.state_dict()
+    for k in sd:
+        if k.endswith('num_batches_tracked'):
+            assert int(sd[k]) == 1
+    keys = [str(s) for s in g['keys']]
+    post = np.array([float(sd[k].double().sum()) for k in keys])
+    tol = np.array([2e-4 * max(2.0, (0.002 if math_mode == 'fp32' else 0.02) * sd[k].numel()) for k in keys])
+    assert np.all(np.abs(post - g['post_sum']) <= tol), float(np.abs(post - g['post_sum']).max())
+
+
+@pytest.mark.parametrize('name', NATIVE_CASES)
+def test_forward_backward_against_oracle_same_weights(name, math_mode):
+    """Oracle and CUDA path start from identical weights (no optimizer step in between): train-mode forward,
+    loss, every gradient, updated running statistics, then eval-mode forward."""
+    kwargs, B, T = CASES[name]
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    pkeys = [k for k, _ in model.named_parameters()]
+    for k in pkeys:
+        sd[k].requires_grad_(True)
+    batch = batch_of(name)
+    loss_ref, grads_ref, y_ref = O.train_step(sd, pkeys, batch, spec, None)
+
+    model = model.to(DEV)
+    y, loss, grads, dy = _train_step(model, batch, None)
+    tight = math_mode == 'fp32'
+    assert _rel(y.cpu(), y_ref) <= (2e-6 if tight else 1e-3)
+    assert abs(loss - loss_ref) <= (1e-5 if tight else 2e-3) * abs(loss_ref)
+    for k in pkeys:
+        ref = grads_ref[k]
+        if float(ref.norm()) < 1e-7:
+            assert float(grads[k].norm()) < 1e-5
+            continue
+        assert _rel(grads[k].cpu(), ref) <= (2e-3 if tight else 4e-2), (k, _rel(grads[k].cpu(), ref))
+    msd = model.state_dict()
+    for k, v in sd.items():
+        if 'running_' in k:
+            np.testing.assert_allclose(msd[k].cpu().numpy(), v.detach().numpy(), rtol=1e-4 if tight else 2e-3,
+                                       atol=1e-5 if tight else 1e-3)
+    # eval-mode forward with the updated running statistics
+    with torch.no_grad():
+        y_eval_ref = O.unet_forward(sd, batch['input'], spec, training=False)
+        model.eval()
+        y_eval = model(batch['input'].to(DEV)).cpu()
+    if tight:
+        assert _rel(y_eval, y_eval_ref) <= 5e-6
+    elif kwargs.get('outer_skip', True):
+        rel, same, mae = O.residual_metrics(y_eval, y_eval_ref, batch['input'][:, :1])
+        assert rel <= 1e-3 and same and mae <= 1e-3, (rel, same, mae)
+
+
+def test_autograd_path_fills_param_grad_like_the_fused_path(math_mode):
+    kwargs, B, T = CASES['var_base']
+    batch = _cuda_batch(batch_of('var_base'))
+    m1 = _model(kwargs).to(DEV)
+    m2 = copy.deepcopy(m1)
+    _, _, fused, _ = _train_step(m1, {k: v.cpu() for k, v in batch.items()}, None)
+    m2.train()
+    y = m2(batch['input'])
+    assert y.requires_grad
+    s = batch['dsm_std'].view(-1, 1, 1, 1)
+    msk = batch['loss_mask'].float()
+    loss = (msk * s * (y - batch['target']).abs()).sum() / msk.sum()
+    loss.backward()
+    for n, p in m2.named_parameters():
+        assert p.grad is not None, n
+        assert _rel(p.grad, fused[n]) <= 1e-5, n
+    # a second forward invalidates the first graph
+    y1 = m2(batch['input'])
+    _ = m2(batch['input'])
+    with pytest.raises(RuntimeError):
+        y1.sum().backward()
+
+
+def test_loss_kernel_matches_reference_formula():
+    from resdepth_b200.lib.UNet import UNet
+    kwargs, B, T = CASES['var_base']
+    model = _model(kwargs).to(DEV)
+    h = model.native_handle(torch.device(DEV))
+    h.reserve(B, T, False)
+    b = O.synthetic_batch(5, 1, 64, seed=11)
+    b['dsm_mean'] = torch.tensor([400., 512.5, 13., 1050.25, 0.])
+    b['dsm_std'] = torch.tensor([3.5, 1.25, 7., 0.5, 2.])
+    yp = (b['input'] + 0.2 * torch.randn(5, 1, 64, 64, generator=torch.Generator().manual_seed(2))).requires_grad_(True)
+    ref = O.denormalized_l1(yp, b['target'], b['loss_mask'], b['dsm_mean'], b['dsm_std'])
+    ref.backward()
+    d = _cuda_batch(b)
+    loss = torch.empty(1, device=DEV)
+    dy = torch.empty(5, 1, 64, 64, device=DEV)
+    ypd = yp.detach().to(DEV)
+    h.loss(ypd.data_ptr(), d['target'].data_ptr(), d['loss_mask'].view(torch.uint8).data_ptr(), d['dsm_mean'].data_ptr(),
+           d['dsm_std'].data_ptr(), loss.data_ptr(), dy.data_ptr(), 5, 64, torch.cuda.current_stream().cuda_stream)
+    assert abs(float(loss) - float(ref)) <= 2e-6 * float(ref)
+    np.testing.assert_allclose(dy.cpu().numpy(), yp.grad.numpy(), rtol=1e-5, atol=1e-12)
+
+
+def test_adam_and_sgd_kernels_match_torch_cpu():
+    from resdepth_b200.lib.optim import SGD, Adam
+    gen = torch.Generator().manual_seed(4)
+    shapes = [(64, 3, 3, 3), (64,), (1,), (128, 64, 3, 3), (7,)]
+    ref = [torch.randn(s, generator=gen).requires_grad_(True) for s in shapes]
+    for cls_ref, cls_ours in ((torch.optim.Adam, Adam), (torch.optim.SGD, SGD)):
+        ours = [p.detach().clone().to(DEV).requires_grad_(True) for p in ref]
+        o_ref = cls_ref(ref, lr=2e-4, weight_decay=1e-5)
+        o_ours = cls_ours(ours, lr=2e-4, weight_decay=1e-5)
+        for _ in range(3):
+            for p, q in zip(ref, ours):
+                gr = torch.randn(p.shape, generator=gen)
+                p.grad = gr.clone()
+                q.grad = gr.to(DEV)
+            o_ref.step()
+            o_ours.step()
+        for p, q in zip(ref, ours):
+            np.testing.assert_allclose(q.detach().cpu().numpy(), p.detach().numpy(), rtol=2e-6, atol=1e-7)
+    # state_dict round trip keeps the PyTorch format
+    sd = o_ours.state_dict()
+    assert set(sd.keys()) == {'state', 'param_groups'}
+
+
+@pytest.mark.parametrize('name', ['blend_a', 'blend_b', 'blend_c'])
+def test_blend_kernel_matches_reference_golden(name, golden_dir):
+    from resdepth_b200.lib.evaluation import blend_tiles_into
+    g = np.load(os.path.join(golden_dir, 'blend.npz'))
+    rows, cols, tile, stride = [int(v) for v in g[name + '_geom']]
+    pos, box = g[name + '_pos'], g[name + '_box']
+    geom = np.concatenate([pos, box], axis=1).astype(np.int32)
+    raster = torch.zeros(rows, cols, dtype=torch.float64, device=DEV)
+    blend_tiles_into(raster, torch.from_numpy(g[name + '_tiles']).to(DEV), torch.from_numpy(g[name + '_mean']).to(DEV),
+                     torch.from_numpy(g[name + '_std']).to(DEV), torch.from_numpy(geom).to(DEV), tile, stride)
+    np.testing.assert_allclose(raster.cpu().numpy(), g[name + '_raster'], rtol=0, atol=1e-9)
+
+
+def test_input_validation_and_error_paths():
+    kwargs, B, T = CASES['var_base']
+    model = _model(kwargs).to(DEV)
+    with pytest.raises(RuntimeError):
+        model(torch.zeros(1, 3, 32, 32))                      # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        model(torch.zeros(1, 2, 32, 32, device=DEV))          # wrong channel count
+    with pytest.raises(RuntimeError):
+        model.eval()
+        with torch.no_grad():
+            model(torch.zeros(1, 3, 30, 30, device=DEV))      # tile not a multiple of 2^depth
+    with torch.no_grad():
+        y = model(torch.zeros(0 + 1, 3, 8, 8, device=DEV))    # smallest legal tile for depth 2 ... 2^depth = 4
+    assert y.shape == (1, 1, 8, 8)
+
+
+def test_eval_tiles_are_independent_at_full_size(math_mode):
+    """BASELINE config 2 (3-ch 256x256, depth 5, batch 32, forward only): in eval mode every tile is independent,
+    so one batch-32 call equals four batch-8 calls; two tiles are also checked against the CPU oracle."""
+    kwargs = dict(n_input_channels=3, start_kernel=64, depth=5, bias_conv_layer=True)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(DEV).eval()
+    x = O.synthetic_batch(32, 3, 256)['input']
+    with torch.no_grad():
+        xd = x.to(DEV)
+        y_all = model(xd)
+        y_parts = torch.cat([model(xd[i:i + 8]) for i in range(0, 32, 8)])
+        assert _rel(y_parts, y_all) <= 1e-6
+        y_ref = O.unet_forward(sd, x[:2], spec_of(kwargs), training=False)
+    rel, same, mae = O.residual_metrics(y_all[:2].cpu(), y_ref, x[:2, :1])
+    assert rel <= (1e-5 if math_mode == 'fp32' else 1e-3) and same and mae <= 1e-3, (rel, same, mae)
+
+
+def test_train_batch_replication_property_at_full_size(math_mode):
+    """BASELINE config 3 (batch 64 train step): a batch made of 8 copies of 8 tiles has the same BatchNorm
+    statistics, per-tile outputs, loss and parameter gradients as the 8 tiles alone."""
+    kwargs = dict(n_input_channels=3, start_kernel=64, depth=5, bias_conv_layer=True)
+    small = O.synthetic_batch(8, 3, 256)
+    big = {k: torch.cat([v] * 8) for k, v in small.items()}
+    m1 = _model(kwargs).to(DEV)
+    m2 = copy.deepcopy(m1)
+    y1, l1, g1, _ = _train_step(m1, small)
+    y2, l2, g2, _ = _train_step(m2, big)
+    assert _rel(y2[:8], y1) <= (1e-5 if math_mode == 'fp32' else 1e-3)
+    assert _rel(y2[56:], y2[:8]) <= 1e-6
+    assert abs(l1 - l2) <= 1e-4 * abs(l1)
+    for k in g1:
+        if float(g1[k].norm()) > 1e-6:
+            assert _rel(g2[k], g1[k]) <= (1e-3 if math_mode == 'fp32' else 5e-2), k
+
+
+def test_trainer_three_steps_follow_the_oracle(tmp_path, math_mode):
+    """resdepth_b200.lib.Trainer.inference_one_epoch (train) against the oracle running the same three steps."""
+    from types import SimpleNamespace
+
+    from resdepth_b200.lib.Trainer import Trainer
+    kwargs, B, T = CASES['kat1']
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    pkeys = [k for k, _ in model.named_parameters()]
+    for k in pkeys:
+        sd[k].requires_grad_(True)
+    batches = [O.synthetic_batch(B, 1, T, seed=100 + i) for i in range(3)]
+    opt_ref = torch.optim.Adam([sd[k] for k in pkeys], lr=2e-4, weight_decay=1e-5)
+    ref_losses = [O.train_step(sd, pkeys, b, spec, opt_ref)[0] for b in batches]
+
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=10)
+    args = SimpleNamespace(trainloader=batches, valloader=batches[:1], model=model, optimizer=opt, scheduler=sched,
+                           criterion=torch.nn.L1Loss(reduction='mean'), n_epochs=1, evaluate_rate=1, save_model_rate=1,
+                           freq_average_train_loss=1, save_dir=str(tmp_path), log_file=str(tmp_path / 'training.log'),
+                           checkpoint_dir=str(tmp_path / 'ckpt'), tboard_log_dir=None, pretrained_path=None)
+    tr = Trainer(args)
+    assert tr.optimizer.__class__.__name__ == 'Adam'
+    losses = []
+    for b in batches:
+        losses.append(tr.inference_one_batch(b, 'train')['MAE_metric'])
+        tr.optimizer.step()
+        for p in tr.model.parameters():
+            p.grad = None
+    tol = 1e-4 if math_mode == 'fp32' else 3e-3
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= tol * abs(b), (losses, ref_losses)
+    val = tr.inference_one_batch(batches[0], 'val')['MAE_metric']
+    with torch.no_grad():
+        y = O.unet_forward(sd, batches[0]['input'], spec, training=False)
+        val_ref = float(O.denormalized_l1(y, batches[0]['target'], batches[0]['loss_mask'], batches[0]['dsm_mean'],
+                                          batches[0]['dsm_std']))
+    assert abs(val - val_ref) <= (2e-4 if math_mode == 'fp32' else 5e-3) * abs(val_ref)
+    # full loop incl. checkpoint files
+    tr.train()
+    assert os.path.isfile(tr.path_model_last)
+    ck = torch.load(tr.path_model_last, weights_only=False)
+    assert set(ck) >= {'epoch', 'model_state_dict', 'optimizer_state_dict', 'loss_train', 'loss_val'}
+    assert list(ck['model_state_dict'].keys()) == list(model.state_dict().keys())
+
+
+def test_predict_linear_blend_matches_oracle(math_mode):
+    from types import SimpleNamespace
+
+    from resdepth_b200.lib.evaluation import predict_linear_blend
+    kwargs = dict(n_input_channels=2, start_kernel=32, depth=2, bias_conv_layer=True)
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rows, cols, tile, stride = 80, 100, 32, 16
+    pos, box = O.regular_grid((0, cols - 1), (0, rows - 1), tile, stride)
+    gen = torch.Generator().manual_seed(9)
+    n = len(pos)
+    x = torch.randn(n, 2, tile, tile, generator=gen)
+    mean = 400 + torch.randn(n, generator=gen)
+    std = torch.full((n,), 3.5)
+    with torch.no_grad():
+        y_ref = O.unet_forward(sd, x, spec, training=False).numpy()
+    ref = O.linear_blend(y_ref, mean.numpy(), std.numpy(), pos, box, rows, cols, tile, stride)
+    batches = []
+    for i in range(0, n, 5):
+        sl = slice(i, min(i + 5, n))
+        batches.append({'input': x[sl], 'dsm_mean': mean[sl], 'dsm_std': std[sl],
+                        'patch_offset_y': torch.tensor([p[0] for p in pos[sl]]),
+                        'patch_offset_x': torch.tensor([p[1] for p in pos[sl]]),
+                        'patch_valid_pixels_uly': torch.tensor([b[0] for b in box[sl]]),
+                        'patch_valid_pixels_ulx': torch.tensor([b[1] for b in box[sl]]),
+                        'patch_valid_pixels_lry': torch.tensor([b[2] for b in box[sl]]),
+                        'patch_valid_pixels_lrx': torch.tensor([b[3] for b in box[sl]])})
+
+    class Loader(list):
+        pass
+    loader = Loader(batches)
+    loader.dataset = SimpleNamespace(dsm_input_gdal=SimpleNamespace(RasterXSize=cols, RasterYSize=rows),
+                                     tile_size=tile, stride=stride)
+    out = predict_linear_blend(loader, model)
+    assert out.dtype == np.float64 and out.shape == (rows, cols)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-4 if math_mode == 'fp32' else 5e-3)

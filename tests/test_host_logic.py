@@ -1,0 +1,119 @@
+"""CPU tests: the C-ABI library loads and exports every symbol of include/resdepth_b200.h, the native layer plan
+mirrors the module tree of every constructor variant, host-side error behaviour, optimizer arena detection."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from resdepth_b200 import _native
+from tests.cases import CASES, NATIVE_CASES, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'resdepth_b200.h')).read()
+    declared = set(re.findall(r'\b(rd_[a-z0-9_]+)\s*\(', header))
+    declared -= {'rd_handle', 'rd_config'}
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(_native.library_path())
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert _native.lib().rd_abi_version() == _native.ABI_VERSION
+
+
+@pytest.mark.parametrize('name', NATIVE_CASES)
+def test_native_plan_matches_module_tree(name):
+    from resdepth_b200.lib.UNet import UNet
+    kwargs, _, _ = CASES[name]
+    torch.manual_seed(0)
+    model = UNet(**kwargs)
+    h = _native.Handle(model._config(), 0)           # rd_create builds the plan only; no device work
+    named = dict(model.named_parameters())
+    infos = h.param_infos()
+    assert [n for n, _, _ in infos] == list(named.keys())
+    assert [n for n, _, _ in infos] == [str(k) for k in load_golden(name)['param_keys']]
+    end = 0
+    for n, numel, off in infos:
+        assert numel == named[n].numel()
+        assert off % 4 == 0 and off >= end
+        end = off + numel
+    assert h.param_arena_size() >= end
+    bufs = dict(model.named_buffers())
+    for n, numel, off in h.buffer_infos():
+        assert bufs[n].numel() == numel and off % 4 == 0
+    assert {n for n, _, _ in h.buffer_infos()} == {k for k in bufs if not k.endswith('num_batches_tracked')}
+    h.close()
+
+
+def test_constructor_errors_match_reference_behaviour():
+    from resdepth_b200.lib.UNet import UNet
+    with pytest.raises(ValueError):
+        UNet(act_fn_encoder='gelu')
+    with pytest.raises(ValueError):
+        UNet(up_mode='nearest')
+    m = UNet(n_input_channels=3, start_kernel=32, depth=2, up_mode='bilinear')
+    with pytest.raises(NotImplementedError):
+        m._config()
+    m = UNet(n_input_channels=3, start_kernel=32, depth=2)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 32, 32))                  # CPU tensors are refused: no fallback path
+
+
+def test_rd_create_rejects_unsupported_plans():
+    cfg = _native.RdConfig(n_input_channels=3, start_kernel=48, max_filter_depth=512, depth=3, do_bn=1, outer_skip=1)
+    with pytest.raises(RuntimeError, match='start_kernel'):
+        _native.Handle(cfg, 0)
+    cfg = _native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1, outer_skip=1,
+                           outer_skip_bn=1)
+    with pytest.raises(RuntimeError, match='outer_skip_BN'):
+        _native.Handle(cfg, 0)
+    cfg = _native.RdConfig(n_input_channels=9, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1)
+    with pytest.raises(RuntimeError, match='n_input_channels'):
+        _native.Handle(cfg, 0)
+
+
+def test_flat_span_detection():
+    from resdepth_b200.lib.optim import _flat_span
+    arena = torch.zeros(64)
+    a, b, c = arena[0:10].view(2, 5), arena[12:13], arena[16:48].view(4, 8)
+    ptr, n = _flat_span([c, a, b])
+    assert ptr == arena.data_ptr() and n == 48
+    assert _flat_span([a, c]) is None                  # hole where b should be
+    assert _flat_span([a, torch.zeros(3)]) is None     # different storages
+    assert _flat_span([arena[1:5]]) is None            # misaligned start
+
+
+def test_fuse_optimizer_keeps_class_name_state_and_scheduler():
+    from resdepth_b200.lib.optim import Adam, SGD, fuse_optimizer
+    p = [torch.nn.Parameter(torch.zeros(4))]
+    opt = torch.optim.Adam(p, lr=2e-4, weight_decay=1e-5)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+    fused = fuse_optimizer(opt)
+    assert fused is opt and isinstance(opt, Adam) and opt.__class__.__name__ == 'Adam'
+    assert isinstance(fuse_optimizer(torch.optim.SGD(p, lr=0.1)), SGD)
+    with pytest.raises(NotImplementedError):
+        fuse_optimizer(torch.optim.RMSprop(p))
+    p[0].grad = torch.ones(4)
+    with pytest.raises(RuntimeError):                 # CPU parameters: the fused step refuses, no fallback
+        opt.step()
+    sched.step()
+    assert abs(opt.param_groups[0]['lr'] - 1e-4) < 1e-12
+
+
+def test_average_meter_and_denormalize_helpers():
+    from resdepth_b200.lib.AverageMeter import AverageMeter
+    from resdepth_b200.lib.data_normalization import denormalize_numpy, denormalize_torch
+    m = AverageMeter()
+    m.update(2.0)
+    m.update(4.0, n=3)
+    assert m.avg == pytest.approx(3.5) and m.count == 4 and m.val == 4.0
+    x = torch.arange(8.).view(2, 1, 2, 2)
+    mean, std = torch.tensor([10., 20.]), torch.tensor([2., 3.])
+    out = denormalize_torch(x, mean, std)
+    assert torch.equal(out[1], x[1] * 3 + 20)
+    np.testing.assert_array_equal(denormalize_numpy(x, mean, std), out.numpy())
+    assert torch.equal(denormalize_torch(x, 1.0, 2.0), x * 2 + 1)
