@@ -50,34 +50,46 @@ class NetSpec:
 def _act(h: torch.Tensor, kind: str, prelu_weight: Optional[torch.Tensor]) -> torch.Tensor:
     # lib/UNet.py:27-33
     if kind == 'relu':
-        return F.relu(h)
+        return F.relu(h, inplace=True)                 # nn.ReLU(inplace=True)
     if kind == 'lrelu':
-        return F.leaky_relu(h, LRELU_SLOPE)
+        return F.leaky_relu(h, LRELU_SLOPE, inplace=True)
     if kind == 'prelu':
         return F.prelu(h, prelu_weight)
     raise ValueError(kind)
 
 
+EXPLICIT_BN = False   # True: evaluate the BatchNorm formula term by term (cross-check of the ATen call)
+
+
 def _bn(z: torch.Tensor, prefix: str, sd: Dict[str, torch.Tensor], training: bool,
         update_running: bool) -> torch.Tensor:
-    """nn.BatchNorm2d forward written out (lib/UNet.py:45,66,86,193).
+    """nn.BatchNorm2d forward (lib/UNet.py:45,66,86,193).
 
-    train: batch mean / biased variance normalise, running stats get the
-    unbiased variance with momentum 0.1; eval: running stats.
+    Default: the same ATen operator nn.BatchNorm2d.forward dispatches to (``F.batch_norm`` with momentum 0.1,
+    eps 1e-5), so the CPU baseline timed from this oracle executes the reference's own operator sequence.
+    ``EXPLICIT_BN``: the formula written out -- train: batch mean / biased variance normalise, running stats
+    get the unbiased variance with momentum 0.1; eval: running stats.
     """
     g, b = sd[prefix + '.weight'], sd[prefix + '.bias']
+    rm, rv = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
+    if not EXPLICIT_BN:
+        if training and not update_running:
+            rm, rv = rm.clone(), rv.clone()
+        out = F.batch_norm(z, rm, rv, g, b, training, BN_MOMENTUM, BN_EPS)
+        if training and update_running:
+            sd[prefix + '.num_batches_tracked'] += 1
+        return out
     if training:
         n = z.numel() // z.shape[1]
         mu = z.mean(dim=(0, 2, 3))
         var = ((z - mu[None, :, None, None]) ** 2).mean(dim=(0, 2, 3))
         if update_running:
             with torch.no_grad():
-                rm, rv = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
                 rm.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * mu.detach())
                 rv.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * var.detach() * (n / max(n - 1, 1)))
                 sd[prefix + '.num_batches_tracked'] += 1
     else:
-        mu, var = sd[prefix + '.running_mean'], sd[prefix + '.running_var']
+        mu, var = rm, rv
     xhat = (z - mu[None, :, None, None]) / torch.sqrt(var[None, :, None, None] + BN_EPS)
     return xhat * g[None, :, None, None] + b[None, :, None, None]
 

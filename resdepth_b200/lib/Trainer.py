@@ -226,6 +226,14 @@ class Trainer(object):
         mean = self._to_device(torch.flatten(batch['dsm_mean']), torch.float32)
         std = self._to_device(torch.flatten(batch['dsm_std']), torch.float32)
 
+        loss = self.device_step(x, y, loss_mask, mean, std, train)
+
+        return {'MAE_metric': float(loss.item())}
+
+    def device_step(self, x, y, loss_mask, mean, std, train):
+        """The step on device-resident tensors: forward, fused loss (+ gradient seed), backward, gradient
+        all-reduce; leaves ``param.grad`` set (views of the flat gradient arena) and returns the loss as a
+        device tensor [1] without synchronising.  ``inference_one_batch`` = H2D copies + this + ``loss.item()``."""
         with torch.no_grad():
             y_pred = self.model._forward_native(x, _native.FWD_TRAIN if train else _native.FWD_EVAL)
             loss, dy = self._compute_denormalized_loss(y_pred, y, loss_mask, mean, std, want_grad=train)
@@ -237,8 +245,7 @@ class Trainer(object):
                     self.optimizer.grad_scale = 1.0 / self.world_size
                 for p, g in zip(self.model.parameters(), grads):
                     p.grad = g
-
-        return {'MAE_metric': float(loss.item())}
+        return loss
 
     def inference_one_epoch(self, epoch, phase):
         assert phase in ['train', 'val']

@@ -62,6 +62,24 @@ def test_oracle_train_step_and_eval_match_reference(name):
     assert abs(float(loss_eval) - float(g['loss_eval'])) < 5e-6 * max(1.0, abs(float(g['loss_eval'])))
 
 
+def test_explicit_batchnorm_formula_equals_aten_call():
+    kwargs, B, T = CASES['var_base']
+    spec = spec_of(kwargs)
+    outs = []
+    for explicit in (False, True):
+        O.EXPLICIT_BN = explicit
+        try:
+            sd, _ = _state(kwargs)
+            with torch.no_grad():
+                y = O.unet_forward(sd, batch_of('var_base')['input'], spec, training=True)
+            outs.append((y, sd['encoder.1.0.1.running_var'].clone(), int(sd['bottleneck.1.num_batches_tracked'])))
+        finally:
+            O.EXPLICIT_BN = False
+    np.testing.assert_allclose(outs[0][0].numpy(), outs[1][0].numpy(), rtol=0, atol=5e-6)
+    np.testing.assert_allclose(outs[0][1].numpy(), outs[1][1].numpy(), rtol=1e-5)
+    assert outs[0][2] == outs[1][2] == 1
+
+
 def test_closed_form_loss_equals_reference_form():
     b = O.synthetic_batch(3, 1, 16)
     y = b['input'] + 0.3 * torch.randn(3, 1, 16, 16, generator=torch.Generator().manual_seed(5))
