@@ -8,6 +8,7 @@
 
 #include "../../include/resdepth_b200.h"
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace rd {
 
@@ -41,6 +42,7 @@ struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottl
   float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
   float *w_kn = nullptr, *w_nk = nullptr, *wd_kn = nullptr, *wd_nk = nullptr;
   bool tc = false;     // GEMMs of this block run on tcgen05
+  TcRowsPlan tc_fwd, tc_dgrad;
 };
 
 struct UpConv {        // ConvTranspose2d(C, C, 2, 2) (lib/UNet.py:17-24)
@@ -49,6 +51,7 @@ struct UpConv {        // ConvTranspose2d(C, C, 2, 2) (lib/UNet.py:17-24)
   float *u = nullptr;
   float *w_kn = nullptr, *w_nk = nullptr;
   bool tc = false;
+  TcRowsPlan tc_fwd, tc_dgrad;
 };
 
 }  // namespace rd
@@ -239,6 +242,42 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   return c.off;
 }
 
+// TMA descriptors + tile plans of every tcgen05 layer for the current workspace layout
+int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
+  const int D = h->depth;
+  auto off = [&](ConvBlock& b) { b.tc = false; b.tc_fwd.valid = b.tc_dgrad.valid = false; };
+  for (auto& b : h->enc) off(b);
+  off(h->bott);
+  for (auto& b : h->dec) off(b);
+  for (auto& u : h->ups) { u.tc = false; u.tc_fwd.valid = u.tc_dgrad.valid = false; }
+  if (!h->tf32() || !tc_available()) return 0;
+  auto block = [&](ConvBlock& b, const float* src, int H) -> int {
+    Gather gf = gather_conv3x3(H, H, b.Cin);
+    Gather gd = gather_conv3x3(H, H, b.Cout);
+    if (!tc_rows_eligible(gf, b.Cout) || !tc_rows_eligible(gd, b.Cin)) return 0;
+    RD_TRY(tc_make_rows_plan(&b.tc_fwd, src, gf, B, b.w_nk, b.Cout));
+    if (bwd) RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
+    b.tc = true;
+    return 0;
+  };
+  for (int i = 1; i < D; ++i) RD_TRY(block(h->enc[i], h->enc[i - 1].p, T >> i));
+  RD_TRY(block(h->bott, h->enc[D - 1].p, T >> D));
+  for (int j = 0; j < D; ++j) {
+    UpConv& u = h->ups[j];
+    const int Hin = T >> (D - j);
+    const float* src = j == 0 ? h->bott.a : h->dec[j - 1].a;
+    Gather gf = gather_plain(Hin, Hin, u.C);
+    Gather gd = gather_up2(Hin, Hin, u.C);
+    if (tc_rows_eligible(gf, 4 * u.C) && tc_rows_eligible(gd, u.C)) {
+      RD_TRY(tc_make_rows_plan(&u.tc_fwd, src, gf, B, u.w_nk, 4 * u.C));
+      if (bwd) RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
+      u.tc = true;
+    }
+    if (j < D - 1) RD_TRY(block(h->dec[j], u.u, 2 * Hin));
+  }
+  return 0;
+}
+
 int check_shape(const rd_handle* h, int B, int T) {
   if (B < 1) return fail("batch must be >= 1 (got %d)", B);
   const int D = h->depth;
@@ -292,6 +331,7 @@ int conv_block_forward(rd_handle* h, ConvBlock& b, const float* src, int B, int 
   *np = 0;
   const double px = (double)B * H * H;
   ProfScope ps(h, RD_PROF_CONV_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+  if (b.tc) return launch_gemm_rows_tc(b.tc_fwd, e, np, s);
   return launch_gemm_rows_simt(src, g, b.w_kn, B, b.Cout, e, np, s);
 }
 
@@ -432,6 +472,7 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
     RD_CUDA(cudaDeviceSynchronize());   // re-carving a live slab: wait for in-flight work
   }
   carve(h, h->slab, batch, tile, with_backward);
+  RD_TRY(build_tc_plans(h, batch, tile, with_backward));
   const float consts[4] = {0.f, 0.01f, 1.f, 0.f};          // relu slope, LeakyReLU default slope (lib/UNet.py:30)
   RD_CUDA(cudaMemcpy(h->consts, consts, sizeof(consts), cudaMemcpyHostToDevice));
   h->res_batch = batch; h->res_tile = tile; h->res_bwd = with_backward;
@@ -490,7 +531,8 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     {
       const double px = (double)B * Hc * Hc;
       ProfScope ps(h, RD_PROF_CONVT_FWD, 2.0 * 4.0 * u.C * u.C * px, 4.0 * px * u.C * (1.0 + 4.0 + 4.0), s);
-      RD_TRY(launch_gemm_rows_simt(cur, g, u.w_kn, B, 4 * u.C, e, nullptr, s));
+      if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_fwd, e, nullptr, s));
+      else RD_TRY(launch_gemm_rows_simt(cur, g, u.w_kn, B, 4 * u.C, e, nullptr, s));
     }
     Hc *= 2;
     if (j < D - 1) {
@@ -527,7 +569,7 @@ namespace {
 // backward of one conv block.  g_full: gradient at the (un-pooled) block output, g_pool: gradient at the pooled
 // output; src_in: the block's input (NHWC) or, for the first encoder block, the network input x (NCHW).
 int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float* g_pool, int B, int H,
-                   const float* src_in, bool first, float* dgrad_out, cudaStream_t s) {
+                   const float* src_in, bool first, float* dgrad_out, int round_dgrad, cudaStream_t s) {
   BnLayer L = bn_view(h, b);
   Act act = act_view(h, b);
   const int do_bn = h->cfg.do_bn;
@@ -563,8 +605,10 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
     Epilogue e{};
     e.mode = EPI_PLAIN;
     e.out = dgrad_out;
+    e.round_tf32 = round_dgrad;
     ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
-    RD_TRY(launch_gemm_rows_simt(h->gy, g, b.wd_kn, B, b.Cin, e, nullptr, s));
+    if (b.tc) RD_TRY(launch_gemm_rows_tc(b.tc_dgrad, e, nullptr, s));
+    else RD_TRY(launch_gemm_rows_simt(h->gy, g, b.wd_kn, B, b.Cin, e, nullptr, s));
   }
   return 0;
 }
@@ -613,18 +657,21 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     e.out = h->gh;
     {
       ProfScope ps(h, RD_PROF_CONVT_DGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
-      RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
+      if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_dgrad, e, nullptr, s));
+      else RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
     }
     if (j == 0) {
-      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, s));
+      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, s));
     } else {
-      RD_TRY(block_backward(h, h->dec[j - 1], h->gh, nullptr, B, Hin, h->ups[j - 1].u, false, h->g_skip[D - j], s));
+      // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded
+      RD_TRY(block_backward(h, h->dec[j - 1], h->gh, nullptr, B, Hin, h->ups[j - 1].u, false, h->g_skip[D - j],
+                            h->tf32() && h->ups[j - 1].tc, s));
     }
   }
   for (int i = D - 1; i >= 0; --i) {
     const int H = T >> i;
     RD_TRY(block_backward(h, h->enc[i], h->g_skip[i], h->gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
-                          i == 0 ? nullptr : h->gp, s));
+                          i == 0 ? nullptr : h->gp, 0, s));
   }
   return 0;
 }

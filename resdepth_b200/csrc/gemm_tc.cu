@@ -1,0 +1,375 @@
+// GEMM-shaped layers on the 5th-generation tensor cores (RD_MATH_TF32).
+//
+// rows kernel (conv3x3 forward / dgrad, transposed-conv forward / dgrad; reference lib/UNet.py:4-5,21 and their
+// autograd): implicit GEMM  D[128 pixels][BN] = sum_taps sum_c A_tap[pixel][c] * W[n][(tap,c)]
+//   * A tiles: TMA 4-D boxes (32 channels x tw x th x tb pixels) of the NHWC activation tensor, one box per
+//     (tap, 32-channel chunk); negative / overflowing coordinates are zero-filled by the TMA unit, which IS the
+//     convolution padding.  128-byte swizzle, K-major (32 fp32 of K per 128-byte row).
+//   * B tiles: TMA 2-D boxes (32 k x BN) of the packed weights [N][K] (K-major).
+//   * tcgen05.mma kind::tf32, M = 128, N = BN, K = 8 per instruction, fp32 accumulators in TMEM, two
+//     accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+//     (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> 128-byte row stores).
+//   * persistent CTAs, static tile schedule with a fixed N tile per CTA so BatchNorm column sums accumulate in
+//     registers across all of a CTA's tiles (one partial row per CTA-warp instead of one per tile).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "tc_common.cuh"
+
+namespace rd {
+
+using namespace tc;
+
+static constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+template <int BN>
+struct RowsCfg {
+  static constexpr int A_BYTES = 128 * 128;                 // 128 rows x 32 fp32
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const TcRowsParams P) {
+  using Cfg = RowsCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapB);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = P.N / BN;
+  const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int num_tiles = m_tiles * n_tiles;
+  const int kblocks = P.ntaps * P.cchunks;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        int mt = tile / n_tiles;
+        const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
+        const int th_i = mt % P.tiles_h;
+        const int tb_i = mt / P.tiles_h;
+        const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+        for (int tap = 0; tap < P.ntaps; ++tap) {
+          int c[4] = {P.tap_off[tap][0], P.tap_off[tap][1], P.tap_off[tap][2], P.tap_off[tap][3]};
+          c[P.coord_w] += w0;
+          c[P.coord_h] += h0;
+          if (P.coord_b >= 0) c[P.coord_b] += b0;
+          for (int cc = 0; cc < P.cchunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+            tma_load_4d(sa, &mapA, &full_bar[stage], c[0] + cc * 32, c[1], c[2], c[3]);
+            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * 32, nt * BN);
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 4 x (K = 8 fp32 = 32 bytes) inside the 128-byte swizzle atom
+            mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[stage]);             // frees the smem stage when these MMAs have read it
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float cs1[BN / 32], cs2[BN / 32];
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) cs1[i] = cs2[i] = 0.f;
+    const int iw = row % P.tw, ih = (row / P.tw) % P.th, ib = row / (P.tw * P.th);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int nt = tile % n_tiles;
+      int mt = tile / n_tiles;
+      const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
+      const int th_i = mt % P.tiles_h;
+      const int tb_i = mt / P.tiles_h;
+      const int w = tw_i * P.tw + iw, h = th_i * P.th + ih, b = tb_i * P.tb + ib;
+      const bool valid = (w < P.Wo) && (h < P.Ho) && (b < P.Bo);
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+      const size_t pix = ((size_t)b * P.Ho + h) * P.Wo + w;
+#pragma unroll
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tmem_ld32(t_row + ch * 32, v);
+        const int n = nt * BN + ch * 32;
+        if (P.epi_mode == EPI_CONVT) {
+          const int Co = P.N >> 2;
+          const int ab = n / Co, co = n - ab * Co;
+          if (valid) {
+            const size_t o = ((((size_t)b * 2 * P.Ho + 2 * h + (ab >> 1)) * 2 * P.Wo) + 2 * w + (ab & 1)) * Co + co;
+            const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
+            const float4* sp = P.skip ? reinterpret_cast<const float4*>(P.skip + o) : nullptr;
+            float4* op = reinterpret_cast<float4*>(P.out + o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(bp + j);
+              float4 r = make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
+              if (sp) {
+                const float4 sv = sp[j];
+                r.x += sv.x; r.y += sv.y; r.z += sv.z; r.w += sv.w;
+              }
+              if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
+              op[j] = r;
+            }
+          }
+        } else {
+          if (valid) {
+            float4* op = reinterpret_cast<float4*>(P.out + pix * P.N + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
+              op[j] = r;
+            }
+          }
+          if (P.epi_mode == EPI_STATS) {
+            float sq[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = valid ? v[j] : 0.f;
+              sq[j] = v[j] * v[j];
+            }
+            cs1[ch] += warp_colsum32(v, lane);
+            cs2[ch] += warp_colsum32(sq, lane);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+    if (P.epi_mode == EPI_STATS) {
+      // lane c holds the sums of column (chunk*32 + c) over this warp's rows of all tiles of this CTA
+      // partial row = (CTA group, warp); the n_tiles CTAs of a group (fixed N tile each: gridDim.x is a multiple
+      // of n_tiles) fill disjoint column ranges of the same partial rows
+      const int nt = blockIdx.x % n_tiles;
+      float* dst = P.partials + ((size_t)((blockIdx.x / n_tiles) * 4 + q) * P.N + nt * BN) * 2;
+      const bool had_tiles = blockIdx.x < num_tiles;
+#pragma unroll
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col = ch * 32 + lane;
+        dst[col * 2 + 0] = had_tiles ? cs1[ch] : 0.f;
+        dst[col * 2 + 1] = had_tiles ? cs2[ch] : 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides_bytes,
+                  const int* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = (cuuint64_t)dims[i];
+    bx[i] = (cuuint32_t)box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = (cuuint64_t)strides_bytes[i - 1];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed with code %d (rank %d dims %lld %lld %lld %lld box %d %d %d %d)", (int)r,
+                rank, dims[0], rank > 1 ? dims[1] : 0, rank > 2 ? dims[2] : 0, rank > 3 ? dims[3] : 0, box[0],
+                rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+  return 0;
+}
+
+static int pow2_floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+bool tc_rows_eligible(const Gather& g, int N) {
+  if (g.C % 32 || N % 32) return false;
+  if (g.ntaps == 4 && g.ups != 2) return false;
+  return true;
+}
+
+int tc_pick_bn(int N) {
+  if (N % 256 == 0) return 256;
+  if (N % 128 == 0) return 128;
+  if (N % 64 == 0) return 64;
+  return 32;
+}
+
+int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B, const float* w_nk, int N) {
+  if (!tc_rows_eligible(g, N)) return fail("tc rows plan: shape not eligible (C=%d N=%d)", g.C, N);
+  TcRowsParams& P = plan->p;
+  std::memset(&P, 0, sizeof(P));
+  P.N = N;
+  P.ntaps = g.ntaps;
+  P.cchunks = g.C / 32;
+  plan->BN = tc_pick_bn(N);
+  long long dims[4], strides[3];
+  int box[4];
+  if (g.ups == 1) {
+    // source NHWC [B, H, W, C] seen as (C, W, H, B)
+    P.Wo = g.Wo; P.Ho = g.Ho; P.Bo = B;
+    P.tw = pow2_floor(g.Wo < 16 ? g.Wo : 16);
+    int th_max = 128 / P.tw;
+    P.th = pow2_floor(g.Ho < th_max ? g.Ho : th_max);
+    P.tb = 128 / (P.tw * P.th);
+    P.coord_w = 1; P.coord_h = 2; P.coord_b = 3;
+    for (int t = 0; t < g.ntaps; ++t) { P.tap_off[t][0] = 0; P.tap_off[t][1] = g.dw[t]; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
+    dims[0] = g.C; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
+    strides[0] = (long long)g.C * 4; strides[1] = (long long)g.Ws * g.C * 4; strides[2] = (long long)g.Hs * g.Ws * g.C * 4;
+    box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb;
+  } else {
+    // 2x2 stride-2 gather of dU NHWC [B, 2Hin, 2Win, C] seen as (2C, Win, 2, B*Hin): tap (a, b) = (coord2, coord0 / C)
+    P.Wo = g.Wo; P.Ho = B * g.Ho; P.Bo = 1;
+    P.tw = pow2_floor(g.Wo < 16 ? g.Wo : 16);
+    int th_max = 128 / P.tw;
+    P.th = pow2_floor(P.Ho < th_max ? P.Ho : th_max);
+    P.tb = 128 / (P.tw * P.th);
+    if (P.tb != 1) { P.th = 128 / P.tw; P.tb = 1; }     // rows beyond B*Hin are zero-filled and masked
+    P.coord_w = 1; P.coord_h = 3; P.coord_b = -1;
+    for (int t = 0; t < 4; ++t) { P.tap_off[t][0] = g.dw[t] * g.C; P.tap_off[t][1] = 0; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
+    dims[0] = 2LL * g.C; dims[1] = g.Wo; dims[2] = 2; dims[3] = (long long)B * g.Ho;
+    strides[0] = 2LL * g.C * 4; strides[1] = (long long)g.Wo * 2 * g.C * 4; strides[2] = 2LL * g.Wo * 2 * g.C * 4;
+    box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th;
+  }
+  P.tiles_w = cdiv(P.Wo, P.tw);
+  P.tiles_h = cdiv(P.Ho, P.th);
+  P.tiles_b = cdiv(P.Bo, P.tb);
+  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box));
+  const long long K = (long long)g.ntaps * g.C;
+  long long wd[2] = {K, N}, ws[1] = {K * 4};
+  int wb[2] = {32, plan->BN};
+  RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb));
+  plan->valid = true;
+  return 0;
+}
+
+template <int BN>
+static int launch_rows(const TcRowsPlan& plan, const TcRowsParams& P, int grid, cudaStream_t s) {
+  using Cfg = RowsCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  gemm_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
+  RD_LAUNCHED();
+  return 0;
+}
+
+int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partials, cudaStream_t s) {
+  if (!plan.valid) return fail("tc rows: plan not built");
+  TcRowsParams P = plan.p;
+  P.epi_mode = e.mode;
+  P.out = e.out;
+  P.partials = e.partials;
+  P.bias = e.bias;
+  P.skip = e.skip;
+  P.round_tf32 = e.round_tf32;
+  const int n_tiles = P.N / plan.BN;
+  const int num_tiles = P.tiles_w * P.tiles_h * P.tiles_b * n_tiles;
+  int grid = (148 / n_tiles) * n_tiles;
+  if (grid < n_tiles) grid = n_tiles;
+  if (grid > num_tiles) grid = ((num_tiles + n_tiles - 1) / n_tiles) * n_tiles;
+  if (n_partials) *n_partials = (grid / n_tiles) * 4;
+  switch (plan.BN) {
+    case 256: return launch_rows<256>(plan, P, grid, s);
+    case 128: return launch_rows<128>(plan, P, grid, s);
+    case 64: return launch_rows<64>(plan, P, grid, s);
+    case 32: return launch_rows<32>(plan, P, grid, s);
+  }
+  return fail("tc rows: unsupported BN=%d", plan.BN);
+}
+
+bool tc_available() { return encode_fn() != nullptr; }
+
+}  // namespace rd

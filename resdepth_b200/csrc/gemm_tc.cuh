@@ -1,0 +1,41 @@
+// Host-visible types of the tcgen05 GEMM kernels (gemm_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace rd {
+
+struct TcRowsParams {
+  int N;                 // GEMM N (output channels of the layer / 4*C for the transposed conv)
+  int ntaps, cchunks;    // K = ntaps * cchunks * 32
+  int tw, th, tb;        // pixel box of one 128-row tile (tw*th*tb == 128)
+  int tiles_w, tiles_h, tiles_b;
+  int Wo, Ho, Bo;        // output pixel grid the tile coordinates index
+  int coord_w, coord_h, coord_b;   // which tensor-map coordinate receives w0 / h0 / b0 (-1: none)
+  int tap_off[9][4];     // per-tap coordinate offsets (dimension 0 = channel)
+  int epi_mode;          // EPI_*
+  int round_tf32;
+  float* out;
+  float* partials;
+  const float* bias;
+  const float* skip;
+};
+
+struct TcRowsPlan {
+  CUtensorMap mapA, mapB;
+  TcRowsParams p;
+  int BN = 0;
+  bool valid = false;
+};
+
+bool tc_rows_eligible(const Gather& g, int N);
+int tc_pick_bn(int N);
+int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides_bytes,
+                  const int* box);
+// src: activation tensor the gather reads; w_nk: packed weights [N][ntaps*C] (K contiguous)
+int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B, const float* w_nk, int N);
+int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partials, cudaStream_t s);
+
+}  // namespace rd
