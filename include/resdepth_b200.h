@@ -122,6 +122,18 @@ int rd_profile_collect(rd_handle* h);
 int rd_profile_read(const rd_handle* h, int category, char* name64, double* ms, double* flops, double* bytes,
                     int64_t* launches, int64_t* calls);
 
+/* Test hooks: run ONE GEMM-shaped kernel in isolation (used by tests/ to compare the tcgen05 kernels with
+ * the CUDA-core kernels and the oracle layer by layer).  engine: 0 = CUDA-core fp32, 1 = tcgen05 TF32.
+ * kind: 0 = 3x3 taps (conv3x3 forward / dgrad / wgrad), 1 = single tap (transposed-conv forward),
+ *       2 = 2x2 stride-2 gather (transposed-conv dgrad / wgrad; src is [B, 2H, 2W, C]).
+ * rows:   out[B*H*W][N] = gather(src)[.][ntaps*C] x W, with w_kn = [ntaps*C][N] and w_nk = [N][ntaps*C].
+ * reduce: out[ntaps*C][N] = sum over the B*H*W pixels of gather(src)[p][.]^T G[p][N] (splits already summed;
+ *         scratch holds the split partials). */
+int rd_debug_rows(int engine, int kind, const float* src, int batch, int h, int w, int c, const float* w_kn,
+                  const float* w_nk, int n, float* out, void* stream);
+int rd_debug_reduce(int engine, int kind, const float* src, int batch, int h, int w, int c, const float* g, int n,
+                    float* out, float* scratch, int64_t scratch_floats, void* stream);
+
 /* Number of kernels launched by this library since the last call with reset != 0. */
 int64_t rd_launch_count(int reset);
 

@@ -43,6 +43,7 @@ struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottl
   float *w_kn = nullptr, *w_nk = nullptr, *wd_kn = nullptr, *wd_nk = nullptr;
   bool tc = false;     // GEMMs of this block run on tcgen05
   TcRowsPlan tc_fwd, tc_dgrad;
+  TcReducePlan tc_wgrad;
 };
 
 struct UpConv {        // ConvTranspose2d(C, C, 2, 2) (lib/UNet.py:17-24)
@@ -52,6 +53,7 @@ struct UpConv {        // ConvTranspose2d(C, C, 2, 2) (lib/UNet.py:17-24)
   float *w_kn = nullptr, *w_nk = nullptr;
   bool tc = false;
   TcRowsPlan tc_fwd, tc_dgrad;
+  TcReducePlan tc_wgrad;
 };
 
 }  // namespace rd
@@ -245,18 +247,22 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
 // TMA descriptors + tile plans of every tcgen05 layer for the current workspace layout
 int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
   const int D = h->depth;
-  auto off = [&](ConvBlock& b) { b.tc = false; b.tc_fwd.valid = b.tc_dgrad.valid = false; };
+  auto off = [&](ConvBlock& b) { b.tc = false; b.tc_fwd.valid = b.tc_dgrad.valid = b.tc_wgrad.valid = false; };
   for (auto& b : h->enc) off(b);
   off(h->bott);
   for (auto& b : h->dec) off(b);
-  for (auto& u : h->ups) { u.tc = false; u.tc_fwd.valid = u.tc_dgrad.valid = false; }
+  for (auto& u : h->ups) { u.tc = false; u.tc_fwd.valid = u.tc_dgrad.valid = u.tc_wgrad.valid = false; }
   if (!h->tf32() || !tc_available()) return 0;
   auto block = [&](ConvBlock& b, const float* src, int H) -> int {
     Gather gf = gather_conv3x3(H, H, b.Cin);
     Gather gd = gather_conv3x3(H, H, b.Cout);
     if (!tc_rows_eligible(gf, b.Cout) || !tc_rows_eligible(gd, b.Cin)) return 0;
     RD_TRY(tc_make_rows_plan(&b.tc_fwd, src, gf, B, b.w_nk, b.Cout));
-    if (bwd) RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
+    if (bwd) {
+      RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
+      if (tc_reduce_eligible(gf, b.Cout))
+        RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src, gf, B, h->gy, b.Cout, h->part, h->part_floats));
+    }
     b.tc = true;
     return 0;
   };
@@ -270,7 +276,11 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     Gather gd = gather_up2(Hin, Hin, u.C);
     if (tc_rows_eligible(gf, 4 * u.C) && tc_rows_eligible(gd, u.C)) {
       RD_TRY(tc_make_rows_plan(&u.tc_fwd, src, gf, B, u.w_nk, 4 * u.C));
-      if (bwd) RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
+      if (bwd) {
+        RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
+        if (tc_reduce_eligible(gd, u.C))
+          RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, h->g_skip[D - 1 - j], gd, B, src, u.C, h->part, h->part_floats));
+      }
       u.tc = true;
     }
     if (j < D - 1) RD_TRY(block(h->dec[j], u.u, 2 * Hin));
@@ -595,7 +605,12 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
     int S = 0;
     {
       ProfScope ps(h, RD_PROF_CONV_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
-      RD_TRY(launch_gemm_reduce_simt(src_in, g, h->gy, B, b.Cout, h->part, h->part_floats, &S, s));
+      if (b.tc_wgrad.valid) {
+        RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, s));
+        S = b.tc_wgrad.splits;
+      } else {
+        RD_TRY(launch_gemm_reduce_simt(src_in, g, h->gy, B, b.Cout, h->part, h->part_floats, &S, s));
+      }
     }
     ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), s);
     RD_TRY(launch_unpack_conv3x3_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, s));
@@ -646,7 +661,12 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     int S = 0;
     {
       ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
-      RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, s));
+      if (u.tc_wgrad.valid) {
+        RD_TRY(launch_gemm_reduce_tc(u.tc_wgrad, s));
+        S = u.tc_wgrad.splits;
+      } else {
+        RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, s));
+      }
     }
     {
       ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 4.0 * cc * (S + 1.0), s);
@@ -694,6 +714,56 @@ int rd_blend_accumulate(const float* tiles, const float* mean, const float* std,
                         int stride, double* raster, int rows, int cols, void* stream) {
   if (!tiles || !mean || !std || !geom || !raster) return fail("rd_blend_accumulate: null argument");
   return launch_blend(tiles, mean, std, geom, n, tile, stride, raster, rows, cols, reinterpret_cast<cudaStream_t>(stream));
+}
+
+static int debug_gather(int kind, int H, int W, int C, Gather* g) {
+  if (kind == 0) *g = gather_conv3x3(H, W, C);
+  else if (kind == 1) *g = gather_plain(H, W, C);
+  else if (kind == 2) *g = gather_up2(H, W, C);
+  else return fail("rd_debug: unknown kind %d", kind);
+  return 0;
+}
+
+__global__ void debug_sum_splits_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += gridDim.x * 256LL) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += part[(size_t)s * n + i];
+    out[i] = a;
+  }
+}
+
+int rd_debug_rows(int engine, int kind, const float* src, int batch, int hh, int ww, int c, const float* w_kn,
+                  const float* w_nk, int n, float* out, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Gather g;
+  RD_TRY(debug_gather(kind, hh, ww, c, &g));
+  Epilogue e{};
+  e.mode = EPI_PLAIN;
+  e.out = out;
+  if (engine == 0) return launch_gemm_rows_simt(src, g, w_kn, batch, n, e, nullptr, s);
+  TcRowsPlan plan;
+  RD_TRY(tc_make_rows_plan(&plan, src, g, batch, w_nk, n));
+  return launch_gemm_rows_tc(plan, e, nullptr, s);
+}
+
+int rd_debug_reduce(int engine, int kind, const float* src, int batch, int hh, int ww, int c, const float* gm, int n,
+                    float* out, float* scratch, int64_t scratch_floats, void* stream) {
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Gather g;
+  RD_TRY(debug_gather(kind, hh, ww, c, &g));
+  int S = 0;
+  if (engine == 0) {
+    RD_TRY(launch_gemm_reduce_simt(src, g, gm, batch, n, scratch, (size_t)scratch_floats, &S, s));
+  } else {
+    TcReducePlan plan;
+    RD_TRY(tc_make_reduce_plan(&plan, src, g, batch, gm, n, scratch, (size_t)scratch_floats));
+    RD_TRY(launch_gemm_reduce_tc(plan, s));
+    S = plan.splits;
+  }
+  const long long total = (long long)g.ntaps * c * n;
+  debug_sum_splits_kernel<<<(int)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256), 256, 0, s>>>(scratch, S, total, out);
+  RD_LAUNCHED();
+  return 0;
 }
 
 int rd_profile_enable(rd_handle* h, int on) {

@@ -244,7 +244,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides_bytes,
-                  const int* box) {
+                  const int* box, int swizzle_atom32) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5];
@@ -257,7 +257,9 @@ int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long
     if (i > 0) gstr[i - 1] = (cuuint64_t)strides_bytes[i - 1];
   }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail("cuTensorMapEncodeTiled failed with code %d (rank %d dims %lld %lld %lld %lld box %d %d %d %d)", (int)r,
@@ -324,11 +326,11 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
   P.tiles_w = cdiv(P.Wo, P.tw);
   P.tiles_h = cdiv(P.Ho, P.th);
   P.tiles_b = cdiv(P.Bo, P.tb);
-  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box));
+  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 0));
   const long long K = (long long)g.ntaps * g.C;
   long long wd[2] = {K, N}, ws[1] = {K * 4};
   int wb[2] = {32, plan->BN};
-  RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb));
+  RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb, 0));
   plan->valid = true;
   return 0;
 }
@@ -368,6 +370,242 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
     case 32: return launch_rows<32>(plan, P, grid, s);
   }
   return fail("tc rows: unsupported BN=%d", plan.BN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reduce kernel (weight gradients): D[(tap,ca)][n] = sum over pixels A[p + off(tap)][ca] * G[p][n]
+//   * the contraction index is the PIXEL, so both operands are MN-major: a TMA box of 32 pixels x 32 channels
+//     lands as 32 rows (k) x 128 bytes (m or n).  MN-major TF32 operands must use the "128-byte swizzle with
+//     32-byte atomicity" layout (TMA SWIZZLE_128B_ATOM_32B / descriptor layout SWIZZLE_128B_BASE32B): 4-row x
+//     128-byte atoms, 512 bytes apart along K.  A 128-row A tile is four such boxes (one per 32-channel chunk,
+//     each with its own tap shift), the G tile is BN/32 boxes.
+//   * one CTA = one (128-row tile, BN-column tile, pixel split); accumulates in TMEM over its pixel boxes and
+//     writes its partial [128][BN] block; the un-pack kernels sum the splits.
+// ---------------------------------------------------------------------------------------------
+static constexpr int KP = 32;                       // pixels per pipeline stage (4 MMAs of K = 8)
+static constexpr int BOX_BYTES = KP * 128;
+
+template <int BN>
+struct ReduceCfg {
+  static constexpr int NB = BN / 32;
+  static constexpr int STAGE_BYTES = (4 + NB) * BOX_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapG,
+                      const TcReduceParams P) {
+  using Cfg = ReduceCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* done_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapG);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int box_begin = blockIdx.z * P.boxes_per_split;
+  int box_end = box_begin + P.boxes_per_split;
+  if (box_end > total_boxes) box_end = total_boxes;
+  const int nsteps = box_end > box_begin ? box_end - box_begin : 0;
+  int nchunks = (P.Mrows - m0 + 31) / 32;             // live 32-row chunks of this M tile
+  if (nchunks > 4) nchunks = 4;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ctap[4], cch[4];
+      for (int mc = 0; mc < 4; ++mc) {
+        const int r = m0 + mc * 32;
+        ctap[mc] = r < P.Mrows ? r / P.Ca : 0;
+        cch[mc] = r < P.Mrows ? r % P.Ca : 0;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int bx = box_begin; bx < box_end; ++bx) {
+        int t = bx;
+        const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+        const int th_i = t % P.tiles_h;
+        const int tb_i = t / P.tiles_h;
+        const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[stage], (nchunks + Cfg::NB) * BOX_BYTES);
+        for (int mc = 0; mc < nchunks; ++mc) {
+          int c[4] = {P.tap_off[ctap[mc]][0] + cch[mc], P.tap_off[ctap[mc]][1], P.tap_off[ctap[mc]][2],
+                      P.tap_off[ctap[mc]][3]};
+          c[P.coord_w] += w0;
+          c[P.coord_h] += h0;
+          if (P.coord_b >= 0) c[P.coord_b] += b0;
+          tma_load_4d(st + mc * BOX_BYTES, &mapA, &full_bar[stage], c[0], c[1], c[2], c[3]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < Cfg::NB; ++nb) {
+          int c[4] = {n0 + nb * 32, 0, 0, 0};
+          c[P.coord_w] += w0;
+          c[P.coord_h] += h0;
+          if (P.coord_b >= 0) c[P.coord_b] += b0;
+          tma_load_4d(st + (4 + nb) * BOX_BYTES, &mapG, &full_bar[stage], c[0], c[1], c[2], c[3]);
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, BN, 1, 1);       // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nsteps; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sg = sa + 4 * BOX_BYTES;
+#pragma unroll
+        for (int k = 0; k < KP / 8; ++k) {                         // 8 pixels = two 4-row swizzle atoms per MMA
+          const uint64_t da = smem_desc_mn_sw128_32b(sa + k * 1024, BOX_BYTES, 512);
+          const uint64_t dg = smem_desc_mn_sw128_32b(sg + k * 1024, BOX_BYTES, 512);
+          mma_tf32(tmem_base, da, dg, idesc, (i | k) != 0);
+        }
+        tc_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    float* out = P.part + ((size_t)blockIdx.z * P.Mrows + m) * P.N + n0;
+    if (nsteps > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      float v[32];
+      if (nsteps > 0) {
+        tmem_ld32(t_row + ch * 32, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (m < P.Mrows) {
+        float4* op = reinterpret_cast<float4*>(out + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+bool tc_reduce_eligible(const Gather& g, int N) {
+  return g.C % 32 == 0 && N % 32 == 0 && (g.ups == 1 || (g.ups == 2 && g.ntaps == 4));
+}
+
+int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, int B, const float* G, int N,
+                        float* part, size_t part_floats) {
+  if (!tc_reduce_eligible(g, N)) return fail("tc reduce plan: shape not eligible (C=%d N=%d)", g.C, N);
+  TcReduceParams& P = plan->p;
+  std::memset(&P, 0, sizeof(P));
+  P.Mrows = g.ntaps * g.C;
+  P.Ca = g.C;
+  P.N = N;
+  P.ntaps = g.ntaps;
+  P.part = part;
+  plan->BN = tc_pick_bn(N);
+  long long dims[4], strides[3], gdims[4], gstrides[3];
+  int box[4];
+  int Wg, Hg, Bg;                                      // pixel grid of the contraction
+  if (g.ups == 1) {
+    Wg = g.Wo; Hg = g.Ho; Bg = B;
+    P.coord_w = 1; P.coord_h = 2; P.coord_b = 3;
+    for (int t = 0; t < g.ntaps; ++t) { P.tap_off[t][0] = 0; P.tap_off[t][1] = g.dw[t]; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
+    dims[0] = g.C; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
+    strides[0] = (long long)g.C * 4; strides[1] = (long long)g.Ws * g.C * 4; strides[2] = (long long)g.Hs * g.Ws * g.C * 4;
+    gdims[0] = N; gdims[1] = Wg; gdims[2] = Hg; gdims[3] = B;
+    gstrides[0] = (long long)N * 4; gstrides[1] = (long long)Wg * N * 4; gstrides[2] = (long long)Hg * Wg * N * 4;
+  } else {
+    Wg = g.Wo; Hg = B * g.Ho; Bg = 1;
+    P.coord_w = 1; P.coord_h = 3; P.coord_b = -1;
+    for (int t = 0; t < 4; ++t) { P.tap_off[t][0] = g.dw[t] * g.C; P.tap_off[t][1] = 0; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
+    dims[0] = 2LL * g.C; dims[1] = g.Wo; dims[2] = 2; dims[3] = (long long)B * g.Ho;
+    strides[0] = 2LL * g.C * 4; strides[1] = (long long)g.Wo * 2 * g.C * 4; strides[2] = 2LL * g.Wo * 2 * g.C * 4;
+    gdims[0] = N; gdims[1] = Wg; gdims[2] = 1; gdims[3] = Hg;
+    gstrides[0] = (long long)N * 4; gstrides[1] = (long long)Wg * N * 4; gstrides[2] = (long long)Wg * N * 4;
+  }
+  P.tw = pow2_floor(Wg < KP ? Wg : KP);
+  int th_max = KP / P.tw;
+  P.th = pow2_floor(Hg < th_max ? Hg : th_max);
+  P.tb = KP / (P.tw * P.th);
+  if (g.ups == 2 && P.tb != 1) { P.th = KP / P.tw; P.tb = 1; }
+  P.tiles_w = cdiv(Wg, P.tw);
+  P.tiles_h = cdiv(Hg, P.th);
+  P.tiles_b = cdiv(Bg, P.tb);
+  if (g.ups == 1) { box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb; }
+  else { box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th; }
+  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 1));
+  RD_TRY(tc_encode_map(&plan->mapG, G, 4, gdims, gstrides, box, 1));
+  // split the pixel boxes so that ~2 waves of CTAs exist, bounded by the partial buffer
+  const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int tiles = cdiv(P.Mrows, 128) * (N / plan->BN);
+  int S = cdiv(148 * 2, tiles);
+  if (S > total_boxes / 8) S = total_boxes / 8;         // at least 8 K steps per CTA
+  if (S < 1) S = 1;
+  const size_t per = (size_t)P.Mrows * N;
+  while (S > 1 && (size_t)S * per > part_floats) --S;
+  if ((size_t)S * per > part_floats) return fail("tc reduce plan: partial buffer too small (%zu floats needed)", per);
+  P.boxes_per_split = cdiv(total_boxes, S);
+  plan->splits = cdiv(total_boxes, P.boxes_per_split);
+  plan->valid = true;
+  return 0;
+}
+
+template <int BN>
+static int launch_reduce(const TcReducePlan& plan, cudaStream_t s) {
+  using Cfg = ReduceCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(cudaFuncSetAttribute(gemm_reduce_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(plan.p.N / BN, cdiv(plan.p.Mrows, 128), plan.splits);
+  gemm_reduce_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapG, plan.p);
+  RD_LAUNCHED();
+  return 0;
+}
+
+int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s) {
+  if (!plan.valid) return fail("tc reduce: plan not built");
+  switch (plan.BN) {
+    case 256: return launch_reduce<256>(plan, s);
+    case 128: return launch_reduce<128>(plan, s);
+    case 64: return launch_reduce<64>(plan, s);
+    case 32: return launch_reduce<32>(plan, s);
+  }
+  return fail("tc reduce: unsupported BN=%d", plan.BN);
 }
 
 bool tc_available() { return encode_fn() != nullptr; }

@@ -30,10 +30,34 @@ struct TcRowsPlan {
   bool valid = false;
 };
 
+struct TcReduceParams {
+  int Mrows, Ca, N;      // output rows (tap, ca), channels per tap, GEMM N
+  int ntaps;
+  int tw, th, tb;        // pixel box of one K step (tw*th*tb == 32)
+  int tiles_w, tiles_h, tiles_b;
+  int coord_w, coord_h, coord_b;
+  int tap_off[9][4];
+  int boxes_per_split;
+  float* part;           // [splits][Mrows][N]
+};
+
+struct TcReducePlan {
+  CUtensorMap mapA, mapG;
+  TcReduceParams p;
+  int BN = 0, splits = 0;
+  bool valid = false;
+};
+
+bool tc_reduce_eligible(const Gather& g, int N);
+// src: tensor the gather reads (rows of the result); G: [pixels][N] matrix; part_floats: capacity of the split buffer
+int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, int B, const float* G, int N,
+                        float* part, size_t part_floats);
+int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s);
+
 bool tc_rows_eligible(const Gather& g, int N);
 int tc_pick_bn(int N);
 int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides_bytes,
-                  const int* box);
+                  const int* box, int swizzle_atom32);
 // src: activation tensor the gather reads; w_nk: packed weights [N][ntaps*C] (K contiguous)
 int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B, const float* w_nk, int N);
 int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partials, cudaStream_t s);

@@ -136,6 +136,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;        // SWIZZLE_128B
   return d;
 }
+// MN-major TF32 operands: 128-byte swizzle with 32-byte atomicity (layout type 1): atoms of 4 k-rows x 128 bytes;
+// LBO = distance to the next 32 M/N elements, SBO = distance between consecutive 4-row atoms along K.
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;        // descriptor version (Blackwell)
+  d |= (uint64_t)1 << 61;        // SWIZZLE_128B_BASE32B
+  return d;
+}
 // Instruction descriptor for kind::tf32 with fp32 accumulation, M x N tile, given operand majors (0 = K, 1 = MN)
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
