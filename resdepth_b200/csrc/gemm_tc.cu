@@ -13,6 +13,7 @@
 //   * persistent CTAs, static tile schedule with a fixed N tile per CTA so BatchNorm column sums accumulate in
 //     registers across all of a CTA's tiles (one partial row per CTA-warp instead of one per tile).
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -74,30 +75,32 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int kblocks = P.ntaps * P.cchunks;
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nt = tile % n_tiles;
-        int mt = tile / n_tiles;
-        const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
-        const int th_i = mt % P.tiles_h;
-        const int tb_i = mt / P.tiles_h;
-        const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
-        for (int tap = 0; tap < P.ntaps; ++tap) {
-          int c[4] = {P.tap_off[tap][0], P.tap_off[tap][1], P.tap_off[tap][2], P.tap_off[tap][3]};
-          c[P.coord_w] += w0;
-          c[P.coord_h] += h0;
-          if (P.coord_b >= 0) c[P.coord_b] += b0;
-          for (int cc = 0; cc < P.cchunks; ++cc) {
+    // ===== TMA producer: lane 0 waits for the slot and arms the barrier, then lane 0 issues the A box and
+    // lane 1 the B box (coordinates in registers, no indexed arrays) =====
+    const bool up2 = P.coord_b < 0;                   // (c, w, a, b*h) view of the 2x-upsampled tensor; else (c, w, h, b)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % n_tiles;
+      int mt = tile / n_tiles;
+      const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
+      const int th_i = mt % P.tiles_h;
+      const int tb_i = mt / P.tiles_h;
+      const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+      for (int tap = 0; tap < P.ntaps; ++tap) {
+        const int off0 = P.tap_off[tap][0], off1 = P.tap_off[tap][1], off2 = P.tap_off[tap][2];
+        for (int cc = 0; cc < P.cchunks; ++cc) {
+          if (lane == 0) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(sa, &mapA, &full_bar[stage], c[0] + cc * 32, c[1], c[2], c[3]);
-            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * 32, nt * BN);
-            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          if (lane == 0)
+            tma_load_4d(sa, &mapA, &full_bar[stage], off0 + cc * 32, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
+          else if (lane == 1)
+            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * 32, nt * BN);
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -394,7 +397,7 @@ struct ReduceCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN>
+template <int BN, bool EXPERIMENT_KMAJOR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapG,
                       const TcReduceParams P) {
@@ -430,46 +433,45 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   if (nchunks > 4) nchunks = 4;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int ctap[4], cch[4];
-      for (int mc = 0; mc < 4; ++mc) {
-        const int r = m0 + mc * 32;
-        ctap[mc] = r < P.Mrows ? r / P.Ca : 0;
-        cch[mc] = r < P.Mrows ? r % P.Ca : 0;
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int bx = box_begin; bx < box_end; ++bx) {
-        int t = bx;
-        const int tw_i = t % P.tiles_w; t /= P.tiles_w;
-        const int th_i = t % P.tiles_h;
-        const int tb_i = t / P.tiles_h;
-        const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+    // ===== TMA producer: lane i owns box i of every stage (A chunks 0..3, then the G chunks), so the
+    // per-instruction issue cost of the 4 KB boxes is spread over up to 12 lanes; all coordinates live in
+    // registers (no indexed arrays) =====
+    const bool is_a = lane < 4;
+    const bool active = is_a ? (lane < nchunks) : (lane < 4 + Cfg::NB);
+    int off0 = 0, off1 = 0, off2 = 0;
+    if (is_a) {
+      const int r = m0 + lane * 32;
+      const int tap = r < P.Mrows ? r / P.Ca : 0;
+      off0 = P.tap_off[tap][0] + (r < P.Mrows ? r % P.Ca : 0);
+      off1 = P.tap_off[tap][1];
+      off2 = P.tap_off[tap][2];
+    } else {
+      off0 = n0 + (lane - 4) * 32;
+    }
+    const CUtensorMap* map = is_a ? &mapA : &mapG;
+    const bool up2 = P.coord_b < 0;                   // (c, w, a, b*h) view; else (c, w, h, b)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int bx = box_begin; bx < box_end; ++bx) {
+      int t = bx;
+      const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+      const int th_i = t % P.tiles_h;
+      const int tb_i = t / P.tiles_h;
+      const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+      if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full_bar[stage], (nchunks + Cfg::NB) * BOX_BYTES);
-        for (int mc = 0; mc < nchunks; ++mc) {
-          int c[4] = {P.tap_off[ctap[mc]][0] + cch[mc], P.tap_off[ctap[mc]][1], P.tap_off[ctap[mc]][2],
-                      P.tap_off[ctap[mc]][3]};
-          c[P.coord_w] += w0;
-          c[P.coord_h] += h0;
-          if (P.coord_b >= 0) c[P.coord_b] += b0;
-          tma_load_4d(st + mc * BOX_BYTES, &mapA, &full_bar[stage], c[0], c[1], c[2], c[3]);
-        }
-#pragma unroll
-        for (int nb = 0; nb < Cfg::NB; ++nb) {
-          int c[4] = {n0 + nb * 32, 0, 0, 0};
-          c[P.coord_w] += w0;
-          c[P.coord_h] += h0;
-          if (P.coord_b >= 0) c[P.coord_b] += b0;
-          tma_load_4d(st + (4 + nb) * BOX_BYTES, &mapG, &full_bar[stage], c[0], c[1], c[2], c[3]);
-        }
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (active) {
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + lane * BOX_BYTES;
+        tma_load_4d(dst, map, &full_bar[stage], off0, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
+      }
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_tf32(128, BN, 1, 1);       // both operands MN-major
+      constexpr uint32_t idesc = EXPERIMENT_KMAJOR ? idesc_tf32(128, BN, 0, 0) : idesc_tf32(128, BN, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < nsteps; ++i) {
@@ -479,8 +481,10 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         const uint32_t sg = sa + 4 * BOX_BYTES;
 #pragma unroll
         for (int k = 0; k < KP / 8; ++k) {                         // 8 pixels = two 4-row swizzle atoms per MMA
-          const uint64_t da = smem_desc_mn_sw128_32b(sa + k * 1024, BOX_BYTES, 512);
-          const uint64_t dg = smem_desc_mn_sw128_32b(sg + k * 1024, BOX_BYTES, 512);
+          const uint64_t da = EXPERIMENT_KMAJOR ? smem_desc_sw128(sa + k * 32, 16, 1024)
+                                                : smem_desc_mn_sw128_32b(sa + k * 1024, BOX_BYTES, 512);
+          const uint64_t dg = EXPERIMENT_KMAJOR ? smem_desc_sw128(sg + k * 32, 16, 1024)
+                                                : smem_desc_mn_sw128_32b(sg + k * 1024, BOX_BYTES, 512);
           mma_tf32(tmem_base, da, dg, idesc, (i | k) != 0);
         }
         tc_commit(&empty_bar[stage]);
@@ -566,12 +570,14 @@ int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, i
   P.tiles_b = cdiv(Bg, P.tb);
   if (g.ups == 1) { box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb; }
   else { box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th; }
-  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 1));
-  RD_TRY(tc_encode_map(&plan->mapG, G, 4, gdims, gstrides, box, 1));
-  // split the pixel boxes so that ~2 waves of CTAs exist, bounded by the partial buffer
+  static const bool sw128_experiment = getenv("RD_EXPERIMENT_REDUCE_SW128") != nullptr;
+  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, sw128_experiment ? 0 : 1));
+  RD_TRY(tc_encode_map(&plan->mapG, G, 4, gdims, gstrides, box, sw128_experiment ? 0 : 1));
+  // split the pixel boxes so that the CTAs fill ONE wave of the 148 SMs (1 CTA per SM: the kernel is not
+  // persistent, a second partial wave would idle most of the chip), bounded by the partial buffer
   const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_b;
   const int tiles = cdiv(P.Mrows, 128) * (N / plan->BN);
-  int S = cdiv(148 * 2, tiles);
+  int S = 148 / tiles;
   if (S > total_boxes / 8) S = total_boxes / 8;         // at least 8 K steps per CTA
   if (S < 1) S = 1;
   const size_t per = (size_t)P.Mrows * N;
@@ -592,6 +598,15 @@ static int launch_reduce(const TcReducePlan& plan, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(plan.p.N / BN, cdiv(plan.p.Mrows, 128), plan.splits);
+  static const bool kmajor_experiment = getenv("RD_EXPERIMENT_REDUCE_KMAJOR") != nullptr;
+  if (kmajor_experiment) {
+    static bool attr2 = false;
+    if (!attr2) {
+      RD_CUDA(cudaFuncSetAttribute(gemm_reduce_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      attr2 = true;
+    }
+    gemm_reduce_tc_kernel<BN, true><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapG, plan.p);
+  } else
   gemm_reduce_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapG, plan.p);
   RD_LAUNCHED();
   return 0;
