@@ -81,6 +81,8 @@ struct rd_handle {
   size_t partials_floats = 0, scratch_floats = 0, part_floats = 0;
   std::vector<float*> g_skip;
   float *gy = nullptr, *gh = nullptr, *gp = nullptr;
+  float* xcol = nullptr;       // im2col expansion of the input for the first layer's tensor-core wgrad
+  int xcol_k = 0;
   // state of the last forward
   int fwd_batch = 0, fwd_tile = 0, fwd_mode = -1;
   bool tf32() const { return cfg.math_mode == RD_MATH_TF32; }
@@ -236,7 +238,10 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     h->gy = c.take(max_out);
     h->gh = c.take(max_out);
     h->gp = c.take(max_pool);
+    h->xcol_k = (h->enc[0].Cin * 9 + 31) / 32 * 32;
+    h->xcol = tf ? c.take((size_t)B * T * T * h->xcol_k) : nullptr;
   } else {
+    h->xcol = nullptr;
     h->part = nullptr; h->part_floats = 0;
     h->g_skip.assign(D, nullptr);
     h->gy = h->gh = h->gp = nullptr;
@@ -266,6 +271,11 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     b.tc = true;
     return 0;
   };
+  if (bwd && h->xcol && h->enc[0].Cout % 32 == 0) {
+    Gather g0 = gather_plain(T, T, h->xcol_k);
+    if (tc_reduce_eligible(g0, h->enc[0].Cout))
+      RD_TRY(tc_make_reduce_plan(&h->enc[0].tc_wgrad, h->xcol, g0, B, h->gy, h->enc[0].Cout, h->part, h->part_floats));
+  }
   for (int i = 1; i < D; ++i) RD_TRY(block(h->enc[i], h->enc[i - 1].p, T >> i));
   RD_TRY(block(h->bott, h->enc[D - 1].p, T >> D));
   for (int j = 0; j < D; ++j) {
@@ -579,7 +589,8 @@ namespace {
 // backward of one conv block.  g_full: gradient at the (un-pooled) block output, g_pool: gradient at the pooled
 // output; src_in: the block's input (NHWC) or, for the first encoder block, the network input x (NCHW).
 int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float* g_pool, int B, int H,
-                   const float* src_in, bool first, float* dgrad_out, int round_dgrad, cudaStream_t s) {
+                   const float* src_in, bool first, float* dgrad_out, int round_dgrad, float* dgrad_colsum,
+                   cudaStream_t s) {
   BnLayer L = bn_view(h, b);
   Act act = act_view(h, b);
   const int do_bn = h->cfg.do_bn;
@@ -595,11 +606,18 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
   }
   {
     ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (2.0 + gin), s);
-    RD_TRY(launch_bn_bwd_apply(g_full, g_pool, b.z, L, act, h->coef, h->gy, B, H, H, h->tf32() && b.tc, s));
+    RD_TRY(launch_bn_bwd_apply(g_full, g_pool, b.z, L, act, h->coef, h->gy, B, H, H,
+                               h->tf32() && (b.tc || b.tc_wgrad.valid), s));
   }
   if (first) {
     ProfScope ps(h, RD_PROF_FIRST_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
-    RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
+    if (b.tc_wgrad.valid) {
+      RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, h->xcol_k, 1, s));
+      RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, s));
+      RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, h->xcol_k, s));
+    } else {
+      RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
+    }
   } else {
     Gather g = gather_conv3x3(H, H, b.Cin);
     int S = 0;
@@ -618,12 +636,20 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
   if (dgrad_out) {
     Gather g = gather_conv3x3(H, H, b.Cout);
     Epilogue e{};
-    e.mode = EPI_PLAIN;
+    e.mode = dgrad_colsum ? EPI_STATS : EPI_PLAIN;       // column sums of dX = bias gradient of the up-conv before it
     e.out = dgrad_out;
+    e.partials = h->partials;
     e.round_tf32 = round_dgrad;
-    ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
-    if (b.tc) RD_TRY(launch_gemm_rows_tc(b.tc_dgrad, e, nullptr, s));
-    else RD_TRY(launch_gemm_rows_simt(h->gy, g, b.wd_kn, B, b.Cin, e, nullptr, s));
+    int npart = 0;
+    {
+      ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+      if (b.tc) RD_TRY(launch_gemm_rows_tc(b.tc_dgrad, e, &npart, s));
+      else RD_TRY(launch_gemm_rows_simt(h->gy, g, b.wd_kn, B, b.Cin, e, &npart, s));
+    }
+    if (dgrad_colsum) {
+      ProfScope ps(h, RD_PROF_BIAS_GRAD, 0.0, 0.0, s);
+      RD_TRY(launch_sum_partials(h->partials, npart, b.Cin, 2 * b.Cin, 2, dgrad_colsum, s));
+    }
   }
   return 0;
 }
@@ -645,7 +671,8 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     const double px = (double)B * T * T;
     ProfScope ps(h, RD_PROF_LAST_BWD, 2.0 * 2.0 * 9.0 * C0 * px, 4.0 * px * (2.0 * C0 + 1.0), s);
     RD_TRY(launch_conv_last_bwd(h->ups[D - 1].u, dy, h->P + h->last_w, h->g_skip[0], h->G + h->last_w,
-                                h->last_b >= 0 ? h->G + h->last_b : nullptr, h->scratch, h->scratch_floats, B, T, T, C0, s));
+                                h->last_b >= 0 ? h->G + h->last_b : nullptr, h->G + h->ups[D - 1].bias, h->scratch,
+                                h->scratch_floats, B, T, T, C0, s));
   }
   for (int j = D - 1; j >= 0; --j) {
     UpConv& u = h->ups[j];
@@ -653,10 +680,8 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     const float* Gu = h->g_skip[D - 1 - j];                  // gradient at u_j (and at skip a_{D-1-j})
     const float* X = j == 0 ? h->bott.a : h->dec[j - 1].a;   // input of the transposed conv
     const double px = (double)B * Hin * Hin, cc = (double)u.C * u.C;
-    {
-      ProfScope ps(h, RD_PROF_BIAS_GRAD, 0.0, 4.0 * 4.0 * px * u.C, s);
-      RD_TRY(launch_channel_sum(Gu, (long long)B * 4 * Hin * Hin, u.C, h->G + u.bias, h->scratch, h->scratch_floats, s));
-    }
+    // bias gradient = per-channel sum of du_j: produced by the kernel that wrote du_j (last-conv backward for the
+    // last level, the decoder conv's dgrad epilogue for the others)
     Gather g4 = gather_up2(Hin, Hin, u.C);
     int S = 0;
     {
@@ -681,17 +706,17 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
       else RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
     }
     if (j == 0) {
-      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, s));
+      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, nullptr, s));
     } else {
       // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded
       RD_TRY(block_backward(h, h->dec[j - 1], h->gh, nullptr, B, Hin, h->ups[j - 1].u, false, h->g_skip[D - j],
-                            h->tf32() && h->ups[j - 1].tc, s));
+                            h->tf32() && h->ups[j - 1].tc, h->G + h->ups[j - 1].bias, s));
     }
   }
   for (int i = D - 1; i >= 0; --i) {
     const int H = T >> i;
     RD_TRY(block_backward(h, h->enc[i], h->g_skip[i], h->gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
-                          i == 0 ? nullptr : h->gp, 0, s));
+                          i == 0 ? nullptr : h->gp, 0, nullptr, s));
   }
   return 0;
 }

@@ -54,8 +54,10 @@ int launch_conv_first_wgrad(const float* x, const float* dz, float* dw_oihw, flo
 int launch_conv_last_fwd(const float* u, const float* w_oihw, const float* bias, const float* x_nchw, int x_cstride_b,
                          float* y, int B, int H, int W, int C, cudaStream_t s);
 // backward of the last conv: du NHWC (written), dW (OIHW [1,C,3,3], written), dbias (written if non-null)
+//   du_channel_sum (optional, [C]): per-channel sums of du = bias gradient of the transposed conv that produced u
 int launch_conv_last_bwd(const float* u, const float* dy, const float* w_oihw, float* du, float* dw, float* dbias,
-                         float* scratch, size_t scratch_floats, int B, int H, int W, int C, cudaStream_t s);
+                         float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W, int C,
+                         cudaStream_t s);
 
 // ---- elementwise / reduction kernels -----------------------------------------------------------
 struct BnLayer {
@@ -97,6 +99,9 @@ int launch_sgd(float* p, const float* g, long long n, float lr, float wd, float 
 int launch_blend(const float* tiles, const float* mean, const float* std, const int32_t* geom, int n, int T,
                  int stride, double* raster, int rows, int cols, cudaStream_t s);
 int launch_fill(float* p, float v, long long n, cudaStream_t s);
+// out[i] = sum over p of part[p*row_stride + i*col_stride], i < n (double accumulation)
+int launch_sum_partials(const float* part, int nparts, int n, int row_stride, int col_stride, float* out,
+                        cudaStream_t s);
 
 // weight packing (see kernels_elementwise.cu for the layouts); null outputs are skipped
 int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, int Co, int Ci, int round_tf32,
@@ -106,6 +111,10 @@ int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int 
 //   conv: part [S][(t,ci)][co] -> dW OIHW ;  convT: part [S][(a,b,co)][ci] -> dW [ci][co][2][2]
 int launch_unpack_conv3x3_grad(const float* part, int S, float* dw, int Co, int Ci, cudaStream_t s);
 int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co, cudaStream_t s);
+// first-layer wgrad on tensor cores: im2col expansion of the NCHW input and un-packing of the reduce-GEMM result
+int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int round_tf32,
+                        cudaStream_t s);
+int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s);
 // column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)
 int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,
                        cudaStream_t s);

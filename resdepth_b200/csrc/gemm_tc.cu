@@ -23,7 +23,8 @@ namespace rd {
 
 using namespace tc;
 
-static constexpr int TC_THREADS = 192;
+static constexpr int TC_THREADS = 192;          // reduce kernel: TMA warp, MMA warp, 4 epilogue warps
+static constexpr int ROWS_THREADS = 320;        // rows kernel: TMA warp, MMA warp, 8 epilogue warps
 
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;
@@ -42,7 +43,7 @@ struct RowsCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TcRowsParams P) {
   using Cfg = RowsCfg<BN>;
@@ -60,7 +61,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
     for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -132,12 +133,15 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    // ===== 8 epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter take the even / odd
+    // 32-column chunks, doubling the loads and stores in flight for the HBM-bound layers =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    float cs1[BN / 32], cs2[BN / 32];
+    constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
+    float cs1[NCH2], cs2[NCH2];
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) cs1[i] = cs2[i] = 0.f;
+    for (int i = 0; i < NCH2; ++i) cs1[i] = cs2[i] = 0.f;
     const int iw = row % P.tw, ih = (row / P.tw) % P.th, ib = row / (P.tw * P.th);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -154,7 +158,9 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
       const size_t pix = ((size_t)b * P.Ho + h) * P.Wo + w;
 #pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ci = 0; ci < NCH2; ++ci) {
+        const int ch = 2 * ci + half;
+        if (ch >= NCH) break;
         float v[32];
         tmem_ld32(t_row + ch * 32, v);
         const int n = nt * BN + ch * 32;
@@ -195,8 +201,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               v[j] = valid ? v[j] : 0.f;
               sq[j] = v[j] * v[j];
             }
-            cs1[ch] += warp_colsum32(v, lane);
-            cs2[ch] += warp_colsum32(sq, lane);
+            cs1[ci] += warp_colsum32(v, lane);
+            cs2[ci] += warp_colsum32(sq, lane);
           }
         }
       }
@@ -212,10 +218,12 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       float* dst = P.partials + ((size_t)((blockIdx.x / n_tiles) * 4 + q) * P.N + nt * BN) * 2;
       const bool had_tiles = blockIdx.x < num_tiles;
 #pragma unroll
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ci = 0; ci < NCH2; ++ci) {
+        const int ch = 2 * ci + half;
+        if (ch >= NCH) break;
         const int col = ch * 32 + lane;
-        dst[col * 2 + 0] = had_tiles ? cs1[ch] : 0.f;
-        dst[col * 2 + 1] = had_tiles ? cs2[ch] : 0.f;
+        dst[col * 2 + 0] = had_tiles ? cs1[ci] : 0.f;
+        dst[col * 2 + 1] = had_tiles ? cs2[ci] : 0.f;
       }
     }
   }
@@ -346,7 +354,7 @@ static int launch_rows(const TcRowsPlan& plan, const TcRowsParams& P, int grid, 
     RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_rows_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
+  gemm_rows_tc_kernel<BN><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
   RD_LAUNCHED();
   return 0;
 }

@@ -242,9 +242,7 @@ int launch_conv_first_wgrad(const float* x, const float* dz, float* dw, float* s
 #undef RD_WG
   RD_LAUNCHED();
   const int n = Cout * ntaps;
-  reduce_partials_kernel<<<cdiv(n, 256), 256, 0, s>>>(scratch, grid, n, dw);
-  RD_LAUNCHED();
-  return 0;
+  return launch_sum_partials(scratch, grid, n, n, 1, dw, s);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -349,10 +347,11 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
                      int tiles_y, int ntiles) {
   __shared__ float dys[HALO_H * HALO_W];
   extern __shared__ float red_dyn[];                  // [16][RS]
-  constexpr int RS = 9 * 4 * 16 * QPL + 1;
+  constexpr int NDW = 9 * 4 * 16 * QPL;               // weight-gradient entries, then 64*QPL channel sums of du, then db
+  constexpr int RS = NDW + 4 * 16 * QPL + 1;
   const int tid = threadIdx.x;
   const int lane16 = tid & 15, grp = tid >> 4;
-  float4 wr[QPL][9], dwacc[QPL][9];
+  float4 wr[QPL][9], dwacc[QPL][9], dusum[QPL];
   float dbacc = 0.f;
 #pragma unroll
   for (int j = 0; j < QPL; ++j) {
@@ -363,6 +362,7 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
       else wr[j][k] = make_float4(0, 0, 0, 0);
       dwacc[j][k] = make_float4(0, 0, 0, 0);
     }
+    dusum[j] = make_float4(0, 0, 0, 0);
   }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     int t = tile;
@@ -402,6 +402,7 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
             dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
           }
           *reinterpret_cast<float4*>(du + o + c) = d;
+          dusum[j].x += d.x; dusum[j].y += d.y; dusum[j].z += d.z; dusum[j].w += d.w;
         }
       }
     }
@@ -415,51 +416,52 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
       float* rr = red_dyn + grp * RS + base;
       rr[0] = dwacc[j][k].x; rr[1] = dwacc[j][k].y; rr[2] = dwacc[j][k].z; rr[3] = dwacc[j][k].w;
     }
+#pragma unroll
+  for (int j = 0; j < QPL; ++j) {
+    float* rr = red_dyn + grp * RS + NDW + (j * 16 + lane16) * 4;
+    rr[0] = dusum[j].x; rr[1] = dusum[j].y; rr[2] = dusum[j].z; rr[3] = dusum[j].w;
+  }
   if (lane16 == 0) red_dyn[grp * RS + RS - 1] = dbacc;
   __syncthreads();
-  for (int i = tid; i < 9 * 4 * 16 * QPL + 1; i += 256) {
+  const size_t prow = (size_t)blockIdx.x * (C * 10 + 1);   // partial row: [C*9 dW][1 db][C channel sums of du]
+  for (int i = tid; i < RS; i += 256) {
     float a = 0.f;
 #pragma unroll
     for (int g = 0; g < 16; ++g) a += red_dyn[g * RS + i];
-    if (i == 9 * 4 * 16 * QPL) {
-      part[(size_t)blockIdx.x * (C * 9 + 1) + C * 9] = a;
+    if (i == RS - 1) {
+      part[prow + C * 9] = a;
+    } else if (i >= NDW) {
+      const int c = i - NDW;
+      if (c < C) part[prow + C * 9 + 1 + c] = a;
     } else {
       const int cc = i & 3, k = (i >> 2) % 9, ql = (i >> 2) / 9;   // ql = j*16 + lane16 = channel quad
       const int c = ql * 4 + cc;
-      if (c < C) part[(size_t)blockIdx.x * (C * 9 + 1) + c * 9 + k] = a;
+      if (c < C) part[prow + c * 9 + k] = a;
     }
   }
 }
 
-__global__ void last_bwd_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ dw,
-                                       float* __restrict__ dbias) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = C * 9 + 1;
-  if (i >= n) return;
-  double a = 0.0;
-  for (int p = 0; p < nparts; ++p) a += (double)part[(size_t)p * n + i];
-  if (i < C * 9) dw[i] = (float)a;
-  else if (dbias) dbias[0] = (float)a;
-}
-
 int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float* du, float* dw, float* dbias,
-                         float* scratch, size_t scratch_floats, int B, int H, int W, int C, cudaStream_t s) {
+                         float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W, int C,
+                         cudaStream_t s) {
   if (C % 4 || C > 128) return fail("conv_last_bwd: unsupported C=%d", C);
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
   const int ntiles = tiles_x * tiles_y * B;
   int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
-  if ((size_t)grid * (C * 9 + 1) > scratch_floats) return fail("conv_last_bwd: scratch too small");
+  const int PN = C * 10 + 1;
+  if ((size_t)grid * PN > scratch_floats) return fail("conv_last_bwd: scratch too small");
   if (C <= 64) {
-    const int smem = 16 * (9 * 4 * 16 * 1 + 1) * (int)sizeof(float);
+    const int smem = 16 * (10 * 4 * 16 * 1 + 1) * (int)sizeof(float);
     conv_last_bwd_kernel<1><<<grid, 256, smem, s>>>(u, dy, w, du, scratch, B, H, W, C, tiles_x, tiles_y, ntiles);
   } else {
-    const int smem = 16 * (9 * 4 * 16 * 2 + 1) * (int)sizeof(float);
+    const int smem = 16 * (10 * 4 * 16 * 2 + 1) * (int)sizeof(float);
     RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     conv_last_bwd_kernel<2><<<grid, 256, smem, s>>>(u, dy, w, du, scratch, B, H, W, C, tiles_x, tiles_y, ntiles);
   }
   RD_LAUNCHED();
-  last_bwd_finish_kernel<<<cdiv(C * 9 + 1, 128), 128, 0, s>>>(scratch, grid, C, dw, dbias);
-  RD_LAUNCHED();
+  RD_TRY(launch_sum_partials(scratch, grid, C * 9, PN, 1, dw, s));
+  if (dbias) RD_TRY(launch_sum_partials(scratch + C * 9, grid, 1, PN, 1, dbias, s));
+  if (du_channel_sum) RD_TRY(launch_sum_partials(scratch + C * 9 + 1, grid, C, PN, 1, du_channel_sum, s));
   return 0;
 }
 

@@ -38,18 +38,18 @@ static int ew_grid(long long work_items) {
 // ----------------------------------------------------------------------------------------------
 // BN finalize: partials [nparts][C][2] (sum, sumsq) -> mean / invstd / scale / shift
 // ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, int training, int do_bn,
                    const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ conv_bias, float* __restrict__ running_mean,
                    float* __restrict__ running_var, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                    float* __restrict__ scale, float* __restrict__ shift) {
-  __shared__ double red[8][32][2];
+  __shared__ double red[32][33][2];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
   if (do_bn && training && c < C) {
-    for (int p = pl; p < nparts; p += 8) {
+    for (int p = pl; p < nparts; p += 32) {
       const float2 v = *reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2);
       s1 += (double)v.x;
       s2 += (double)v.y;
@@ -67,7 +67,7 @@ bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double
   float mean, invstd;
   if (training) {
 #pragma unroll
-    for (int i = 1; i < 8; ++i) { s1 += red[i][cl][0]; s2 += red[i][cl][1]; }
+    for (int i = 1; i < 32; ++i) { s1 += red[i][cl][0]; s2 += red[i][cl][1]; }
     const double m = s1 / count;
     double var = s2 / count - m * m;
     if (var < 0.0) var = 0.0;
@@ -89,7 +89,7 @@ bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double
 
 int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int training,
                        int do_bn, cudaStream_t s) {
-  bn_finalize_kernel<<<cdiv(L.C, 32), 256, 0, s>>>(partials, nparts, L.C, (double)count, training, do_bn, L.gamma,
+  bn_finalize_kernel<<<cdiv(L.C, 32), 1024, 0, s>>>(partials, nparts, L.C, (double)count, training, do_bn, L.gamma,
                                                    L.beta, L.conv_bias, L.running_mean, L.running_var, L.mean,
                                                    L.invstd, L.scale, L.shift);
   RD_LAUNCHED();
@@ -338,17 +338,17 @@ int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* 
 }
 
 // partials [nparts][C][3] -> dgamma/dbeta (or conv dbias), PReLU slope grad partial, pass-2 coefficients
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double count, int do_bn,
                        int batch_stats, const float* __restrict__ gamma, const float* __restrict__ mean,
                        const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
                        float* __restrict__ dslope_part, BwdCoef* __restrict__ coef) {
-  __shared__ double red[8][32][3];
+  __shared__ double red[32][33][3];
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (c < C) {
-    for (int p = pl; p < nparts; p += 8) {
+    for (int p = pl; p < nparts; p += 32) {
       const float* v = partials + ((size_t)p * C + c) * 3;
       s1 += (double)v[0]; s2 += (double)v[1]; s3 += (double)v[2];
     }
@@ -357,7 +357,7 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, do
   __syncthreads();
   if (pl != 0) return;
 #pragma unroll
-  for (int i = 1; i < 8; ++i) { s1 += red[i][cl][0]; s2 += red[i][cl][1]; s3 += red[i][cl][2]; }
+  for (int i = 1; i < 32; ++i) { s1 += red[i][cl][0]; s2 += red[i][cl][1]; s3 += red[i][cl][2]; }
   if (c < C) {
     BwdCoef k;
     if (do_bn) {
@@ -397,7 +397,7 @@ int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, 
                            int batch_stats, float* dgamma, float* dbeta, float* dslope, float* dslope_scratch, void* coef,
                            cudaStream_t s) {
   const int nb = cdiv(L.C, 32);
-  bn_bwd_finalize_kernel<<<nb, 256, 0, s>>>(partials, nparts, L.C, (double)count, do_bn, batch_stats, L.gamma, L.mean,
+  bn_bwd_finalize_kernel<<<nb, 1024, 0, s>>>(partials, nparts, L.C, (double)count, do_bn, batch_stats, L.gamma, L.mean,
                                             L.invstd, dgamma, dbeta, dslope ? dslope_scratch : nullptr,
                                             reinterpret_cast<BwdCoef*>(coef));
   RD_LAUNCHED();
@@ -708,6 +708,57 @@ int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co
   return 0;
 }
 
+// First-layer weight gradient on tensor cores: the NCHW network input is expanded to an NHWC "im2col" tensor
+// xcol[b,h,w,k] with k = ci*9 + r*3 + s  (value x[b,ci,h+r-1,w+s-1], zero outside the image and for k >= Cin*9,
+// Kc = Cin*9 rounded up to 32) so that dW[co][k] = sum_p xcol[p][k] * dz[p][co] is a plain reduce GEMM.
+__global__ void __launch_bounds__(256)
+im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B, int Cin, int H, int W, int Kc,
+                    int rnd) {
+  const int KQ = Kc >> 2;
+  const long long total = (long long)B * H * W * KQ;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int kq = (int)(i % KQ);
+    long long p = i / KQ;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int b = (int)(p / H);
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kq * 4 + j;
+      float val = 0.f;
+      if (k < Cin * 9) {
+        const int ci = k / 9, t = k - ci * 9;
+        const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + (((size_t)b * Cin + ci) * H + hh) * W + ww);
+      }
+      v[j] = rnd ? tf32_rn(val) : val;
+    }
+    st4(xcol + i * 4, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int rnd, cudaStream_t s) {
+  im2col_first_kernel<<<ew_grid((long long)B * H * W * (Kc / 4)), 256, 0, s>>>(x, xcol, B, Cin, H, W, Kc, rnd);
+  RD_LAUNCHED();
+  return 0;
+}
+// part [S][Kc][Co] summed over S -> dW [Co][K] (K = Cin*9 <= Kc; OIHW flattening of the first conv)
+__global__ void unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co, int K,
+                                         int Kc) {
+  const int total = Co * K;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int co = i % Co, k = i / Co;
+    float a = 0.f;
+    for (int sp = 0; sp < S; ++sp) a += part[((size_t)sp * Kc + k) * Co + co];
+    dw[(size_t)co * K + k] = a;
+  }
+}
+int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s) {
+  unpack_first_grad_kernel<<<cdiv(Co * K, 256), 256, 0, s>>>(part, S, dw, Co, K, Kc);
+  RD_LAUNCHED();
+  return 0;
+}
+
 // out[c] = sum over pixels of g[p][c]
 __global__ void __launch_bounds__(256)
 channel_sum_kernel(const float* __restrict__ g, long long npix, int C, float* __restrict__ part) {
@@ -729,12 +780,29 @@ channel_sum_kernel(const float* __restrict__ g, long long npix, int C, float* __
     part[(size_t)blockIdx.x * C + i] = acc;
   }
 }
-__global__ void channel_sum_finish_kernel(const float* __restrict__ part, int nparts, int C, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// out[i] = sum_p part[p][i] (double accumulation): 32 columns x 32 partial lanes per block
+__global__ void __launch_bounds__(1024)
+sum_partials_kernel(const float* __restrict__ part, int nparts, int n, int row_stride, int col_stride,
+                    float* __restrict__ out) {
+  __shared__ double red[32][33];
+  const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + cl;
   double a = 0.0;
-  for (int p = 0; p < nparts; ++p) a += (double)part[(size_t)p * C + c];
-  out[c] = (float)a;
+  if (i < n)
+    for (int p = pl; p < nparts; p += 32) a += (double)part[(size_t)p * row_stride + (size_t)i * col_stride];
+  red[pl][cl] = a;
+  __syncthreads();
+  if (pl == 0 && i < n) {
+#pragma unroll
+    for (int k = 1; k < 32; ++k) a += red[k][cl];
+    out[i] = (float)a;
+  }
+}
+int launch_sum_partials(const float* part, int nparts, int n, int row_stride, int col_stride, float* out,
+                        cudaStream_t s) {
+  sum_partials_kernel<<<cdiv(n, 32), 1024, 0, s>>>(part, nparts, n, row_stride, col_stride, out);
+  RD_LAUNCHED();
+  return 0;
 }
 int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,
                        cudaStream_t s) {
@@ -746,9 +814,7 @@ int launch_channel_sum(const float* g, long long npix, int C, float* out, float*
   if ((size_t)grid * C > scratch_floats) return fail("channel_sum: scratch too small");
   channel_sum_kernel<<<grid, 256, (size_t)PL * C * sizeof(float), s>>>(g, npix, C, scratch);
   RD_LAUNCHED();
-  channel_sum_finish_kernel<<<cdiv(C, 128), 128, 0, s>>>(scratch, grid, C, out);
-  RD_LAUNCHED();
-  return 0;
+  return launch_sum_partials(scratch, grid, C, C, 1, out, s);
 }
 
 // NCHW [B,1,H,W] BatchNorm on channel 0 of the input for outer_skip_BN is handled by the host wrapper (1 channel).
