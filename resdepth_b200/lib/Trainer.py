@@ -25,6 +25,7 @@ import torch
 
 from .. import _native
 from .AverageMeter import AverageMeter
+from .distributed import allreduce_gradients
 from .optim import fuse_optimizer
 from .UNet import UNet
 
@@ -239,10 +240,8 @@ class Trainer(object):
             loss, dy = self._compute_denormalized_loss(y_pred, y, loss_mask, mean, std, want_grad=train)
             if train:
                 grads = self.model._backward_native(x, dy, detach_copy=False)
-                if self.distributed and self.world_size > 1:
-                    # the ONE collective of the path: sum the flat gradient arena over ranks (NCCL / NVLink)
-                    torch.distributed.all_reduce(self.model._rt['grads'], op=torch.distributed.ReduceOp.SUM)
-                    self.optimizer.grad_scale = 1.0 / self.world_size
+                # the ONE collective of the path: sum the flat gradient arena over ranks (NCCL / NVLink)
+                self.optimizer.grad_scale = allreduce_gradients(self.model._rt['grads'])
                 for p, g in zip(self.model.parameters(), grads):
                     p.grad = g
         return loss

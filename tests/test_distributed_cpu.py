@@ -1,0 +1,64 @@
+"""CPU, world_size 2, gloo: the host-side logic of the data-parallel path (batch sharding, the single gradient
+all-reduce and the 1/world scale handed to the fused optimizer)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from resdepth_b200.lib.distributed import allreduce_gradients, shard_batch, shard_bounds, world
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world_size, port, out_dir):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world_size))
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    try:
+        assert world() == (rank, world_size)
+        g = torch.Generator().manual_seed(0)
+        full = {'input': torch.randn(5, 3, 8, 8, generator=g), 'target': torch.randn(5, 1, 8, 8, generator=g),
+                'dsm_std': torch.full((5,), 3.5), 'tile_size': 8}
+        mine = shard_batch(full, rank, world_size)
+        lo, hi = shard_bounds(5, rank, world_size)
+        assert mine['input'].shape[0] == hi - lo and mine['tile_size'] == 8
+        assert torch.equal(mine['input'], full['input'][lo:hi])
+        # per-rank "gradient arena": the sum over ranks must equal the gradient of the whole batch
+        grads = torch.stack([full['input'][i].sum() * torch.arange(16.) for i in range(lo, hi)]).sum(0)
+        scale = allreduce_gradients(grads)
+        expect = sum(full['input'][i].sum() for i in range(5)) * torch.arange(16.)
+        assert abs(scale - 1.0 / world_size) < 1e-12
+        assert torch.allclose(grads, expect, rtol=1e-5, atol=1e-5)
+        torch.save({'grads': grads, 'scale': scale}, os.path.join(out_dir, f'rank{rank}.pt'))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_gloo(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = torch.load(tmp_path / 'rank0.pt')
+    b = torch.load(tmp_path / 'rank1.pt')
+    assert torch.equal(a['grads'], b['grads']) and a['scale'] == b['scale'] == 0.5
+
+
+def test_shard_bounds_cover_the_batch():
+    for n in (1, 5, 64, 65):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def test_single_process_is_a_no_op():
+    g = torch.ones(8)
+    assert allreduce_gradients(g) == 1.0 and torch.equal(g, torch.ones(8))
