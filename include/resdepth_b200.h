@@ -26,12 +26,13 @@
 extern "C" {
 #endif
 
-#define RD_ABI_VERSION 1
+#define RD_ABI_VERSION 2
 
 typedef struct rd_handle rd_handle;
 
 enum { RD_ACT_RELU = 0, RD_ACT_LRELU = 1, RD_ACT_PRELU = 2 };      /* lib/UNet.py:27-33 */
 enum { RD_MATH_FP32 = 0, RD_MATH_TF32 = 1 };  /* CUDA-core fp32 FMA | tcgen05 kind::tf32 */
+enum { RD_UP_TRANSPOSE = 0, RD_UP_BILINEAR = 1 };                  /* lib/UNet.py:17-24 */
 /* rd_forward modes: model.eval() under no_grad | model.train() | model.eval() with autograd recording */
 enum { RD_FWD_EVAL = 0, RD_FWD_TRAIN = 1, RD_FWD_EVAL_SAVE = 2 };
 
@@ -45,8 +46,9 @@ typedef struct rd_config {
   int32_t do_bn;
   int32_t bias_conv_layer;    /* bias of last_layer, lib/UNet.py:184 */
   int32_t outer_skip;
-  int32_t outer_skip_bn;      /* not supported by the CUDA path yet: rd_create fails */
+  int32_t outer_skip_bn;      /* BatchNorm2d(1) on input channel 0 before the outer residual, lib/UNet.py:192-193 */
   int32_t math_mode;          /* RD_MATH_* for the GEMM-shaped layers */
+  int32_t up_mode;            /* RD_UP_* */
 } rd_config;
 
 int rd_abi_version(void);

@@ -14,7 +14,8 @@ _LOCK = threading.Lock()
 ACT_IDS = {'relu': 0, 'lrelu': 1, 'prelu': 2}          # RD_ACT_*
 MATH_FP32, MATH_TF32 = 0, 1                             # RD_MATH_*
 FWD_EVAL, FWD_TRAIN, FWD_EVAL_SAVE = 0, 1, 2            # RD_FWD_*
-ABI_VERSION = 1
+UP_IDS = {'transpose': 0, 'bilinear': 1}                # RD_UP_*
+ABI_VERSION = 2
 
 # every symbol include/resdepth_b200.h declares
 EXPORTED_SYMBOLS = (
@@ -30,7 +31,7 @@ PROF_NUM = 18                                           # RD_PROF_NUM
 class RdConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'n_input_channels', 'start_kernel', 'max_filter_depth', 'depth', 'act_encoder', 'act_decoder',
-        'act_bottleneck', 'do_bn', 'bias_conv_layer', 'outer_skip', 'outer_skip_bn', 'math_mode')]
+        'act_bottleneck', 'do_bn', 'bias_conv_layer', 'outer_skip', 'outer_skip_bn', 'math_mode', 'up_mode')]
 
 
 def library_path() -> str:

@@ -46,10 +46,13 @@ struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottl
   TcReducePlan tc_wgrad;
 };
 
-struct UpConv {        // ConvTranspose2d(C, C, 2, 2) (lib/UNet.py:17-24)
+struct UpConv {        // ConvTranspose2d(C, C, 2, 2), or Upsample(bilinear, x2) + Conv2d 1x1 (lib/UNet.py:17-24)
   int C = 0;
+  bool bilinear = false;
   long long w = -1, bias = -1;
   float *u = nullptr;
+  float *t = nullptr;      // bilinear: 1x1-conv output at the low resolution
+  // transposed: w_kn = [ci][(ab,co)], w_nk = its transpose;  bilinear: w_kn = W^T = [ci][co], w_nk = W = [co][ci]
   float *w_kn = nullptr, *w_nk = nullptr;
   bool tc = false;
   TcRowsPlan tc_fwd, tc_dgrad;
@@ -83,6 +86,10 @@ struct rd_handle {
   float *gy = nullptr, *gh = nullptr, *gp = nullptr;
   float* xcol = nullptr;       // im2col expansion of the input for the first layer's tensor-core wgrad
   int xcol_k = 0;
+  float* gt = nullptr;         // bilinear up-mode: gradient at the low-resolution 1x1-conv output
+  // outer_skip_BN: BatchNorm2d(1) on input channel 0
+  long long ob_gamma = -1, ob_beta = -1, ob_rm = -1, ob_rv = -1;
+  float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
   // state of the last forward
   int fwd_batch = 0, fwd_tile = 0, fwd_mode = -1;
   bool tf32() const { return cfg.math_mode == RD_MATH_TF32; }
@@ -222,6 +229,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     u.u = c.take((size_t)B * Hout * Hout * u.C);
     u.w_kn = c.take((size_t)4 * u.C * u.C);
     u.w_nk = c.take((size_t)4 * u.C * u.C);
+    u.t = u.bilinear ? c.take((size_t)B * (Hout / 2) * (Hout / 2) * u.C) : nullptr;
     if (j < D - 1) block(h->dec[j], Hout, false);
   }
   h->partials_floats = (size_t)2 << 20;
@@ -230,6 +238,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   h->scratch = c.take(h->scratch_floats);
   h->coef = c.take(4 * 2048);
   h->consts = c.take(64);
+  h->ob_mean = c.take(4); h->ob_invstd = c.take(4); h->ob_affine = c.take(4);
   if (bwd) {
     h->part_floats = (size_t)8 << 20;
     h->part = c.take(h->part_floats);
@@ -238,10 +247,12 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     h->gy = c.take(max_out);
     h->gh = c.take(max_out);
     h->gp = c.take(max_pool);
+    h->gt = h->cfg.up_mode == RD_UP_BILINEAR ? c.take(max_out / 4 + 64) : nullptr;
     h->xcol_k = (h->enc[0].Cin * 9 + 31) / 32 * 32;
     h->xcol = tf ? c.take((size_t)B * T * T * h->xcol_k) : nullptr;
   } else {
     h->xcol = nullptr;
+    h->gt = nullptr;
     h->part = nullptr; h->part_floats = 0;
     h->g_skip.assign(D, nullptr);
     h->gy = h->gh = h->gp = nullptr;
@@ -284,7 +295,17 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     const float* src = j == 0 ? h->bott.a : h->dec[j - 1].a;
     Gather gf = gather_plain(Hin, Hin, u.C);
     Gather gd = gather_up2(Hin, Hin, u.C);
-    if (tc_rows_eligible(gf, 4 * u.C) && tc_rows_eligible(gd, u.C)) {
+    if (u.bilinear) {
+      if (tc_rows_eligible(gf, u.C)) {
+        RD_TRY(tc_make_rows_plan(&u.tc_fwd, src, gf, B, u.w_nk, u.C));
+        if (bwd) {
+          RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->gt, gf, B, u.w_kn, u.C));
+          if (tc_reduce_eligible(gf, u.C))
+            RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, src, gf, B, h->gt, u.C, h->part, h->part_floats));
+        }
+        u.tc = true;
+      }
+    } else if (tc_rows_eligible(gf, 4 * u.C) && tc_rows_eligible(gd, u.C)) {
       RD_TRY(tc_make_rows_plan(&u.tc_fwd, src, gf, B, u.w_nk, 4 * u.C));
       if (bwd) {
         RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
@@ -330,13 +351,18 @@ int pack_weights(rd_handle* h, bool for_backward, cudaStream_t s) {
   ProfScope ps(h, RD_PROF_PACK, 0.0, 4.0 * 3.0 * (double)h->param_floats, s);
   auto block = [&](ConvBlock& b) -> int {
     if (!b.w_kn) return 0;
-    return launch_pack_conv3x3(h->P + b.w, b.w_kn, b.w_nk, for_backward ? b.wd_kn : nullptr,
-                               for_backward ? b.wd_nk : nullptr, b.Cout, b.Cin, rnd && b.tc, s);
+    // tcgen05 layers read the [N][K] copies, CUDA-core layers the [K][N] copies: pack only what is used
+    return launch_pack_conv3x3(h->P + b.w, b.tc ? nullptr : b.w_kn, b.tc ? b.w_nk : nullptr,
+                               for_backward && !b.tc ? b.wd_kn : nullptr, for_backward && b.tc ? b.wd_nk : nullptr,
+                               b.Cout, b.Cin, rnd && b.tc, s);
   };
   for (auto& b : h->enc) RD_TRY(block(b));
   RD_TRY(block(h->bott));
   for (auto& b : h->dec) RD_TRY(block(b));
-  for (auto& u : h->ups) RD_TRY(launch_pack_convt(h->P + u.w, u.w_kn, u.w_nk, u.C, u.C, rnd && u.tc, s));
+  for (auto& u : h->ups) {
+    if (u.bilinear) RD_TRY(launch_pack_conv1x1(h->P + u.w, u.w_nk, u.w_kn, u.C, u.C, rnd && u.tc, s));
+    else RD_TRY(launch_pack_convt(h->P + u.w, u.w_kn, u.w_nk, u.C, u.C, rnd && u.tc, s));
+  }
   return 0;
 }
 
@@ -387,7 +413,7 @@ int rd_create(const rd_config* cfg, int device, rd_handle** out) {
   if (cfg->start_kernel > 128) return fail("start_kernel=%d > 128 is not supported by the full-resolution kernels", cfg->start_kernel);
   if (cfg->max_filter_depth % 32 || cfg->max_filter_depth < cfg->start_kernel || cfg->max_filter_depth > 1024)
     return fail("max_filter_depth=%d must be a multiple of 32 in [start_kernel, 1024]", cfg->max_filter_depth);
-  if (cfg->outer_skip_bn) return fail("outer_skip_BN=True is not supported by the CUDA path");
+  if (cfg->up_mode != RD_UP_TRANSPOSE && cfg->up_mode != RD_UP_BILINEAR) return fail("unknown up_mode %d", cfg->up_mode);
   for (int a : {cfg->act_encoder, cfg->act_decoder, cfg->act_bottleneck})
     if (a < RD_ACT_RELU || a > RD_ACT_PRELU) return fail("unknown activation id %d", a);
   if (cfg->math_mode != RD_MATH_FP32 && cfg->math_mode != RD_MATH_TF32) return fail("unknown math mode %d", cfg->math_mode);
@@ -410,19 +436,23 @@ int rd_create(const rd_config* cfg, int device, rd_handle** out) {
   for (int j = 0; j < D; ++j) {
     const int C = h->widths[D - 1 - j];
     h->ups[j].C = C;
-    if (j < D - 1) {
-      const std::string p = "decoder." + std::to_string(j);
-      add_param(h, p + ".0.weight", (long long)C * C * 4, &h->ups[j].w);
-      add_param(h, p + ".0.bias", C, &h->ups[j].bias);
-      plan_block(h, h->dec[j], p + ".1", C, h->widths[D - 2 - j], cfg->act_decoder, false);
-    } else {
-      const std::string p = "decoder." + std::to_string(j);
-      add_param(h, p + ".weight", (long long)C * C * 4, &h->ups[j].w);
-      add_param(h, p + ".bias", C, &h->ups[j].bias);
-    }
+    const bool bil = cfg->up_mode == RD_UP_BILINEAR;
+    h->ups[j].bilinear = bil;
+    // transposed: the ConvTranspose2d itself; bilinear: Sequential(Upsample, Conv2d 1x1) -> ".1" is the conv
+    const std::string p = "decoder." + std::to_string(j) + (j < D - 1 ? ".0" : "") + (bil ? ".1" : "");
+    add_param(h, p + ".weight", (long long)C * C * (bil ? 1 : 4), &h->ups[j].w);
+    add_param(h, p + ".bias", C, &h->ups[j].bias);
+    if (j < D - 1)
+      plan_block(h, h->dec[j], "decoder." + std::to_string(j) + ".1", C, h->widths[D - 2 - j], cfg->act_decoder, false);
   }
   add_param(h, "last_layer.weight", (long long)cfg->start_kernel * 9, &h->last_w);
   if (cfg->bias_conv_layer) add_param(h, "last_layer.bias", 1, &h->last_b);
+  if (cfg->outer_skip && cfg->outer_skip_bn) {                       // lib/UNet.py:189-194
+    add_param(h, "layer_outer_skip.0.weight", 1, &h->ob_gamma);
+    add_param(h, "layer_outer_skip.0.bias", 1, &h->ob_beta);
+    add_buffer(h, "layer_outer_skip.0.running_mean", 1, &h->ob_rm);
+    add_buffer(h, "layer_outer_skip.0.running_var", 1, &h->ob_rv);
+  }
   *out = h;
   return 0;
 }
@@ -506,7 +536,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
   if (!h || !x || !y) return fail("rd_forward: null argument");
   if (!h->P) return fail("rd_forward: parameters not bound (rd_bind)");
   if (mode < RD_FWD_EVAL || mode > RD_FWD_EVAL_SAVE) return fail("rd_forward: bad mode %d", mode);
-  if (h->cfg.do_bn && !h->BUF) return fail("rd_forward: BatchNorm buffers not bound");
+  if ((h->cfg.do_bn || h->ob_gamma >= 0) && !h->BUF) return fail("rd_forward: BatchNorm buffers not bound");
   RD_CUDA(cudaSetDevice(h->device));
   const int save = mode != RD_FWD_EVAL;
   RD_TRY(rd_reserve(h, batch, tile, save));
@@ -548,7 +578,17 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     e.bias = h->P + u.bias;
     e.skip = h->enc[D - 1 - j].a;                       // additive skip, lib/UNet.py:96-101,220,224
     e.round_tf32 = (j < D - 1) ? tf : 0;
-    {
+    if (u.bilinear) {
+      // conv1x1(upsample(h)) == upsample(conv1x1(h)): 1-tap GEMM at the low resolution, then interpolate + bias + skip
+      const double px = (double)B * Hc * Hc;
+      ProfScope ps(h, RD_PROF_CONVT_FWD, 2.0 * u.C * u.C * px, 4.0 * px * u.C * (1.0 + 4.0 + 4.0), s);
+      Epilogue ep{};
+      ep.mode = EPI_PLAIN;
+      ep.out = u.t;
+      if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_fwd, ep, nullptr, s));
+      else RD_TRY(launch_gemm_rows_simt(cur, g, u.w_kn, B, u.C, ep, nullptr, s));
+      RD_TRY(launch_bilinear_up_add(u.t, e.bias, e.skip, u.u, B, Hc, Hc, u.C, e.round_tf32, s));
+    } else {
       const double px = (double)B * Hc * Hc;
       ProfScope ps(h, RD_PROF_CONVT_FWD, 2.0 * 4.0 * u.C * u.C * px, 4.0 * px * u.C * (1.0 + 4.0 + 4.0), s);
       if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_fwd, e, nullptr, s));
@@ -566,8 +606,21 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
   {
     const double px = (double)B * T * T;
     ProfScope ps(h, RD_PROF_LAST_FWD, 2.0 * 9.0 * C0 * px, 4.0 * px * (C0 + 2.0), s);
+    const float* x_affine = nullptr;
+    if (h->ob_gamma >= 0) {                                   // outer_skip_BN: BatchNorm2d(1) on channel 0 of x
+      int nparts = 0;
+      if (train) RD_TRY(launch_outer_bn_reduce(x, nullptr, nullptr, h->partials, &nparts, B, h->cfg.n_input_channels, T * T, s));
+      BnLayer L{};
+      L.C = 1;
+      L.gamma = h->P + h->ob_gamma; L.beta = h->P + h->ob_beta;
+      L.running_mean = h->BUF + h->ob_rm; L.running_var = h->BUF + h->ob_rv;
+      L.mean = h->ob_mean; L.invstd = h->ob_invstd; L.scale = h->ob_affine; L.shift = h->ob_affine + 1;
+      RD_TRY(launch_bn_finalize(L, h->partials, nparts, (long long)B * T * T, train, 1, s));
+      x_affine = h->ob_affine;
+    }
     RD_TRY(launch_conv_last_fwd(h->ups[D - 1].u, h->P + h->last_w, h->last_b >= 0 ? h->P + h->last_b : nullptr,
-                                h->cfg.outer_skip ? x : nullptr, h->cfg.n_input_channels * T * T, y, B, T, T, C0, s));
+                                h->cfg.outer_skip ? x : nullptr, h->cfg.n_input_channels * T * T, x_affine, y, B, T, T,
+                                C0, s));
   }
   if (save) { h->fwd_batch = B; h->fwd_tile = T; h->fwd_mode = mode; }
   return 0;
@@ -631,7 +684,7 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
       }
     }
     ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), s);
-    RD_TRY(launch_unpack_conv3x3_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, s));
+    RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, 9, s));
   }
   if (dgrad_out) {
     Gather g = gather_conv3x3(H, H, b.Cout);
@@ -674,6 +727,11 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
                                 h->last_b >= 0 ? h->G + h->last_b : nullptr, h->G + h->ups[D - 1].bias, h->scratch,
                                 h->scratch_floats, B, T, T, C0, s));
   }
+  if (h->ob_gamma >= 0) {
+    int nparts = 0;
+    RD_TRY(launch_outer_bn_reduce(x, dy, h->ob_mean, h->partials, &nparts, B, h->cfg.n_input_channels, T * T, s));
+    RD_TRY(launch_outer_bn_bwd_finalize(h->partials, nparts, h->ob_invstd, h->G + h->ob_gamma, h->G + h->ob_beta, s));
+  }
   for (int j = D - 1; j >= 0; --j) {
     UpConv& u = h->ups[j];
     const int Hin = T >> (D - j);
@@ -682,6 +740,29 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     const double px = (double)B * Hin * Hin, cc = (double)u.C * u.C;
     // bias gradient = per-channel sum of du_j: produced by the kernel that wrote du_j (last-conv backward for the
     // last level, the decoder conv's dgrad epilogue for the others)
+    if (u.bilinear) {
+      Gather g1 = gather_plain(Hin, Hin, u.C);
+      int S = 0;
+      RD_TRY(launch_bilinear_up_adjoint(Gu, h->gt, B, Hin, Hin, u.C, h->tf32() && u.tc, s));
+      {
+        ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * cc * px, 4.0 * px * u.C * 2.0, s);
+        if (u.tc_wgrad.valid) {
+          RD_TRY(launch_gemm_reduce_tc(u.tc_wgrad, s));
+          S = u.tc_wgrad.splits;
+        } else {
+          RD_TRY(launch_gemm_reduce_simt(X, g1, h->gt, B, u.C, h->part, h->part_floats, &S, s));
+        }
+      }
+      RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + u.w, u.C, u.C, 1, s));
+      Epilogue e{};
+      e.mode = EPI_PLAIN;
+      e.out = h->gh;
+      {
+        ProfScope ps(h, RD_PROF_CONVT_DGRAD, 2.0 * cc * px, 4.0 * px * u.C * 2.0, s);
+        if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_dgrad, e, nullptr, s));
+        else RD_TRY(launch_gemm_rows_simt(h->gt, g1, u.w_nk, B, u.C, e, nullptr, s));
+      }
+    } else {
     Gather g4 = gather_up2(Hin, Hin, u.C);
     int S = 0;
     {
@@ -704,6 +785,7 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
       ProfScope ps(h, RD_PROF_CONVT_DGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
       if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_dgrad, e, nullptr, s));
       else RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
+    }
     }
     if (j == 0) {
       RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, nullptr, s));

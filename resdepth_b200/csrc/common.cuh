@@ -51,8 +51,9 @@ int launch_conv_first_fwd(const float* x, const float* w_oihw, float* z, float* 
 int launch_conv_first_wgrad(const float* x, const float* dz, float* dw_oihw, float* scratch, size_t scratch_floats,
                             int B, int Cin, int H, int W, int Cout, cudaStream_t s);
 // last conv C->1 (+bias +residual x[:,0]):  u NHWC [B,H,W,C] -> y [B,H,W]
+//   x_affine (optional, 2 floats: scale, shift): the residual is x0*scale+shift (outer_skip_BN)
 int launch_conv_last_fwd(const float* u, const float* w_oihw, const float* bias, const float* x_nchw, int x_cstride_b,
-                         float* y, int B, int H, int W, int C, cudaStream_t s);
+                         const float* x_affine, float* y, int B, int H, int W, int C, cudaStream_t s);
 // backward of the last conv: du NHWC (written), dW (OIHW [1,C,3,3], written), dbias (written if non-null)
 //   du_channel_sum (optional, [C]): per-channel sums of du = bias gradient of the transposed conv that produced u
 int launch_conv_last_bwd(const float* u, const float* dy, const float* w_oihw, float* du, float* dw, float* dbias,
@@ -109,8 +110,21 @@ int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float*
 int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int round_tf32, cudaStream_t s);
 // reduce split partials and un-pack to the PyTorch layouts
 //   conv: part [S][(t,ci)][co] -> dW OIHW ;  convT: part [S][(a,b,co)][ci] -> dW [ci][co][2][2]
-int launch_unpack_conv3x3_grad(const float* part, int S, float* dw, int Co, int Ci, cudaStream_t s);
+int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s);
 int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co, cudaStream_t s);
+// outer_skip_BN (BatchNorm2d(1) on input channel 0): statistics / backward reductions over x[:,0] (NCHW)
+//   dy == null: partials (sum x0, sum x0^2) in the [nparts][1][2] layout of launch_bn_finalize
+//   dy != null: partials (sum dy, sum dy*(x0-mean))
+int launch_outer_bn_reduce(const float* x, const float* dy, const float* mean, float* partials, int* n_partials, int B,
+                           int Cin, int HW, cudaStream_t s);
+int launch_outer_bn_bwd_finalize(const float* partials, int nparts, const float* invstd, float* dgamma, float* dbeta,
+                                 cudaStream_t s);
+// up_mode='bilinear': x2 bilinear interpolation (+bias +skip) of the low-resolution 1x1-conv output, and its adjoint
+int launch_bilinear_up_add(const float* t, const float* bias, const float* skip, float* u, int B, int Hin, int Win,
+                           int C, int round_tf32, cudaStream_t s);
+int launch_bilinear_up_adjoint(const float* du, float* dt, int B, int Hin, int Win, int C, int round_tf32,
+                               cudaStream_t s);
+int launch_pack_conv1x1(const float* w, float* w_copy, float* w_t, int Co, int Ci, int round_tf32, cudaStream_t s);
 // first-layer wgrad on tensor cores: im2col expansion of the NCHW input and un-packing of the reduce-GEMM result
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int round_tf32,
                         cudaStream_t s);

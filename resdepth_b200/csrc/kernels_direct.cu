@@ -253,8 +253,8 @@ int launch_conv_first_wgrad(const float* x, const float* dz, float* dw, float* s
 template <int QPL>
 __global__ void __launch_bounds__(256)
 conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
-                     const float* __restrict__ x0, long long x_bstride, float* __restrict__ y, int B, int H,
-                     int W, int C, int tiles_x, int tiles_y) {
+                     const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
+                     float* __restrict__ y, int B, int H, int W, int C, int tiles_x, int tiles_y) {
   __shared__ float ts[HALO_H * HALO_W][9];
   const int tid = threadIdx.x;
   const int lane16 = tid & 15, grp = tid >> 4;
@@ -317,21 +317,24 @@ conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, c
 #pragma unroll
         for (int s = 0; s < 3; ++s) a += ts[(lh + r) * HALO_W + lw + s][r * 3 + s];
       const size_t o = ((size_t)b * H + gh) * W + gw;
-      if (x0) a += x0[(size_t)b * x_bstride + (size_t)gh * W + gw];
+      if (x0) {
+        const float xv = x0[(size_t)b * x_bstride + (size_t)gh * W + gw];
+        a += x_affine ? fmaf(xv, x_affine[0], x_affine[1]) : xv;
+      }
       y[o] = a;
     }
   }
 }
 
 int launch_conv_last_fwd(const float* u, const float* w, const float* bias, const float* x, int x_bstride,
-                         float* y, int B, int H, int W, int C, cudaStream_t s) {
+                         const float* x_affine, float* y, int B, int H, int W, int C, cudaStream_t s) {
   if (C % 4 || C > 128) return fail("conv_last: unsupported C=%d (needs C%%4==0, C<=128)", C);
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
   const int grid = tiles_x * tiles_y * B;
   if (C <= 64)
-    conv_last_fwd_kernel<1><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, y, B, H, W, C, tiles_x, tiles_y);
+    conv_last_fwd_kernel<1><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
   else
-    conv_last_fwd_kernel<2><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, y, B, H, W, C, tiles_x, tiles_y);
+    conv_last_fwd_kernel<2><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
   RD_LAUNCHED();
   return 0;
 }

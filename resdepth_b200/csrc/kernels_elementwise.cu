@@ -671,8 +671,8 @@ int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int 
 
 // gradient un-packing: part [S][(t,ci)][co] summed over S -> dW OIHW
 __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co,
-                                           int Ci) {
-  const long long total = (long long)Co * Ci * 9;
+                                           int Ci, int ntaps) {
+  const long long total = (long long)Co * Ci * ntaps;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     // i indexes the packed layout (coalesced reads); scatter to OIHW
     const int co = (int)(i % Co);
@@ -680,11 +680,11 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ part, int S
     const int t = (int)(i / ((long long)Co * Ci));
     float a = 0.f;
     for (int sp = 0; sp < S; ++sp) a += part[(size_t)sp * total + i];
-    dw[((size_t)co * Ci + ci) * 9 + t] = a;
+    dw[((size_t)co * Ci + ci) * ntaps + t] = a;
   }
 }
-int launch_unpack_conv3x3_grad(const float* part, int S, float* dw, int Co, int Ci, cudaStream_t s) {
-  unpack_conv3x3_grad_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(part, S, dw, Co, Ci);
+int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s) {
+  unpack_conv3x3_grad_kernel<<<ew_grid((long long)Co * Ci * ntaps), 256, 0, s>>>(part, S, dw, Co, Ci, ntaps);
   RD_LAUNCHED();
   return 0;
 }
@@ -817,6 +817,171 @@ int launch_channel_sum(const float* g, long long npix, int C, float* out, float*
   return launch_sum_partials(scratch, grid, C, C, 1, out, s);
 }
 
-// NCHW [B,1,H,W] BatchNorm on channel 0 of the input for outer_skip_BN is handled by the host wrapper (1 channel).
+// ----------------------------------------------------------------------------------------------
+// outer_skip_BN: BatchNorm2d(1) on channel 0 of the NCHW input (lib/UNet.py:192-193,231-237)
+//   stats : partials [nblk][1][2] = (sum x0, sum x0^2)          -> bn_finalize with C = 1
+//   bwd   : partials [nblk][2]    = (sum dy, sum dy*(x0-mean))  -> dgamma = invstd * S2, dbeta = S1
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+outer_bn_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ mean,
+                       float* __restrict__ partials, int B, int Cin, int HW) {
+  __shared__ float r1[256], r2[256];
+  const float mu = dy ? mean[0] : 0.f;
+  float a = 0.f, b = 0.f;
+  const long long total = (long long)B * HW;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const long long bi = i / HW, p = i - bi * HW;
+    const float v = x[(size_t)bi * Cin * HW + p];
+    if (dy) {
+      const float g = dy[i];
+      a += g;
+      b = fmaf(g, v - mu, b);
+    } else {
+      a += v;
+      b = fmaf(v, v, b);
+    }
+  }
+  r1[threadIdx.x] = a; r2[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { partials[blockIdx.x * 2] = r1[0]; partials[blockIdx.x * 2 + 1] = r2[0]; }
+}
+int launch_outer_bn_reduce(const float* x, const float* dy, const float* mean, float* partials, int* n_partials, int B,
+                           int Cin, int HW, cudaStream_t s) {
+  const int nb = 296;
+  outer_bn_reduce_kernel<<<nb, 256, 0, s>>>(x, dy, mean, partials, B, Cin, HW);
+  RD_LAUNCHED();
+  *n_partials = nb;
+  return 0;
+}
+__global__ void outer_bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts,
+                                             const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                             float* __restrict__ dbeta) {
+  if (threadIdx.x != 0) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < nparts; ++i) { s1 += (double)partials[i * 2]; s2 += (double)partials[i * 2 + 1]; }
+  dbeta[0] = (float)s1;
+  dgamma[0] = (float)(s2 * (double)invstd[0]);
+}
+int launch_outer_bn_bwd_finalize(const float* partials, int nparts, const float* invstd, float* dgamma, float* dbeta,
+                                 cudaStream_t s) {
+  outer_bn_bwd_finalize_kernel<<<1, 32, 0, s>>>(partials, nparts, invstd, dgamma, dbeta);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// up_mode='bilinear': nn.Upsample(scale_factor=2, mode='bilinear') (align_corners=False) followed by a 1x1 conv
+// (lib/UNet.py:20).  The 1x1 conv commutes with the interpolation (the weights of every output pixel sum to 1),
+// so it runs at the LOW resolution as a 1-tap GEMM and these kernels interpolate its output:
+//   forward : u[b,oy,ox,c] = bilinear(t)[oy,ox,c] + bias[c] + skip[b,oy,ox,c]
+//   adjoint : dt[b,i,j,c]  = sum over the output pixels that read (i,j) of weight * du
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_src(int o, int n_in, int& i0, int& i1, float& l1) {
+  float src = 0.5f * ((float)o + 0.5f) - 0.5f;          // area_pixel_compute_source_index, align_corners=False
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+__global__ void __launch_bounds__(256)
+bilinear_up_add_kernel(const float* __restrict__ t, const float* __restrict__ bias, const float* __restrict__ skip,
+                       float* __restrict__ u, int B, int Hin, int Win, int C, int rnd) {
+  const int Q = C >> 2, Ho = 2 * Hin, Wo = 2 * Win;
+  const long long total = (long long)B * Ho * Wo * Q;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int q = (int)(i % Q);
+    long long p = i / Q;
+    const int ox = (int)(p % Wo); p /= Wo;
+    const int oy = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bilinear_src(oy, Hin, y0, y1, ly);
+    bilinear_src(ox, Win, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const float* base = t + (size_t)b * Hin * Win * C + q * 4;
+    const float4 v00 = ld4(base + ((size_t)y0 * Win + x0) * C), v01 = ld4(base + ((size_t)y0 * Win + x1) * C);
+    const float4 v10 = ld4(base + ((size_t)y1 * Win + x0) * C), v11 = ld4(base + ((size_t)y1 * Win + x1) * C);
+    const float4 bv = ld4(bias + q * 4);
+    float4 r;
+    r.x = hy * (hx * v00.x + lx * v01.x) + ly * (hx * v10.x + lx * v11.x) + bv.x;
+    r.y = hy * (hx * v00.y + lx * v01.y) + ly * (hx * v10.y + lx * v11.y) + bv.y;
+    r.z = hy * (hx * v00.z + lx * v01.z) + ly * (hx * v10.z + lx * v11.z) + bv.z;
+    r.w = hy * (hx * v00.w + lx * v01.w) + ly * (hx * v10.w + lx * v11.w) + bv.w;
+    if (skip) {
+      const float4 sv = ld4(skip + i * 4);
+      r.x += sv.x; r.y += sv.y; r.z += sv.z; r.w += sv.w;
+    }
+    st4(u + i * 4, rnd ? tf32_rn4(r) : r);
+  }
+}
+int launch_bilinear_up_add(const float* t, const float* bias, const float* skip, float* u, int B, int Hin, int Win,
+                           int C, int rnd, cudaStream_t s) {
+  if (C % 4) return fail("bilinear_up: C=%d not a multiple of 4", C);
+  bilinear_up_add_kernel<<<ew_grid((long long)B * 4 * Hin * Win * (C / 4)), 256, 0, s>>>(t, bias, skip, u, B, Hin, Win,
+                                                                                        C, rnd);
+  RD_LAUNCHED();
+  return 0;
+}
+__global__ void __launch_bounds__(256)
+bilinear_up_adjoint_kernel(const float* __restrict__ du, float* __restrict__ dt, int B, int Hin, int Win, int C,
+                           int rnd) {
+  const int Q = C >> 2, Ho = 2 * Hin, Wo = 2 * Win;
+  const long long total = (long long)B * Hin * Win * Q;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int q = (int)(i % Q);
+    long long p = i / Q;
+    const int ix = (int)(p % Win); p /= Win;
+    const int iy = (int)(p % Hin);
+    const int b = (int)(p / Hin);
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int oy = 2 * iy - 2; oy <= 2 * iy + 2; ++oy) {
+      if (oy < 0 || oy >= Ho) continue;
+      int y0, y1;
+      float ly;
+      bilinear_src(oy, Hin, y0, y1, ly);
+      const float wy = (y0 == iy ? 1.f - ly : 0.f) + (y1 == iy ? ly : 0.f);
+      if (wy == 0.f) continue;
+      for (int ox = 2 * ix - 2; ox <= 2 * ix + 2; ++ox) {
+        if (ox < 0 || ox >= Wo) continue;
+        int x0, x1;
+        float lx;
+        bilinear_src(ox, Win, x0, x1, lx);
+        const float wx = (x0 == ix ? 1.f - lx : 0.f) + (x1 == ix ? lx : 0.f);
+        if (wx == 0.f) continue;
+        const float4 g = ld4(du + (((size_t)b * Ho + oy) * Wo + ox) * C + q * 4);
+        const float w = wy * wx;
+        acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y); acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+      }
+    }
+    st4(dt + i * 4, rnd ? tf32_rn4(acc) : acc);
+  }
+}
+int launch_bilinear_up_adjoint(const float* du, float* dt, int B, int Hin, int Win, int C, int rnd, cudaStream_t s) {
+  bilinear_up_adjoint_kernel<<<ew_grid((long long)B * Hin * Win * (C / 4)), 256, 0, s>>>(du, dt, B, Hin, Win, C, rnd);
+  RD_LAUNCHED();
+  return 0;
+}
+// 1x1 conv weight [Co][Ci] -> its transpose (and TF32 rounding of both copies when requested)
+__global__ void pack_conv1x1_kernel(const float* __restrict__ w, float* __restrict__ w_copy, float* __restrict__ w_t,
+                                    int Co, int Ci, int rnd) {
+  const int total = Co * Ci;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int ci = i % Ci, co = i / Ci;
+    float v = w[i];
+    if (rnd) v = tf32_rn(v);
+    w_copy[i] = v;
+    w_t[(size_t)ci * Co + co] = v;
+  }
+}
+int launch_pack_conv1x1(const float* w, float* w_copy, float* w_t, int Co, int Ci, int rnd, cudaStream_t s) {
+  pack_conv1x1_kernel<<<ew_grid((long long)Co * Ci), 256, 0, s>>>(w, w_copy, w_t, Co, Ci, rnd);
+  RD_LAUNCHED();
+  return 0;
+}
 
 }  // namespace rd

@@ -151,15 +151,14 @@ class UNet(nn.Module):
         return _native.MATH_TF32 if m == 'tf32' else _native.MATH_FP32
 
     def _config(self) -> _native.RdConfig:
-        if self.up_mode != 'transpose':
-            raise NotImplementedError("resdepth_b200: up_mode='bilinear' has no CUDA path (only 'transpose')")
         return _native.RdConfig(
             n_input_channels=self.n_input_channels, start_kernel=self.start_kernel,
             max_filter_depth=self.max_filter_depth, depth=self.depth,
             act_encoder=_native.ACT_IDS[self.act_fn_encoder], act_decoder=_native.ACT_IDS[self.act_fn_decoder],
             act_bottleneck=_native.ACT_IDS[self.act_fn_bottleneck], do_bn=int(bool(self.do_BN)),
             bias_conv_layer=int(bool(self.bias_conv_layer)), outer_skip=int(bool(self.do_outer_skip)),
-            outer_skip_bn=int(bool(self.do_outer_skip_BN)), math_mode=self._math_mode())
+            outer_skip_bn=int(bool(self.do_outer_skip_BN)), math_mode=self._math_mode(),
+            up_mode=_native.UP_IDS[self.up_mode])
 
     def _runtime(self, device: torch.device) -> dict:
         """Creates (once per device) the native handle and moves parameters/buffers into flat arenas."""

@@ -376,3 +376,79 @@ def test_predict_linear_blend_matches_oracle(math_mode):
     out = predict_linear_blend(loader, model)
     assert out.dtype == np.float64 and out.shape == (rows, cols)
     np.testing.assert_allclose(out, ref, rtol=0, atol=2e-4 if math_mode == 'fp32' else 5e-3)
+
+
+EXTRA_SHAPES = [
+    # kwargs, B, T  -- shapes the golden table does not cover: non-power-of-two tiles (masked partial GEMM tiles),
+    # batch 1, wider inputs, channel counts that are multiples of 32 but not powers of two
+    (dict(n_input_channels=2, start_kernel=32, depth=3, bias_conv_layer=True), 1, 96),
+    (dict(n_input_channels=4, start_kernel=96, depth=2, bias_conv_layer=False), 3, 40),
+    (dict(n_input_channels=6, start_kernel=64, max_filter_depth=128, depth=4, bias_conv_layer=True), 2, 48),
+    (dict(n_input_channels=1, start_kernel=32, depth=1, bias_conv_layer=True), 5, 16),
+]
+
+
+@pytest.mark.parametrize('kwargs,B,T', EXTRA_SHAPES)
+def test_extra_shapes_against_oracle(kwargs, B, T, math_mode):
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    pkeys = [k for k, _ in model.named_parameters()]
+    for k in pkeys:
+        sd[k].requires_grad_(True)
+    batch = O.synthetic_batch(B, kwargs['n_input_channels'], T, seed=77)
+    loss_ref, grads_ref, y_ref = O.train_step(sd, pkeys, batch, spec, None)
+    model = model.to(DEV)
+    y, loss, grads, _ = _train_step(model, batch, None)
+    tight = math_mode == 'fp32'
+    rel, same, mae = O.residual_metrics(y.cpu(), y_ref, batch['input'][:, :1])
+    assert rel <= (1e-5 if tight else 1e-3) and same and mae <= 1e-3, (rel, same, mae)
+    assert abs(loss - loss_ref) <= (1e-5 if tight else 2e-3) * abs(loss_ref)
+    flat = torch.cat([grads[k].cpu().flatten() for k in pkeys])
+    flat_ref = torch.cat([grads_ref[k].flatten() for k in pkeys])
+    assert _rel(flat, flat_ref) <= (1e-3 if tight else 1e-2), _rel(flat, flat_ref)
+
+
+def test_depth6_512_tiles_against_oracle(math_mode):
+    """BASELINE config 5 shape (3-ch 512x512 tiles, U-Net depth 6) on two tiles."""
+    kwargs = dict(n_input_channels=3, start_kernel=64, depth=6, bias_conv_layer=True)
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = O.synthetic_batch(2, 3, 512)
+    with torch.no_grad():
+        y_ref = O.unet_forward(sd, batch['input'], spec, training=True, update_running=False)
+    model = model.to(DEV)
+    y, loss, grads, _ = _train_step(model, batch, None)
+    rel, same, mae = O.residual_metrics(y.cpu(), y_ref, batch['input'][:, :1])
+    assert rel <= (1e-5 if math_mode == 'fp32' else 1e-3) and same and mae <= 1e-3, (rel, same, mae)
+    assert all(torch.isfinite(g).all() for g in grads.values())
+
+
+def test_trainer_with_sgd_and_checkpoint_resume(tmp_path):
+    from types import SimpleNamespace
+
+    from resdepth_b200.lib.Trainer import Trainer
+    kwargs, B, T = CASES['var_base']
+    batches = [O.synthetic_batch(B, 3, T, seed=300 + i) for i in range(2)]
+
+    def make(pretrained=None, n_epochs=1):
+        model = _model(kwargs)
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3, weight_decay=1e-5)
+        args = SimpleNamespace(trainloader=batches, valloader=batches[:1], model=model, optimizer=opt, scheduler=None,
+                               criterion=torch.nn.L1Loss(reduction='mean'), n_epochs=n_epochs, evaluate_rate=1,
+                               save_model_rate=1, freq_average_train_loss=1, save_dir=str(tmp_path),
+                               log_file=str(tmp_path / 'training.log'), checkpoint_dir=str(tmp_path / 'ckpt'),
+                               tboard_log_dir=None, pretrained_path=pretrained)
+        return Trainer(args)
+    tr = make()
+    assert tr.optimizer.__class__.__name__ == 'SGD'
+    tr.train()
+    ck = torch.load(tr.path_model_last, weights_only=False)
+    tr2 = make(pretrained=tr.path_model_last)
+    assert tr2.start_epoch == 1 and tr2.n_epochs == 2
+    for k, v in tr2.model.state_dict().items():
+        assert torch.equal(v.cpu(), ck['model_state_dict'][k].cpu()), k
+    v0 = tr.inference_one_batch(batches[0], 'val')['MAE_metric']
+    v1 = tr2.inference_one_batch(batches[0], 'val')['MAE_metric']
+    assert abs(v0 - v1) <= 1e-6 * abs(v0)

@@ -55,9 +55,6 @@ def test_constructor_errors_match_reference_behaviour():
         UNet(act_fn_encoder='gelu')
     with pytest.raises(ValueError):
         UNet(up_mode='nearest')
-    m = UNet(n_input_channels=3, start_kernel=32, depth=2, up_mode='bilinear')
-    with pytest.raises(NotImplementedError):
-        m._config()
     m = UNet(n_input_channels=3, start_kernel=32, depth=2)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 32, 32))                  # CPU tensors are refused: no fallback path
@@ -68,8 +65,8 @@ def test_rd_create_rejects_unsupported_plans():
     with pytest.raises(RuntimeError, match='start_kernel'):
         _native.Handle(cfg, 0)
     cfg = _native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1, outer_skip=1,
-                           outer_skip_bn=1)
-    with pytest.raises(RuntimeError, match='outer_skip_BN'):
+                           up_mode=7)
+    with pytest.raises(RuntimeError, match='up_mode'):
         _native.Handle(cfg, 0)
     cfg = _native.RdConfig(n_input_channels=9, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1)
     with pytest.raises(RuntimeError, match='n_input_channels'):
