@@ -381,6 +381,28 @@ int conv_block_forward(rd_handle* h, ConvBlock& b, const float* src, int B, int 
   return launch_gemm_rows_simt(src, g, b.w_kn, B, b.Cout, e, np, s);
 }
 
+// Inference (RD_FWD_EVAL) on a tcgen05 block: BatchNorm(running stats) + activation (+ 2x2 max-pool) folded into the
+// conv epilogue -- the raw conv output z is never written
+int conv_block_forward_fused_eval(rd_handle* h, ConvBlock& b, int B, int H, int round_a, int round_p, cudaStream_t s) {
+  BnLayer L = bn_view(h, b);
+  {
+    ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
+    RD_TRY(launch_bn_finalize(L, h->partials, 0, (long long)B * H * H, 0, h->cfg.do_bn, s));
+  }
+  Epilogue e{};
+  e.mode = EPI_BNACT;
+  e.out = b.a;
+  e.round_tf32 = round_a;
+  e.scale = b.scale;
+  e.shift = b.shift;
+  e.slope = act_view(h, b).slope;
+  e.pool_out = b.pool ? b.p : nullptr;
+  e.round_pool = round_p;
+  const double px = (double)B * H * H;
+  ProfScope ps(h, RD_PROF_CONV_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout * (b.pool ? 1.25 : 1.0)), s);
+  return launch_gemm_rows_tc(b.tc_fwd, e, nullptr, s);
+}
+
 // BN statistics finalize + fused normalise/activation(/pool) pass of one block
 int bn_act_forward(rd_handle* h, ConvBlock& b, int np, int B, int H, bool train, int round_a, int round_p,
                    cudaStream_t s) {
@@ -545,6 +567,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
   const bool train = mode == RD_FWD_TRAIN;
   const bool stats = train && h->cfg.do_bn;
   const int tf = h->tf32() ? 1 : 0;
+  const bool fuse_eval = mode == RD_FWD_EVAL;         // nothing is kept for a backward pass: fold BN into the convs
   h->fwd_mode = -1;
   RD_TRY(pack_weights(h, save, s));
 
@@ -556,6 +579,9 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
       const double px = (double)B * H * H;
       ProfScope ps(h, RD_PROF_FIRST_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
       RD_TRY(launch_conv_first_fwd(x, h->P + b.w, b.z, stats ? h->partials : nullptr, &np, B, b.Cin, H, H, b.Cout, s));
+    } else if (fuse_eval && b.tc) {
+      RD_TRY(conv_block_forward_fused_eval(h, b, B, H, 0, tf, s));
+      continue;
     } else {
       RD_TRY(conv_block_forward(h, b, h->enc[i - 1].p, B, H, stats, &np, s));
     }
@@ -564,8 +590,12 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
   {
     ConvBlock& b = h->bott;
     const int H = T >> D;
-    RD_TRY(conv_block_forward(h, b, h->enc[D - 1].p, B, H, stats, &np, s));
-    RD_TRY(bn_act_forward(h, b, np, B, H, train, tf, 0, s));
+    if (fuse_eval && b.tc) {
+      RD_TRY(conv_block_forward_fused_eval(h, b, B, H, tf, 0, s));
+    } else {
+      RD_TRY(conv_block_forward(h, b, h->enc[D - 1].p, B, H, stats, &np, s));
+      RD_TRY(bn_act_forward(h, b, np, B, H, train, tf, 0, s));
+    }
   }
   const float* cur = h->bott.a;
   int Hc = T >> D;
@@ -597,8 +627,12 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     Hc *= 2;
     if (j < D - 1) {
       ConvBlock& b = h->dec[j];
-      RD_TRY(conv_block_forward(h, b, u.u, B, Hc, stats, &np, s));
-      RD_TRY(bn_act_forward(h, b, np, B, Hc, train, tf, 0, s));
+      if (fuse_eval && b.tc) {
+        RD_TRY(conv_block_forward_fused_eval(h, b, B, Hc, tf, 0, s));
+      } else {
+        RD_TRY(conv_block_forward(h, b, u.u, B, Hc, stats, &np, s));
+        RD_TRY(bn_act_forward(h, b, np, B, Hc, train, tf, 0, s));
+      }
       cur = b.a;
     }
   }

@@ -142,14 +142,21 @@ struct Gather {      // how GEMM rows (output pixels) map to source pixels per t
   int C;             // channels per tap (source tensor channel count)
   signed char dh[9], dw[9];
 };
-enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_CONVT = 2 };
+enum { EPI_PLAIN = 0, EPI_STATS = 1, EPI_CONVT = 2, EPI_BNACT = 3 };
 struct Epilogue {
   int mode;
-  float* out;             // PLAIN/STATS: [M][N] ; CONVT: u NHWC [B,2Ho,2Wo,N/4]
+  float* out;             // PLAIN/STATS/BNACT: [M][N] ; CONVT: u NHWC [B,2Ho,2Wo,N/4]
   float* partials;        // STATS: [m_tiles][N][2]
   const float* bias;      // CONVT: [N/4]
   const float* skip;      // CONVT: NHWC same shape as out (may be null)
-  int round_tf32;         // CONVT: round the stored sum
+  int round_tf32;         // round the stored values to TF32 (they feed a tcgen05 GEMM)
+  // BNACT (eval-mode BatchNorm folded into the conv, tcgen05 kernel only): out = act(acc*scale + shift),
+  // optionally also the 2x2 max-pooled tensor
+  const float* scale;     // [N]
+  const float* shift;     // [N]
+  const float* slope;     // device scalar: negative slope of the activation
+  float* pool_out;        // [B,Ho/2,Wo/2,N] or null
+  int round_pool;
 };
 // C[M=B*Ho*Wo][N] = gather(src)[M][ntaps*C] * Bm[ntaps*C][N]
 int launch_gemm_rows_simt(const float* src, const Gather& g, const float* Bm, int B, int N, const Epilogue& e,

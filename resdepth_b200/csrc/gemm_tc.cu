@@ -24,7 +24,7 @@ namespace rd {
 using namespace tc;
 
 static constexpr int TC_THREADS = 192;          // reduce kernel: TMA warp, MMA warp, 4 epilogue warps
-static constexpr int ROWS_THREADS = 320;        // rows kernel: TMA warp, MMA warp, 8 epilogue warps
+static constexpr int ROWS_THREADS = 384;        // rows kernel: A-TMA warp, MMA warp, B-TMA warp (halo variant), spare, 8 epilogue warps
 
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;
@@ -32,26 +32,42 @@ __device__ __forceinline__ float tf32_round(float v) {
   return __uint_as_float(u);
 }
 
-template <int BN>
+// HALO variant (3x3 taps, image at least 16x8): the 128-pixel tile is 16 rows x 8 pixels and its 18x10 halo patch
+// of one 32-channel chunk is loaded ONCE (23 KB) and reused by all nine taps -- a tap is just a different start
+// row of the UMMA descriptor inside the patch (start address + (dh*10+dw)*128 bytes, 8-row groups 10 rows =
+// 1280 bytes apart), which the 128-byte swizzle tolerates because it is a function of the shared-memory address.
+// This cuts the activation traffic of the conv layers 6x; the weight tiles stream through their own ring.
+static constexpr int HALO_W = 10, HALO_H = 18;
+static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;             // 23040
+static constexpr int HALO_SLOT = 23 * 1024;                           // 1024-byte aligned slot
+
+template <int BN, bool HALO>
 struct RowsCfg {
-  static constexpr int A_BYTES = 128 * 128;                 // 128 rows x 32 fp32
+  static constexpr int A_BYTES = HALO ? HALO_SLOT : 128 * 128;       // plain: 128 rows x 32 fp32
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // plain variant: one ring of (A, B) stages
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_SLOTS = 3;                                  // halo variant: separate rings
+  static constexpr int B_SLOTS = (BN == 256) ? 4 : 8;
+  static constexpr int DATA_BYTES = HALO ? A_SLOTS * HALO_SLOT + B_SLOTS * B_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int NBAR_A = HALO ? A_SLOTS : STAGES;
+  static constexpr int NBAR_B = HALO ? B_SLOTS : 0;
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
 
-template <int BN>
+template <int BN, bool HALO>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TcRowsParams P) {
-  using Cfg = RowsCfg<BN>;
+  using Cfg = RowsCfg<BN, HALO>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + Cfg::STAGES;
-  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);     // plain: stage ring; halo: A ring
+  uint64_t* empty_bar = full_bar + Cfg::NBAR_A;
+  uint64_t* bfull_bar = empty_bar + Cfg::NBAR_A;                                // halo: B ring
+  uint64_t* bempty_bar = bfull_bar + Cfg::NBAR_B;
+  uint64_t* tfull_bar = bempty_bar + Cfg::NBAR_B;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -60,7 +76,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapB);
-    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < Cfg::NBAR_A; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < Cfg::NBAR_B; ++i) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_mbar_init();
   }
@@ -75,7 +92,71 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int num_tiles = m_tiles * n_tiles;
   const int kblocks = P.ntaps * P.cchunks;
 
-  if (warp == 0) {
+  if (HALO && (warp == 0 || warp == 2)) {
+    // ===== halo variant: warp 0 streams the halo patches (one per 32-channel chunk), warp 2 the weight tiles
+    // (one per chunk and tap); the two rings advance independently =====
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t phase = 0;
+      uint8_t* bring = smem + Cfg::A_SLOTS * HALO_SLOT;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % n_tiles;
+        int mt = tile / n_tiles;
+        const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
+        const int th_i = mt % P.tiles_h;
+        const int tb_i = mt / P.tiles_h;
+        for (int cc = 0; cc < P.cchunks; ++cc) {
+          if (warp == 0) {
+            mbar_wait(&empty_bar[slot], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[slot], HALO_BYTES);
+            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * 32, tw_i * P.tw - 1, th_i * P.th - 1, tb_i);
+            if (++slot == Cfg::A_SLOTS) { slot = 0; phase ^= 1; }
+          } else {
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&bempty_bar[slot], phase ^ 1);
+              mbar_arrive_expect_tx(&bfull_bar[slot], Cfg::B_BYTES);
+              tma_load_2d(bring + slot * Cfg::B_BYTES, &mapB, &bfull_bar[slot], (tap * P.cchunks + cc) * 32, nt * BN);
+              if (++slot == Cfg::B_SLOTS) { slot = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (HALO && warp == 1) {
+    // ===== halo variant MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
+      int aslot = 0, bslot = 0;
+      uint32_t aphase = 0, bphase = 0;
+      const uint32_t a_base = smem_u32(smem), b_base = a_base + Cfg::A_SLOTS * HALO_SLOT;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int cc = 0; cc < P.cchunks; ++cc) {
+          mbar_wait(&full_bar[aslot], aphase);
+          const uint32_t sa = a_base + aslot * HALO_SLOT;
+          for (int tap = 0; tap < 9; ++tap) {
+            mbar_wait(&bfull_bar[bslot], bphase);
+            tc_fence_after();
+            const uint32_t sa_tap = sa + ((tap / 3) * HALO_W + (tap % 3)) * 128;
+            const uint32_t sb = b_base + bslot * Cfg::B_BYTES;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_tf32(d_tmem, smem_desc_sw128(sa_tap + k * 32, 16, HALO_W * 128), smem_desc_sw128(sb + k * 32, 16, 1024),
+                       idesc, (cc | tap | k) != 0);
+            tc_commit(&bempty_bar[bslot]);
+            if (++bslot == Cfg::B_SLOTS) { bslot = 0; bphase ^= 1; }
+          }
+          tc_commit(&empty_bar[aslot]);
+          if (++aslot == Cfg::A_SLOTS) { aslot = 0; aphase ^= 1; }
+        }
+        tc_commit(&tfull_bar[acc]);
+      }
+    }
+  } else if (!HALO && warp == 0) {
     // ===== TMA producer: lane 0 waits for the slot and arms the barrier, then lane 0 issues the A box and
     // lane 1 the B box (coordinates in registers, no indexed arrays) =====
     const bool up2 = P.coord_b < 0;                   // (c, w, a, b*h) view of the 2x-upsampled tensor; else (c, w, h, b)
@@ -105,7 +186,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (!HALO && warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
@@ -132,11 +213,11 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         tc_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
       }
     }
-  } else {
+  } else if (warp >= 4) {
     // ===== 8 epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter take the even / odd
     // 32-column chunks, doubling the loads and stores in flight for the HBM-bound layers =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
     float cs1[NCH2], cs2[NCH2];
@@ -182,6 +263,48 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               }
               if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
               op[j] = r;
+            }
+          }
+        } else if (P.epi_mode == EPI_BNACT) {
+          // eval-mode BatchNorm folded into the conv: a = act(acc*scale + shift); optional fused 2x2 max-pool
+          // (the 2x2 window of a pixel lives in lanes l, l^1, l^tw, l^tw^1 of this warp)
+          const float slope = __ldg(P.slope);
+          const float4* scp = reinterpret_cast<const float4*>(P.scale + n);
+          const float4* shp = reinterpret_cast<const float4*>(P.shift + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = __ldg(scp + j), sh = __ldg(shp + j);
+            float y0 = fmaf(v[4 * j], sc.x, sh.x), y1 = fmaf(v[4 * j + 1], sc.y, sh.y);
+            float y2 = fmaf(v[4 * j + 2], sc.z, sh.z), y3 = fmaf(v[4 * j + 3], sc.w, sh.w);
+            v[4 * j] = y0 > 0.f ? y0 : y0 * slope;
+            v[4 * j + 1] = y1 > 0.f ? y1 : y1 * slope;
+            v[4 * j + 2] = y2 > 0.f ? y2 : y2 * slope;
+            v[4 * j + 3] = y3 > 0.f ? y3 : y3 * slope;
+          }
+          if (valid) {
+            float4* op = reinterpret_cast<float4*>(P.out + pix * P.N + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
+              op[j] = r;
+            }
+          }
+          if (P.pool_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+              v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, P.tw));
+            }
+            if (valid && !(w & 1) && !(h & 1)) {
+              const size_t pp = ((size_t)b * (P.Ho >> 1) + (h >> 1)) * (P.Wo >> 1) + (w >> 1);
+              float4* op = reinterpret_cast<float4*>(P.pool_out + pp * P.N + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (P.round_pool) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
+                op[j] = r;
+              }
             }
           }
         } else {
@@ -306,6 +429,7 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
   P.ntaps = g.ntaps;
   P.cchunks = g.C / 32;
   plan->BN = tc_pick_bn(N);
+  plan->halo = false;
   long long dims[4], strides[3];
   int box[4];
   if (g.ups == 1) {
@@ -320,6 +444,13 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
     dims[0] = g.C; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
     strides[0] = (long long)g.C * 4; strides[1] = (long long)g.Ws * g.C * 4; strides[2] = (long long)g.Hs * g.Ws * g.C * 4;
     box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb;
+    static const bool no_halo = getenv("RESDEPTH_NO_HALO") != nullptr;
+    if (g.ntaps == 9 && g.Ho >= 16 && g.Wo >= 8 && !no_halo) {
+      // halo-reuse variant: 16 x 8 pixel tiles, one 18 x 10 halo patch per 32-channel chunk serves all nine taps
+      plan->halo = true;
+      P.tw = 8; P.th = 16; P.tb = 1;
+      box[1] = HALO_W; box[2] = HALO_H; box[3] = 1;
+    }
   } else {
     // 2x2 stride-2 gather of dU NHWC [B, 2Hin, 2Win, C] seen as (2C, Win, 2, B*Hin): tap (a, b) = (coord2, coord0 / C)
     P.Wo = g.Wo; P.Ho = B * g.Ho; P.Bo = 1;
@@ -346,15 +477,16 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
   return 0;
 }
 
-template <int BN>
+template <int BN, bool HALO>
 static int launch_rows(const TcRowsPlan& plan, const TcRowsParams& P, int grid, cudaStream_t s) {
-  using Cfg = RowsCfg<BN>;
+  using Cfg = RowsCfg<BN, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_rows_tc_kernel<BN><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
+  gemm_rows_tc_kernel<BN, HALO><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
   RD_LAUNCHED();
   return 0;
 }
@@ -368,17 +500,33 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
   P.bias = e.bias;
   P.skip = e.skip;
   P.round_tf32 = e.round_tf32;
+  P.scale = e.scale;
+  P.shift = e.shift;
+  P.slope = e.slope;
+  P.pool_out = e.pool_out;
+  P.round_pool = e.round_pool;
+  if (e.mode == EPI_BNACT && e.pool_out && (P.tw < 2 || P.th < 2 || (P.Wo & 1) || (P.Ho & 1)))
+    return fail("tc rows: fused pooling needs even image sizes and a tile of at least 2x2 pixels");
   const int n_tiles = P.N / plan.BN;
   const int num_tiles = P.tiles_w * P.tiles_h * P.tiles_b * n_tiles;
   int grid = (148 / n_tiles) * n_tiles;
   if (grid < n_tiles) grid = n_tiles;
   if (grid > num_tiles) grid = ((num_tiles + n_tiles - 1) / n_tiles) * n_tiles;
   if (n_partials) *n_partials = (grid / n_tiles) * 4;
-  switch (plan.BN) {
-    case 256: return launch_rows<256>(plan, P, grid, s);
-    case 128: return launch_rows<128>(plan, P, grid, s);
-    case 64: return launch_rows<64>(plan, P, grid, s);
-    case 32: return launch_rows<32>(plan, P, grid, s);
+  if (plan.halo) {
+    switch (plan.BN) {
+      case 256: return launch_rows<256, true>(plan, P, grid, s);
+      case 128: return launch_rows<128, true>(plan, P, grid, s);
+      case 64: return launch_rows<64, true>(plan, P, grid, s);
+      case 32: return launch_rows<32, true>(plan, P, grid, s);
+    }
+  } else {
+    switch (plan.BN) {
+      case 256: return launch_rows<256, false>(plan, P, grid, s);
+      case 128: return launch_rows<128, false>(plan, P, grid, s);
+      case 64: return launch_rows<64, false>(plan, P, grid, s);
+      case 32: return launch_rows<32, false>(plan, P, grid, s);
+    }
   }
   return fail("tc rows: unsupported BN=%d", plan.BN);
 }

@@ -21,12 +21,18 @@ struct TcRowsParams {
   float* partials;
   const float* bias;
   const float* skip;
+  const float* scale;    // EPI_BNACT
+  const float* shift;
+  const float* slope;
+  float* pool_out;
+  int round_pool;
 };
 
 struct TcRowsPlan {
   CUtensorMap mapA, mapB;
   TcRowsParams p;
   int BN = 0;
+  bool halo = false;     // 3x3 halo-reuse variant (16x8 tiles)
   bool valid = false;
 };
 
