@@ -93,7 +93,7 @@ int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z
 
 int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
                 float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s);
-static constexpr size_t LOSS_SCRATCH_FLOATS = 2 * 2 * 256 + 4;
+static constexpr size_t LOSS_SCRATCH_FLOATS = 2 * 2 * 1184 + 4;
 int launch_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 float wd, long long step, float gscale, cudaStream_t s);
 int launch_sgd(float* p, const float* g, long long n, float lr, float wd, float gscale, cudaStream_t s);

@@ -32,14 +32,17 @@ __device__ __forceinline__ float tf32_round(float v) {
   return __uint_as_float(u);
 }
 
-// HALO variant (3x3 taps, image at least 16x8): the 128-pixel tile is 16 rows x 8 pixels and its 18x10 halo patch
-// of one 32-channel chunk is loaded ONCE (23 KB) and reused by all nine taps -- a tap is just a different start
-// row of the UMMA descriptor inside the patch (start address + (dh*10+dw)*128 bytes, 8-row groups 10 rows =
-// 1280 bytes apart), which the 128-byte swizzle tolerates because it is a function of the shared-memory address.
-// This cuts the activation traffic of the conv layers 6x; the weight tiles stream through their own ring.
-static constexpr int HALO_W = 10, HALO_H = 18;
-static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;             // 23040
-static constexpr int HALO_SLOT = 23 * 1024;                           // 1024-byte aligned slot
+// HALO variant (3x3 taps, image at least 16x16): one CTA tile is 16 x 16 pixels = TWO 128-row MMA sub-tiles
+// (16 rows x 8 pixels each) with separate TMEM accumulators.
+//   * The 18x18 halo patch of one 32-channel chunk is loaded ONCE (40.5 KB) and reused by all nine taps and both
+//     sub-tiles: a (tap, sub-tile) is just a different start row of the UMMA descriptor inside the patch
+//     (start address + (dh*18 + dw + 8*sub)*128 bytes, 8-row groups 18 rows = 2304 bytes apart).  The 128-byte
+//     swizzle tolerates the unaligned start rows because it is a function of the shared-memory address.
+//   * Every weight tile (32 k x BN) is used by both sub-tiles, halving the weight traffic per MMA -- with the
+//     plain kernel the operand traffic is 96-187 B per MMA cycle per SM, here 40-50.
+static constexpr int HALO_W = 18, HALO_H = 18, HALO_SUB = 2;
+static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;             // 41472
+static constexpr int HALO_SLOT = 41 * 1024;                           // 1024-byte aligned slot
 
 template <int BN, bool HALO>
 struct RowsCfg {
@@ -47,12 +50,15 @@ struct RowsCfg {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // plain variant: one ring of (A, B) stages
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int A_SLOTS = 3;                                  // halo variant: separate rings
-  static constexpr int B_SLOTS = (BN == 256) ? 4 : 8;
+  static_assert(!HALO || BN <= 128, "halo variant: two sub-tiles x two accumulator stages x BN columns <= 512");
+  static constexpr int A_SLOTS = 2;                                  // halo variant: separate rings
+  static constexpr int B_SLOTS = (BN == 128) ? 6 : 8;
+  static constexpr int SUB = HALO ? HALO_SUB : 1;                    // 128-row sub-tiles per CTA tile
+  static constexpr int ACC_COLS = SUB * BN;                          // TMEM columns of one accumulator stage
   static constexpr int DATA_BYTES = HALO ? A_SLOTS * HALO_SLOT + B_SLOTS * B_BYTES : STAGES * STAGE_BYTES;
   static constexpr int NBAR_A = HALO ? A_SLOTS : STAGES;
   static constexpr int NBAR_B = HALO ? B_SLOTS : 0;
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
 };
 
@@ -109,7 +115,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (warp == 0) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[slot], HALO_BYTES);
-            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * 32, tw_i * P.tw - 1, th_i * P.th - 1, tb_i);
+            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * 32, tw_i * P.tw * HALO_SUB - 1,
+                        th_i * P.th - 1, tb_i);
             if (++slot == Cfg::A_SLOTS) { slot = 0; phase ^= 1; }
           } else {
             for (int tap = 0; tap < 9; ++tap) {
@@ -134,7 +141,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         const int acc = it & 1;
         mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
         for (int cc = 0; cc < P.cchunks; ++cc) {
           mbar_wait(&full_bar[aslot], aphase);
           const uint32_t sa = a_base + aslot * HALO_SLOT;
@@ -144,9 +151,11 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const uint32_t sa_tap = sa + ((tap / 3) * HALO_W + (tap % 3)) * 128;
             const uint32_t sb = b_base + bslot * Cfg::B_BYTES;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_tf32(d_tmem, smem_desc_sw128(sa_tap + k * 32, 16, HALO_W * 128), smem_desc_sw128(sb + k * 32, 16, 1024),
-                       idesc, (cc | tap | k) != 0);
+            for (int sub = 0; sub < HALO_SUB; ++sub)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_tf32(d_tmem + sub * BN, smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128),
+                         smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (cc | tap | k) != 0);
             tc_commit(&bempty_bar[bslot]);
             if (++bslot == Cfg::B_SLOTS) { bslot = 0; bphase ^= 1; }
           }
@@ -232,11 +241,13 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
       const int th_i = mt % P.tiles_h;
       const int tb_i = mt / P.tiles_h;
-      const int w = tw_i * P.tw + iw, h = th_i * P.th + ih, b = tb_i * P.tb + ib;
-      const bool valid = (w < P.Wo) && (h < P.Ho) && (b < P.Bo);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int sub = 0; sub < Cfg::SUB; ++sub) {       // halo variant: two 16x8-pixel sub-tiles side by side
+      const int w = (tw_i * Cfg::SUB + sub) * P.tw + iw, h = th_i * P.th + ih, b = tb_i * P.tb + ib;
+      const bool valid = (w < P.Wo) && (h < P.Ho) && (b < P.Bo);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + sub * BN;
       const size_t pix = ((size_t)b * P.Ho + h) * P.Wo + w;
 #pragma unroll
       for (int ci = 0; ci < NCH2; ++ci) {
@@ -329,6 +340,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           }
         }
       }
+      }   // sub-tiles
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -445,8 +457,9 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
     strides[0] = (long long)g.C * 4; strides[1] = (long long)g.Ws * g.C * 4; strides[2] = (long long)g.Hs * g.Ws * g.C * 4;
     box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb;
     static const bool no_halo = getenv("RESDEPTH_NO_HALO") != nullptr;
-    if (g.ntaps == 9 && g.Ho >= 16 && g.Wo >= 8 && !no_halo) {
-      // halo-reuse variant: 16 x 8 pixel tiles, one 18 x 10 halo patch per 32-channel chunk serves all nine taps
+    if (g.ntaps == 9 && g.Ho >= 16 && g.Wo >= 16 && plan->BN <= 128 && !no_halo) {
+      // halo-reuse variant: 16 x 16 pixel tiles (two 16 x 8 MMA sub-tiles), one 18 x 18 halo patch per 32-channel
+      // chunk serves all nine taps and both sub-tiles; N tile capped at 128 (TMEM: 2 stages x 2 sub-tiles x BN)
       plan->halo = true;
       P.tw = 8; P.th = 16; P.tb = 1;
       box[1] = HALO_W; box[2] = HALO_H; box[3] = 1;
@@ -465,7 +478,7 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
     strides[0] = 2LL * g.C * 4; strides[1] = (long long)g.Wo * 2 * g.C * 4; strides[2] = 2LL * g.Wo * 2 * g.C * 4;
     box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th;
   }
-  P.tiles_w = cdiv(P.Wo, P.tw);
+  P.tiles_w = cdiv(P.Wo, P.tw * (plan->halo ? HALO_SUB : 1));
   P.tiles_h = cdiv(P.Ho, P.th);
   P.tiles_b = cdiv(P.Bo, P.tb);
   RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 0));
@@ -515,7 +528,6 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
   if (n_partials) *n_partials = (grid / n_tiles) * 4;
   if (plan.halo) {
     switch (plan.BN) {
-      case 256: return launch_rows<256, true>(plan, P, grid, s);
       case 128: return launch_rows<128, true>(plan, P, grid, s);
       case 64: return launch_rows<64, true>(plan, P, grid, s);
       case 32: return launch_rows<32, true>(plan, P, grid, s);

@@ -250,78 +250,63 @@ int launch_conv_first_wgrad(const float* x, const float* dz, float* dw, float* s
 //   phase 1: per input pixel, 9 partial dot products over channels (each u element read once)
 //   phase 2: per output pixel, gather the 9 partials of its 3x3 neighbourhood
 // ----------------------------------------------------------------------------------------------
-template <int QPL>
+static constexpr int LT_H = 16, LT_W = 32;                       // output tile of one block
+static constexpr int LH_H = LT_H + 2, LH_W = LT_W + 2;           // with halo
 __global__ void __launch_bounds__(256)
 conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
                      float* __restrict__ y, int B, int H, int W, int C, int tiles_x, int tiles_y) {
-  __shared__ float ts[HALO_H * HALO_W][9];
+  __shared__ float ts[LH_H * LH_W][9];                            // per input pixel: its 9 tap partial sums
+  __shared__ __align__(16) float ws[128 * 9 + 12];                // W[c][t]
   const int tid = threadIdx.x;
-  const int lane16 = tid & 15, grp = tid >> 4;
   int t = blockIdx.x;
   const int tx = t % tiles_x; t /= tiles_x;
   const int ty = t % tiles_y;
   const int b = t / tiles_y;
-  const int h0 = ty * TH, w0 = tx * TW;
-  float4 wr[QPL][9];
-#pragma unroll
-  for (int j = 0; j < QPL; ++j) {
-    const int c = (lane16 + 16 * j) * 4;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (c < C) wr[j][k] = make_float4(w[(c + 0) * 9 + k], w[(c + 1) * 9 + k], w[(c + 2) * 9 + k], w[(c + 3) * 9 + k]);
-      else wr[j][k] = make_float4(0, 0, 0, 0);
-    }
-  }
-  for (int p = grp; p < HALO_H * HALO_W; p += 16) {
-    const int hh = p / HALO_W, ww = p % HALO_W;
+  const int h0 = ty * LT_H, w0 = tx * LT_W;
+  for (int i = tid; i < C * 9; i += 256) ws[i] = w[i];
+  __syncthreads();
+  // phase 1: one thread per (halo) input pixel streams its C channels once and forms all 9 tap dot products
+  for (int p = tid; p < LH_H * LH_W; p += 256) {
+    const int hh = p / LH_W, ww = p - hh * LH_W;
     const int gh = h0 + hh - 1, gw = w0 + ww - 1;
     float acc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.f;
     if (gh >= 0 && gh < H && gw >= 0 && gw < W) {
-      const float* up = u + (((size_t)b * H + gh) * W + gw) * C;
+      const float4* up = reinterpret_cast<const float4*>(u + (((size_t)b * H + gh) * W + gw) * C);
+#pragma unroll 4
+      for (int cq = 0; cq < (C >> 2); ++cq) {
+        const float4 v = __ldg(up + cq);
+        const float* wq = ws + cq * 36;                            // 4 channels x 9 taps
+        float wr[36];
 #pragma unroll
-      for (int j = 0; j < QPL; ++j) {
-        const int c = (lane16 + 16 * j) * 4;
-        if (c < C) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(up + c));
+        for (int j = 0; j < 9; ++j) *reinterpret_cast<float4*>(wr + 4 * j) = *reinterpret_cast<const float4*>(wq + 4 * j);
 #pragma unroll
-          for (int k = 0; k < 9; ++k)
-            acc[k] += v.x * wr[j][k].x + v.y * wr[j][k].y + v.z * wr[j][k].z + v.w * wr[j][k].w;
-        }
+        for (int k = 0; k < 9; ++k)
+          acc[k] += v.x * wr[k] + v.y * wr[9 + k] + v.z * wr[18 + k] + v.w * wr[27 + k];
       }
     }
 #pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      float a = acc[k];
-      a += __shfl_xor_sync(0xffffffffu, a, 8);
-      a += __shfl_xor_sync(0xffffffffu, a, 4);
-      a += __shfl_xor_sync(0xffffffffu, a, 2);
-      a += __shfl_xor_sync(0xffffffffu, a, 1);
-      acc[k] = a;
-    }
-    if (lane16 == 0) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) ts[p][k] = acc[k];
-    }
+    for (int k = 0; k < 9; ++k) ts[p][k] = acc[k];
   }
   __syncthreads();
-  {
-    const int lh = tid / TW, lw = tid % TW;
+  // phase 2: one thread per output pixel gathers the 9 partials of its 3x3 neighbourhood
+  const float bv = bias ? bias[0] : 0.f;
+  for (int o = tid; o < LT_H * LT_W; o += 256) {
+    const int lh = o / LT_W, lw = o - lh * LT_W;
     const int gh = h0 + lh, gw = w0 + lw;
     if (gh < H && gw < W) {
-      float a = bias ? bias[0] : 0.f;
+      float a = bv;
 #pragma unroll
       for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int s = 0; s < 3; ++s) a += ts[(lh + r) * HALO_W + lw + s][r * 3 + s];
-      const size_t o = ((size_t)b * H + gh) * W + gw;
+        for (int q = 0; q < 3; ++q) a += ts[(lh + r) * LH_W + lw + q][r * 3 + q];
       if (x0) {
         const float xv = x0[(size_t)b * x_bstride + (size_t)gh * W + gw];
         a += x_affine ? fmaf(xv, x_affine[0], x_affine[1]) : xv;
       }
-      y[o] = a;
+      y[((size_t)b * H + gh) * W + gw] = a;
     }
   }
 }
@@ -329,12 +314,9 @@ conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, c
 int launch_conv_last_fwd(const float* u, const float* w, const float* bias, const float* x, int x_bstride,
                          const float* x_affine, float* y, int B, int H, int W, int C, cudaStream_t s) {
   if (C % 4 || C > 128) return fail("conv_last: unsupported C=%d (needs C%%4==0, C<=128)", C);
-  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
+  const int tiles_x = cdiv(W, LT_W), tiles_y = cdiv(H, LT_H);
   const int grid = tiles_x * tiles_y * B;
-  if (C <= 64)
-    conv_last_fwd_kernel<1><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
-  else
-    conv_last_fwd_kernel<2><<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
+  conv_last_fwd_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
   RD_LAUNCHED();
   return 0;
 }

@@ -489,7 +489,7 @@ loss_grad_kernel(const float* __restrict__ y_pred, const float* __restrict__ tar
 int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
                 float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s) {
   // scratch: >= 2*LOSS_BLOCKS doubles + 2 floats
-  const int nb = 256;
+  const int nb = 1184;
   double* part = reinterpret_cast<double*>(scratch);
   float* inv_count = scratch + 2 * 2 * nb;
   loss_partial_kernel<<<nb, 256, 0, s>>>(y_pred, target, mask, mean, std, part, B, HW);
@@ -711,34 +711,47 @@ int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co
 // First-layer weight gradient on tensor cores: the NCHW network input is expanded to an NHWC "im2col" tensor
 // xcol[b,h,w,k] with k = ci*9 + r*3 + s  (value x[b,ci,h+r-1,w+s-1], zero outside the image and for k >= Cin*9,
 // Kc = Cin*9 rounded up to 32) so that dW[co][k] = sum_p xcol[p][k] * dz[p][co] is a plain reduce GEMM.
+// one thread per pixel: reads its 3x3 neighbourhood of every input channel (neighbours hit in L1) and writes the
+// Kc-float row of xcol as full 128-byte lines
+template <int KC>
 __global__ void __launch_bounds__(256)
-im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B, int Cin, int H, int W, int Kc,
-                    int rnd) {
-  const int KQ = Kc >> 2;
-  const long long total = (long long)B * H * W * KQ;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
-    const int kq = (int)(i % KQ);
-    long long p = i / KQ;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H);
-    const int b = (int)(p / H);
-    float v[4];
+im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B, int Cin, int H, int W, int rnd) {
+  const long long npix = (long long)B * H * W;
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < npix; p += gridDim.x * 256LL) {
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    float v[KC];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = kq * 4 + j;
-      float val = 0.f;
-      if (k < Cin * 9) {
-        const int ci = k / 9, t = k - ci * 9;
-        const int hh = h + t / 3 - 1, ww = w + t % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(x + (((size_t)b * Cin + ci) * H + hh) * W + ww);
+    for (int k = 0; k < KC; ++k) v[k] = 0.f;
+    const float* xb = x + (size_t)b * Cin * H * W;
+#pragma unroll
+    for (int ci = 0; ci < KC / 9; ++ci) {
+      if (ci < Cin) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const int hh = h + r - 1;
+#pragma unroll
+          for (int q = 0; q < 3; ++q) {
+            const int ww = w + q - 1;
+            float val = 0.f;
+            if (hh >= 0 && hh < H && ww >= 0 && ww < W) val = __ldg(xb + ((size_t)ci * H + hh) * W + ww);
+            v[ci * 9 + r * 3 + q] = rnd ? tf32_rn(val) : val;
+          }
+        }
       }
-      v[j] = rnd ? tf32_rn(val) : val;
     }
-    st4(xcol + i * 4, make_float4(v[0], v[1], v[2], v[3]));
+    float4* dst = reinterpret_cast<float4*>(xcol + (size_t)p * KC);
+#pragma unroll
+    for (int j = 0; j < KC / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
 }
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int rnd, cudaStream_t s) {
-  im2col_first_kernel<<<ew_grid((long long)B * H * W * (Kc / 4)), 256, 0, s>>>(x, xcol, B, Cin, H, W, Kc, rnd);
+  const int grid = ew_grid((long long)B * H * W);
+  if (Kc == 32) im2col_first_kernel<32><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else if (Kc == 64) im2col_first_kernel<64><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else if (Kc == 96) im2col_first_kernel<96><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else return fail("im2col_first: unsupported Kc=%d", Kc);
   RD_LAUNCHED();
   return 0;
 }
