@@ -600,7 +600,50 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   int nchunks = (P.Mrows - m0 + 31) / 32;             // live 32-row chunks of this M tile
   if (nchunks > 4) nchunks = 4;
 
-  if (warp == 0) {
+  if (warp == 0 && P.a_nch > 0) {
+    // ===== TMA producer, grouped loads: the TMA unit needs ~120-150 cycles per instruction whatever the box
+    // size, so a stage is fetched with as few instructions as possible -- lane g < groups: a_nch consecutive
+    // 32-channel chunks of A (one tap) through a 5-D map, lane 4: all BN/32 chunks of G =====
+    const int groups = 4 / P.a_nch;
+    const bool is_a = lane < 4;
+    int chunk0 = 0, off1 = 0, off2 = 0;
+    bool active;
+    if (is_a) {
+      const int r = m0 + lane * P.a_nch * 32;
+      active = lane < groups && r < P.Mrows;
+      const int tap = active ? r / P.Ca : 0;
+      chunk0 = P.a_chunk_off[tap] + (active ? (r % P.Ca) / 32 : 0);
+      off1 = P.tap_off[tap][1];
+      off2 = P.tap_off[tap][2];
+    } else {
+      active = lane == 4;
+      chunk0 = n0 / 32;
+    }
+    int live_chunks = 0;                                 // A chunks actually fetched (zero-filled ones included)
+    for (int gI = 0; gI < groups; ++gI)
+      if (m0 + gI * P.a_nch * 32 < P.Mrows) live_chunks += P.a_nch;
+    const CUtensorMap* map = is_a ? &mapA : &mapG;
+    const bool up2 = P.coord_b < 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int bx = box_begin; bx < box_end; ++bx) {
+      int t = bx;
+      const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+      const int th_i = t % P.tiles_h;
+      const int tb_i = t / P.tiles_h;
+      const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], (live_chunks + Cfg::NB) * BOX_BYTES);
+      }
+      __syncwarp();
+      if (active) {
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? lane * P.a_nch : 4) * BOX_BYTES;
+        tma_load_5d(dst, map, &full_bar[stage], 0, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0, chunk0);
+      }
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 0) {
     // ===== TMA producer: lane i owns box i of every stage (A chunks 0..3, then the G chunks), so the
     // per-instruction issue cost of the 4 KB boxes is spread over up to 12 lanes; all coordinates live in
     // registers (no indexed arrays) =====
@@ -738,9 +781,31 @@ int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, i
   P.tiles_b = cdiv(Bg, P.tb);
   if (g.ups == 1) { box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb; }
   else { box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th; }
-  static const bool sw128_experiment = getenv("RD_EXPERIMENT_REDUCE_SW128") != nullptr;
-  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, sw128_experiment ? 0 : 1));
-  RD_TRY(tc_encode_map(&plan->mapG, G, 4, gdims, gstrides, box, sw128_experiment ? 0 : 1));
+  // grouped 5-D maps (chunk index slowest) when the 128-row tile splits into whole same-tap groups
+  static const bool no_group = getenv("RESDEPTH_NO_GROUPED_TMA") != nullptr;
+  P.a_nch = 0;
+  const int a_nch = g.C % 128 == 0 ? 4 : (g.C == 64 ? 2 : (g.C == 32 ? 1 : 0));
+  bool grouped = false;
+  if (a_nch > 0 && !no_group) {
+    long long d5[5], s5[4], gd5[5], gs5[4];
+    int b5[5], gb5[5];
+    const long long csrc = g.ups == 1 ? g.C : 2LL * g.C;          // channels of one pixel row of the A tensor
+    d5[0] = 32; d5[1] = dims[1]; d5[2] = dims[2]; d5[3] = dims[3]; d5[4] = csrc / 32;
+    s5[0] = strides[0]; s5[1] = strides[1]; s5[2] = strides[2]; s5[3] = 128;
+    b5[0] = 32; b5[1] = box[1]; b5[2] = box[2]; b5[3] = box[3]; b5[4] = a_nch;
+    gd5[0] = 32; gd5[1] = gdims[1]; gd5[2] = gdims[2]; gd5[3] = gdims[3]; gd5[4] = N / 32;
+    gs5[0] = gstrides[0]; gs5[1] = gstrides[1]; gs5[2] = gstrides[2]; gs5[3] = 128;
+    gb5[0] = 32; gb5[1] = box[1]; gb5[2] = box[2]; gb5[3] = box[3]; gb5[4] = plan->BN / 32;
+    if (tc_encode_map(&plan->mapA, src, 5, d5, s5, b5, 1) == 0 && tc_encode_map(&plan->mapG, G, 5, gd5, gs5, gb5, 1) == 0) {
+      grouped = true;
+      P.a_nch = a_nch;
+      for (int t = 0; t < g.ntaps; ++t) P.a_chunk_off[t] = P.tap_off[t][0] / 32;
+    }
+  }
+  if (!grouped) {
+    RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 1));
+    RD_TRY(tc_encode_map(&plan->mapG, G, 4, gdims, gstrides, box, 1));
+  }
   // split the pixel boxes so that the CTAs fill ONE wave of the 148 SMs (1 CTA per SM: the kernel is not
   // persistent, a second partial wave would idle most of the chip), bounded by the partial buffer
   const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_b;

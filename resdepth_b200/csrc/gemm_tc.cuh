@@ -45,6 +45,10 @@ struct TcReduceParams {
   int tap_off[9][4];
   int boxes_per_split;
   float* part;           // [splits][Mrows][N]
+  // grouped loads (5-D tensor maps with the 32-channel chunk index as the slowest dimension): one TMA fetches
+  // a_nch consecutive chunks of A (same tap) / all BN/32 chunks of G; 0 = one 4-D TMA per chunk
+  int a_nch;
+  int a_chunk_off[9];    // per tap: chunk offset of the tap inside the A tensor map (2x2 gather: (b*C)/32)
 };
 
 struct TcReducePlan {
