@@ -553,17 +553,19 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
 //   * one CTA = one (128-row tile, BN-column tile, pixel split); accumulates in TMEM over its pixel boxes and
 //     writes its partial [128][BN] block; the un-pack kernels sum the splits.
 // ---------------------------------------------------------------------------------------------
-static constexpr int KP = 32;                       // pixels per pipeline stage (4 MMAs of K = 8)
-static constexpr int BOX_BYTES = KP * 128;
-
 template <int BN>
 struct ReduceCfg {
+  // pixels per pipeline stage: the TMA unit costs ~130 cycles per instruction, so narrow N tiles (few MMA cycles
+  // per pixel) take 64 pixels per stage to amortise it
+  static constexpr int KP = (BN == 256) ? 32 : 64;
+  static constexpr int BOX_BYTES = KP * 128;
   static constexpr int NB = BN / 32;
   static constexpr int STAGE_BYTES = (4 + NB) * BOX_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 3 : 4);
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
+static int reduce_kp(int BN) { return BN == 256 ? 32 : 64; }
 
 template <int BN, bool EXPERIMENT_KMAJOR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -634,11 +636,11 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], (live_chunks + Cfg::NB) * BOX_BYTES);
+        mbar_arrive_expect_tx(&full_bar[stage], (live_chunks + Cfg::NB) * Cfg::BOX_BYTES);
       }
       __syncwarp();
       if (active) {
-        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? lane * P.a_nch : 4) * BOX_BYTES;
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? lane * P.a_nch : 4) * Cfg::BOX_BYTES;
         tma_load_5d(dst, map, &full_bar[stage], 0, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0, chunk0);
       }
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -671,11 +673,11 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], (nchunks + Cfg::NB) * BOX_BYTES);
+        mbar_arrive_expect_tx(&full_bar[stage], (nchunks + Cfg::NB) * Cfg::BOX_BYTES);
       }
       __syncwarp();
       if (active) {
-        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + lane * BOX_BYTES;
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + lane * Cfg::BOX_BYTES;
         tma_load_4d(dst, map, &full_bar[stage], off0, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
       }
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -689,13 +691,13 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sg = sa + 4 * BOX_BYTES;
+        const uint32_t sg = sa + 4 * Cfg::BOX_BYTES;
 #pragma unroll
-        for (int k = 0; k < KP / 8; ++k) {                         // 8 pixels = two 4-row swizzle atoms per MMA
+        for (int k = 0; k < Cfg::KP / 8; ++k) {                         // 8 pixels = two 4-row swizzle atoms per MMA
           const uint64_t da = EXPERIMENT_KMAJOR ? smem_desc_sw128(sa + k * 32, 16, 1024)
-                                                : smem_desc_mn_sw128_32b(sa + k * 1024, BOX_BYTES, 512);
+                                                : smem_desc_mn_sw128_32b(sa + k * 1024, Cfg::BOX_BYTES, 512);
           const uint64_t dg = EXPERIMENT_KMAJOR ? smem_desc_sw128(sg + k * 32, 16, 1024)
-                                                : smem_desc_mn_sw128_32b(sg + k * 1024, BOX_BYTES, 512);
+                                                : smem_desc_mn_sw128_32b(sg + k * 1024, Cfg::BOX_BYTES, 512);
           mma_tf32(tmem_base, da, dg, idesc, (i | k) != 0);
         }
         tc_commit(&empty_bar[stage]);
@@ -771,6 +773,7 @@ int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, i
     gdims[0] = N; gdims[1] = Wg; gdims[2] = 1; gdims[3] = Hg;
     gstrides[0] = (long long)N * 4; gstrides[1] = (long long)Wg * N * 4; gstrides[2] = (long long)Wg * N * 4;
   }
+  const int KP = reduce_kp(plan->BN);
   P.tw = pow2_floor(Wg < KP ? Wg : KP);
   int th_max = KP / P.tw;
   P.th = pow2_floor(Hg < th_max ? Hg : th_max);

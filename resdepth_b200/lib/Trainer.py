@@ -221,22 +221,35 @@ class Trainer(object):
         self.model.train() if train else self.model.eval()
 
         x, y, loss_mask = self._extract_inputs_outputs_loss_masks(batch)
+        # the input tiles are needed first: copy them on the compute stream; target / mask / normalisation constants
+        # are only needed by the loss, so their copies ride a side stream and overlap the forward pass
         x = self._to_device(x, torch.float32)
-        y = self._to_device(y, torch.float32)
-        loss_mask = self._to_device(loss_mask)
-        mean = self._to_device(torch.flatten(batch['dsm_mean']), torch.float32)
-        std = self._to_device(torch.flatten(batch['dsm_std']), torch.float32)
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        self._copy_stream.wait_stream(main)
+        with torch.cuda.stream(self._copy_stream):
+            y = self._to_device(y, torch.float32)
+            loss_mask = self._to_device(loss_mask)
+            mean = self._to_device(torch.flatten(batch['dsm_mean']), torch.float32)
+            std = self._to_device(torch.flatten(batch['dsm_std']), torch.float32)
+            copied = torch.cuda.Event()
+            copied.record(self._copy_stream)
+        for t in (y, loss_mask, mean, std):
+            t.record_stream(main)
 
-        loss = self.device_step(x, y, loss_mask, mean, std, train)
+        loss = self.device_step(x, y, loss_mask, mean, std, train, wait_before_loss=copied)
 
         return {'MAE_metric': float(loss.item())}
 
-    def device_step(self, x, y, loss_mask, mean, std, train):
+    def device_step(self, x, y, loss_mask, mean, std, train, wait_before_loss=None):
         """The step on device-resident tensors: forward, fused loss (+ gradient seed), backward, gradient
         all-reduce; leaves ``param.grad`` set (views of the flat gradient arena) and returns the loss as a
         device tensor [1] without synchronising.  ``inference_one_batch`` = H2D copies + this + ``loss.item()``."""
         with torch.no_grad():
             y_pred = self.model._forward_native(x, _native.FWD_TRAIN if train else _native.FWD_EVAL)
+            if wait_before_loss is not None:
+                torch.cuda.current_stream(self.device).wait_event(wait_before_loss)
             loss, dy = self._compute_denormalized_loss(y_pred, y, loss_mask, mean, std, want_grad=train)
             if train:
                 grads = self.model._backward_native(x, dy, detach_copy=False)
