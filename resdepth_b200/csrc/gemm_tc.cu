@@ -59,8 +59,49 @@ struct RowsCfg {
   static constexpr int NBAR_A = HALO ? A_SLOTS : STAGES;
   static constexpr int NBAR_B = HALO ? B_SLOTS : 0;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
+
+// Epilogue store of one warp's 32 rows x 32 columns.  After tcgen05.ld a lane owns one ROW (32 consecutive floats of
+// one pixel); storing that directly makes every warp-level STG.128 touch 32 different 128-byte lines (32 L1 wavefronts
+// for 512 bytes).  The tile is therefore transposed through 4 KB of XOR-swizzled shared memory so that 8 lanes
+// cover one row: each warp-level access then touches 4 rows x 128 contiguous bytes (4 wavefronts).  `off` is the
+// element offset of the lane's row, `add` an optional tensor added element-wise at the same offsets (the additive
+// skip connection of the decoder).
+__device__ __forceinline__ void warp_store_rows(float* stg, int lane, const float (&v)[32], float* __restrict__ out,
+                                                long long off, bool ok, const float* __restrict__ add, int rnd) {
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4)
+    *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
+        make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+  __syncwarp();
+  const int c4 = lane & 7;
+  const unsigned off_lo = (unsigned)(off & 0xffffffffu), off_hi = (unsigned)((unsigned long long)off >> 32);
+  long long o[8];
+  unsigned okm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    const unsigned lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
+    okm |= (unsigned)__shfl_sync(0xffffffffu, (int)ok, r) << i;
+    o[i] = (long long)(((unsigned long long)hi << 32) | lo) + c4 * 4;
+  }
+  float4 a[8];
+  if (add) {                         // all eight loads in flight before any dependent store
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      a[i] = (okm >> i) & 1 ? __ldg(reinterpret_cast<const float4*>(add + o[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    float4 val = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+    if (add) { val.x += a[i].x; val.y += a[i].y; val.z += a[i].z; val.w += a[i].w; }
+    if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
+    if ((okm >> i) & 1) *reinterpret_cast<float4*>(out + o[i]) = val;
+  }
+  __syncwarp();
+}
 
 template <int BN, bool HALO>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
@@ -228,6 +269,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::DATA_BYTES + 512) + (warp - 4) * 1024;   // 4 KB per warp
     constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
     float cs1[NCH2], cs2[NCH2];
 #pragma unroll
@@ -257,25 +299,17 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         tmem_ld32(t_row + ch * 32, v);
         const int n = nt * BN + ch * 32;
         if (P.epi_mode == EPI_CONVT) {
+          // + bias here (row-independent); the additive skip is read in the transposed, coalesced domain
           const int Co = P.N >> 2;
           const int ab = n / Co, co = n - ab * Co;
-          if (valid) {
-            const size_t o = ((((size_t)b * 2 * P.Ho + 2 * h + (ab >> 1)) * 2 * P.Wo) + 2 * w + (ab & 1)) * Co + co;
-            const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
-            const float4* sp = P.skip ? reinterpret_cast<const float4*>(P.skip + o) : nullptr;
-            float4* op = reinterpret_cast<float4*>(P.out + o);
+          const long long o = (long long)(((((size_t)b * 2 * P.Ho + 2 * h + (ab >> 1)) * 2 * P.Wo) + 2 * w + (ab & 1)) * Co + co);
+          const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bv = __ldg(bp + j);
-              float4 r = make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
-              if (sp) {
-                const float4 sv = sp[j];
-                r.x += sv.x; r.y += sv.y; r.z += sv.z; r.w += sv.w;
-              }
-              if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
-              op[j] = r;
-            }
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(bp + j);
+            v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
           }
+          warp_store_rows(stg, lane, v, P.out, o, valid, P.skip, P.round_tf32);
         } else if (P.epi_mode == EPI_BNACT) {
           // eval-mode BatchNorm folded into the conv: a = act(acc*scale + shift); optional fused 2x2 max-pool
           // (the 2x2 window of a pixel lives in lanes l, l^1, l^tw, l^tw^1 of this warp)
@@ -292,52 +326,29 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             v[4 * j + 2] = y2 > 0.f ? y2 : y2 * slope;
             v[4 * j + 3] = y3 > 0.f ? y3 : y3 * slope;
           }
-          if (valid) {
-            float4* op = reinterpret_cast<float4*>(P.out + pix * P.N + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
-              op[j] = r;
-            }
-          }
+          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, nullptr, P.round_tf32);
           if (P.pool_out) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
               v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, P.tw));
             }
-            if (valid && !(w & 1) && !(h & 1)) {
-              const size_t pp = ((size_t)b * (P.Ho >> 1) + (h >> 1)) * (P.Wo >> 1) + (w >> 1);
-              float4* op = reinterpret_cast<float4*>(P.pool_out + pp * P.N + n);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (P.round_pool) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
-                op[j] = r;
-              }
-            }
+            const size_t pp = ((size_t)b * (P.Ho >> 1) + (h >> 1)) * (P.Wo >> 1) + (w >> 1);
+            warp_store_rows(stg, lane, v, P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1), nullptr,
+                            P.round_pool);
           }
         } else {
-          if (valid) {
-            float4* op = reinterpret_cast<float4*>(P.out + pix * P.N + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              if (P.round_tf32) { r.x = tf32_round(r.x); r.y = tf32_round(r.y); r.z = tf32_round(r.z); r.w = tf32_round(r.w); }
-              op[j] = r;
-            }
-          }
           if (P.epi_mode == EPI_STATS) {
-            float sq[32];
+            float sv[32], sq[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              v[j] = valid ? v[j] : 0.f;
-              sq[j] = v[j] * v[j];
+              sv[j] = valid ? v[j] : 0.f;
+              sq[j] = sv[j] * sv[j];
             }
-            cs1[ci] += warp_colsum32(v, lane);
+            cs1[ci] += warp_colsum32(sv, lane);
             cs2[ci] += warp_colsum32(sq, lane);
           }
+          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, nullptr, P.round_tf32);
         }
       }
       }   // sub-tiles
