@@ -245,6 +245,15 @@ def run_native(args):
         return ms, launches, prof, clocks, last
 
     K, W = args.steps, max(args.warmup, 3)
+    # secondary figure (BASELINE configs[1]): eval-mode forward only, 32 tiles per call, device-resident inputs
+    infer_x = resident[0]['input'][:32].contiguous()
+
+    def infer_step(i):
+        model.eval()
+        with torch.no_grad():
+            return model(infer_x)
+    infer_ms, _, _, _, _ = timed(infer_step, K, W)
+    model.train()
     ms, launches, prof, clocks, last_loss = timed(device_step, K, W, profile=True)
     loss_value = float(last_loss.item())
     e2e_ms, _, _, e2e_clocks, _ = timed(e2e_step, K, 2)
@@ -298,6 +307,8 @@ def run_native(args):
             'kernel_ms_per_step': breakdown,
             'kernel_ms_total_per_step': total_ms / K,
             'loss': loss_value,
+            'inference': {'workload': 'BASELINE configs[1]: eval-mode forward, 3-ch 256x256, depth 5, batch 32/GPU',
+                          'value': 32 * world * K / (infer_ms * 1e-3), 'unit': UNIT, 'ms_per_call': infer_ms / K},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

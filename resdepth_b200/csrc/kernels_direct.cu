@@ -362,32 +362,52 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
       dys[i] = (gh >= 0 && gh < H && gw >= 0 && gw < W) ? dy[((size_t)b * H + gh) * W + gw] : 0.f;
     }
     __syncthreads();
-    for (int p = grp; p < TH * TW; p += 16) {
-      const int lh = p / TW, lw = p % TW;
-      const int gh = h0 + lh, gw = w0 + lw;
-      if (gh >= H || gw >= W) continue;
-      float n[9];
+    // four pixels per iteration: their u loads are issued together (memory-level parallelism), then consumed
+    for (int p0 = grp; p0 < TH * TW; p0 += 64) {
+      float4 uvs[4][QPL];
+      bool okp[4];
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+      for (int i = 0; i < 4; ++i) {
+        const int p = p0 + 16 * i;
+        const int lh = p / TW, lw = p % TW;
+        const int gh = h0 + lh, gw = w0 + lw;
+        okp[i] = p < TH * TW && gh < H && gw < W;
+        const size_t o = (((size_t)b * H + gh) * W + gw) * C;
 #pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * HALO_W + (lw + 1 - (s2 - 1))];
-      if (lane16 == 0) dbacc += n[4];
-      const size_t o = (((size_t)b * H + gh) * W + gw) * C;
+        for (int j = 0; j < QPL; ++j) {
+          const int c = (lane16 + 16 * j) * 4;
+          uvs[i][j] = (okp[i] && c < C) ? __ldg(reinterpret_cast<const float4*>(u + o + c)) : make_float4(0, 0, 0, 0);
+        }
+      }
 #pragma unroll
-      for (int j = 0; j < QPL; ++j) {
-        const int c = (lane16 + 16 * j) * 4;
-        if (c < C) {
-          const float4 uv = __ldg(reinterpret_cast<const float4*>(u + o + c));
-          float4 d = make_float4(0, 0, 0, 0);
+      for (int i = 0; i < 4; ++i) {
+        if (!okp[i]) continue;
+        const int p = p0 + 16 * i;
+        const int lh = p / TW, lw = p % TW;
+        const int gh = h0 + lh, gw = w0 + lw;
+        float n[9];
 #pragma unroll
-          for (int k = 0; k < 9; ++k) {
-            d.x = fmaf(n[k], wr[j][k].x, d.x); d.y = fmaf(n[k], wr[j][k].y, d.y);
-            d.z = fmaf(n[k], wr[j][k].z, d.z); d.w = fmaf(n[k], wr[j][k].w, d.w);
-            dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
-            dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * HALO_W + (lw + 1 - (s2 - 1))];
+        if (lane16 == 0) dbacc += n[4];
+        const size_t o = (((size_t)b * H + gh) * W + gw) * C;
+#pragma unroll
+        for (int j = 0; j < QPL; ++j) {
+          const int c = (lane16 + 16 * j) * 4;
+          if (c < C) {
+            const float4 uv = uvs[i][j];
+            float4 d = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+              d.x = fmaf(n[k], wr[j][k].x, d.x); d.y = fmaf(n[k], wr[j][k].y, d.y);
+              d.z = fmaf(n[k], wr[j][k].z, d.z); d.w = fmaf(n[k], wr[j][k].w, d.w);
+              dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
+              dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
+            }
+            *reinterpret_cast<float4*>(du + o + c) = d;
+            dusum[j].x += d.x; dusum[j].y += d.y; dusum[j].z += d.z; dusum[j].w += d.w;
           }
-          *reinterpret_cast<float4*>(du + o + c) = d;
-          dusum[j].x += d.x; dusum[j].y += d.y; dusum[j].z += d.z; dusum[j].w += d.w;
         }
       }
     }
