@@ -125,7 +125,8 @@ int rd_profile_read(const rd_handle* h, int category, char* name64, double* ms, 
                     int64_t* launches, int64_t* calls);
 
 /* Test hooks: run ONE GEMM-shaped kernel in isolation (used by tests/ to compare the tcgen05 kernels with
- * the CUDA-core kernels and the oracle layer by layer).  engine: 0 = CUDA-core fp32, 1 = tcgen05 TF32.
+ * the CUDA-core kernels and the oracle layer by layer).  engine: 0 = CUDA-core fp32, 1 = tcgen05 TF32,
+ * 2 = tcgen05 bf16 (backward GEMMs; src, w_nk and g then point to bf16 tensors, out stays fp32).
  * kind: 0 = 3x3 taps (conv3x3 forward / dgrad / wgrad), 1 = single tap (transposed-conv forward),
  *       2 = 2x2 stride-2 gather (transposed-conv dgrad / wgrad; src is [B, 2H, 2W, C]).
  * rows:   out[B*H*W][N] = gather(src)[.][ntaps*C] x W, with w_kn = [ntaps*C][N] and w_nk = [N][ntaps*C].

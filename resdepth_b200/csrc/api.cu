@@ -883,7 +883,7 @@ int rd_debug_rows(int engine, int kind, const float* src, int batch, int hh, int
   e.out = out;
   if (engine == 0) return launch_gemm_rows_simt(src, g, w_kn, batch, n, e, nullptr, s);
   TcRowsPlan plan;
-  RD_TRY(tc_make_rows_plan(&plan, src, g, batch, w_nk, n));
+  RD_TRY(tc_make_rows_plan(&plan, src, g, batch, w_nk, n, engine == 2));   // engine 2: src / w_nk are bf16
   return launch_gemm_rows_tc(plan, e, nullptr, s);
 }
 
@@ -897,7 +897,7 @@ int rd_debug_reduce(int engine, int kind, const float* src, int batch, int hh, i
     RD_TRY(launch_gemm_reduce_simt(src, g, gm, batch, n, scratch, (size_t)scratch_floats, &S, s));
   } else {
     TcReducePlan plan;
-    RD_TRY(tc_make_reduce_plan(&plan, src, g, batch, gm, n, scratch, (size_t)scratch_floats));
+    RD_TRY(tc_make_reduce_plan(&plan, src, g, batch, gm, n, scratch, (size_t)scratch_floats, engine == 2));
     RD_TRY(launch_gemm_reduce_tc(plan, s));
     S = plan.splits;
   }

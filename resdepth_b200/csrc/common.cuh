@@ -157,6 +157,7 @@ struct Epilogue {
   const float* slope;     // device scalar: negative slope of the activation
   float* pool_out;        // [B,Ho/2,Wo/2,N] or null
   int round_pool;
+  void* out_b;            // optional bf16 copy of `out` (tcgen05 kernel only)
 };
 // C[M=B*Ho*Wo][N] = gather(src)[M][ntaps*C] * Bm[ntaps*C][N]
 int launch_gemm_rows_simt(const float* src, const Gather& g, const float* Bm, int B, int N, const Epilogue& e,

@@ -13,6 +13,7 @@
 //   * persistent CTAs, static tile schedule with a fixed N tile per CTA so BatchNorm column sums accumulate in
 //     registers across all of a CTA's tiles (one partial row per CTA-warp instead of one per tile).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -69,7 +70,8 @@ struct RowsCfg {
 // element offset of the lane's row, `add` an optional tensor added element-wise at the same offsets (the additive
 // skip connection of the decoder).
 __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const float (&v)[32], float* __restrict__ out,
-                                                long long off, bool ok, const float* __restrict__ add, int rnd) {
+                                                long long off, bool ok, const float* __restrict__ add, int rnd,
+                                                __nv_bfloat16* __restrict__ outb = nullptr) {
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4)
     *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
@@ -98,7 +100,16 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
     float4 val = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
     if (add) { val.x += a[i].x; val.y += a[i].y; val.z += a[i].z; val.w += a[i].w; }
     if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
-    if ((okm >> i) & 1) *reinterpret_cast<float4*>(out + o[i]) = val;
+    if ((okm >> i) & 1) {
+      *reinterpret_cast<float4*>(out + o[i]) = val;
+      if (outb) {
+        __nv_bfloat162 lo2 = __floats2bfloat162_rn(val.x, val.y), hi2 = __floats2bfloat162_rn(val.z, val.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+        *reinterpret_cast<uint2*>(outb + o[i]) = pk;
+      }
+    }
   }
   __syncwarp();
 }
@@ -156,14 +167,14 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (warp == 0) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[slot], HALO_BYTES);
-            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * 32, tw_i * P.tw * HALO_SUB - 1,
+            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * P.kchunk, tw_i * P.tw * HALO_SUB - 1,
                         th_i * P.th - 1, tb_i);
             if (++slot == Cfg::A_SLOTS) { slot = 0; phase ^= 1; }
           } else {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&bempty_bar[slot], phase ^ 1);
               mbar_arrive_expect_tx(&bfull_bar[slot], Cfg::B_BYTES);
-              tma_load_2d(bring + slot * Cfg::B_BYTES, &mapB, &bfull_bar[slot], (tap * P.cchunks + cc) * 32, nt * BN);
+              tma_load_2d(bring + slot * Cfg::B_BYTES, &mapB, &bfull_bar[slot], (tap * P.cchunks + cc) * P.kchunk, nt * BN);
               if (++slot == Cfg::B_SLOTS) { slot = 0; phase ^= 1; }
             }
           }
@@ -173,7 +184,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (HALO && warp == 1) {
     // ===== halo variant MMA issuer =====
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
+      const uint32_t idesc = P.bf16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int aslot = 0, bslot = 0;
       uint32_t aphase = 0, bphase = 0;
       const uint32_t a_base = smem_u32(smem), b_base = a_base + Cfg::A_SLOTS * HALO_SLOT;
@@ -194,9 +205,12 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
             for (int sub = 0; sub < HALO_SUB; ++sub)
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                mma_tf32(d_tmem + sub * BN, smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128),
-                         smem_desc_sw128(sb + k * 32, 16, 1024), idesc, (cc | tap | k) != 0);
+              for (int k = 0; k < 4; ++k) {      // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
+                const uint64_t da = smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128);
+                const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
+                if (P.bf16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
+                else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
+              }
             tc_commit(&bempty_bar[bslot]);
             if (++bslot == Cfg::B_SLOTS) { bslot = 0; bphase ^= 1; }
           }
@@ -229,9 +243,9 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           __syncwarp();
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if (lane == 0)
-            tma_load_4d(sa, &mapA, &full_bar[stage], off0 + cc * 32, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
+            tma_load_4d(sa, &mapA, &full_bar[stage], off0 + cc * P.kchunk, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
           else if (lane == 1)
-            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * 32, nt * BN);
+            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * P.kchunk, nt * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -239,7 +253,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (!HALO && warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = idesc_tf32(128, BN, 0, 0);
+      const uint32_t idesc = P.bf16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -255,8 +269,10 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint64_t da = smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 4 x (K = 8 fp32 = 32 bytes) inside the 128-byte swizzle atom
-            mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) { // 4 x 32 bytes of K (8 fp32 / 16 bf16) inside the 128-byte swizzle atom
+            if (P.bf16) mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            else mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           tc_commit(&empty_bar[stage]);             // frees the smem stage when these MMAs have read it
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -309,7 +325,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             const float4 bv = __ldg(bp + j);
             v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
           }
-          warp_store_rows(stg, lane, v, P.out, o, valid, P.skip, P.round_tf32);
+          warp_store_rows(stg, lane, v, P.out, o, valid, P.skip, P.round_tf32, reinterpret_cast<__nv_bfloat16*>(P.out_b));
         } else if (P.epi_mode == EPI_BNACT) {
           // eval-mode BatchNorm folded into the conv: a = act(acc*scale + shift); optional fused 2x2 max-pool
           // (the 2x2 window of a pixel lives in lanes l, l^1, l^tw, l^tw^1 of this warp)
@@ -348,7 +364,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             cs1[ci] += warp_colsum32(sv, lane);
             cs2[ci] += warp_colsum32(sq, lane);
           }
-          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, nullptr, P.round_tf32);
+          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, nullptr, P.round_tf32,
+                          reinterpret_cast<__nv_bfloat16*>(P.out_b));
         }
       }
       }   // sub-tiles
@@ -400,8 +417,8 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides_bytes,
-                  const int* box, int swizzle_atom32) {
+int tc_encode_map(CUtensorMap* map, const void* base, int rank, const long long* dims, const long long* strides_bytes,
+                  const int* box, int swizzle_atom32, int elem_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5];
@@ -413,7 +430,8 @@ int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long
     es[i] = 1;
     if (i > 0) gstr[i - 1] = (cuuint64_t)strides_bytes[i - 1];
   }
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                  (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -431,8 +449,8 @@ static int pow2_floor(int v) {
   return p;
 }
 
-bool tc_rows_eligible(const Gather& g, int N) {
-  if (g.C % 32 || N % 32) return false;
+bool tc_rows_eligible(const Gather& g, int N, int bf16) {
+  if (g.C % (bf16 ? 64 : 32) || N % 32) return false;
   if (g.ntaps == 4 && g.ups != 2) return false;
   return true;
 }
@@ -444,13 +462,16 @@ int tc_pick_bn(int N) {
   return 32;
 }
 
-int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B, const float* w_nk, int N) {
-  if (!tc_rows_eligible(g, N)) return fail("tc rows plan: shape not eligible (C=%d N=%d)", g.C, N);
+int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B, const void* w_nk, int N, int bf16) {
+  if (!tc_rows_eligible(g, N, bf16)) return fail("tc rows plan: shape not eligible (C=%d N=%d bf16=%d)", g.C, N, bf16);
   TcRowsParams& P = plan->p;
   std::memset(&P, 0, sizeof(P));
+  const int EB = bf16 ? 2 : 4;                 // element bytes; an operand row is always 128 bytes
   P.N = N;
   P.ntaps = g.ntaps;
-  P.cchunks = g.C / 32;
+  P.bf16 = bf16;
+  P.kchunk = 128 / EB;
+  P.cchunks = g.C / P.kchunk;
   plan->BN = tc_pick_bn(N);
   plan->halo = false;
   long long dims[4], strides[3];
@@ -465,8 +486,8 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
     P.coord_w = 1; P.coord_h = 2; P.coord_b = 3;
     for (int t = 0; t < g.ntaps; ++t) { P.tap_off[t][0] = 0; P.tap_off[t][1] = g.dw[t]; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
     dims[0] = g.C; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
-    strides[0] = (long long)g.C * 4; strides[1] = (long long)g.Ws * g.C * 4; strides[2] = (long long)g.Hs * g.Ws * g.C * 4;
-    box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb;
+    strides[0] = (long long)g.C * EB; strides[1] = (long long)g.Ws * g.C * EB; strides[2] = (long long)g.Hs * g.Ws * g.C * EB;
+    box[0] = P.kchunk; box[1] = P.tw; box[2] = P.th; box[3] = P.tb;
     static const bool no_halo = getenv("RESDEPTH_NO_HALO") != nullptr;
     if (g.ntaps == 9 && g.Ho >= 16 && g.Wo >= 16 && plan->BN <= 128 && !no_halo) {
       // halo-reuse variant: 16 x 16 pixel tiles (two 16 x 8 MMA sub-tiles), one 18 x 18 halo patch per 32-channel
@@ -486,17 +507,17 @@ int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B
     P.coord_w = 1; P.coord_h = 3; P.coord_b = -1;
     for (int t = 0; t < 4; ++t) { P.tap_off[t][0] = g.dw[t] * g.C; P.tap_off[t][1] = 0; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
     dims[0] = 2LL * g.C; dims[1] = g.Wo; dims[2] = 2; dims[3] = (long long)B * g.Ho;
-    strides[0] = 2LL * g.C * 4; strides[1] = (long long)g.Wo * 2 * g.C * 4; strides[2] = 2LL * g.Wo * 2 * g.C * 4;
-    box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th;
+    strides[0] = 2LL * g.C * EB; strides[1] = (long long)g.Wo * 2 * g.C * EB; strides[2] = 2LL * g.Wo * 2 * g.C * EB;
+    box[0] = P.kchunk; box[1] = P.tw; box[2] = 1; box[3] = P.th;
   }
   P.tiles_w = cdiv(P.Wo, P.tw * (plan->halo ? HALO_SUB : 1));
   P.tiles_h = cdiv(P.Ho, P.th);
   P.tiles_b = cdiv(P.Bo, P.tb);
-  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 0));
+  RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 0, EB));
   const long long K = (long long)g.ntaps * g.C;
-  long long wd[2] = {K, N}, ws[1] = {K * 4};
-  int wb[2] = {32, plan->BN};
-  RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb, 0));
+  long long wd[2] = {K, N}, ws[1] = {K * EB};
+  int wb[2] = {P.kchunk, plan->BN};
+  RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb, 0, EB));
   plan->valid = true;
   return 0;
 }
@@ -529,6 +550,7 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
   P.slope = e.slope;
   P.pool_out = e.pool_out;
   P.round_pool = e.round_pool;
+  P.out_b = e.out_b;
   if (e.mode == EPI_BNACT && e.pool_out && (P.tw < 2 || P.th < 2 || (P.Wo & 1) || (P.Ho & 1)))
     return fail("tc rows: fused pooling needs even image sizes and a tile of at least 2x2 pixels");
   const int n_tiles = P.N / plan.BN;
@@ -749,21 +771,167 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
   }
 }
 
-bool tc_reduce_eligible(const Gather& g, int N) {
-  return g.C % 32 == 0 && N % 32 == 0 && (g.ups == 1 || (g.ups == 2 && g.ntaps == 4));
+// ---------------------------------------------------------------------------------------------
+// bf16 variant of the reduce kernel (backward only; SURVEY.md 0.5: the gradients tolerate bf16 operands).
+// 64-channel chunks (128 bytes of bf16), standard 128-byte swizzle, MN-major atoms of 8 pixel rows, K = 16 pixels
+// per tcgen05.mma kind::f16 -- half the operand bytes and twice the MMA rate of the TF32 kernel.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+struct ReduceBCfg {
+  static constexpr int KP = 64;                      // pixels per stage = 4 MMAs of K = 16
+  static constexpr int BOX_BYTES = KP * 128;
+  static constexpr int NB = BN / 64;
+  static constexpr int STAGE_BYTES = (2 + NB) * BOX_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapG,
+                        const TcReduceParams P) {
+  using Cfg = ReduceBCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* done_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapG);
+    for (int i = 0; i < Cfg::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int box_begin = blockIdx.z * P.boxes_per_split;
+  int box_end = box_begin + P.boxes_per_split;
+  if (box_end > total_boxes) box_end = total_boxes;
+  const int nsteps = box_end > box_begin ? box_end - box_begin : 0;
+
+  if (warp == 0) {
+    const int groups = 2 / P.a_nch;                    // A: two 64-channel chunks per 128-row tile
+    const bool is_a = lane < 4;
+    int chunk0 = 0, off1 = 0, off2 = 0;
+    bool active;
+    if (is_a) {
+      const int r = m0 + lane * P.a_nch * 64;
+      active = lane < groups && r < P.Mrows;
+      const int tap = active ? r / P.Ca : 0;
+      chunk0 = P.a_chunk_off[tap] + (active ? (r % P.Ca) / 64 : 0);
+      off1 = P.tap_off[tap][1];
+      off2 = P.tap_off[tap][2];
+    } else {
+      active = lane == 4;
+      chunk0 = n0 / 64;
+    }
+    int live_chunks = 0;
+    for (int gI = 0; gI < groups; ++gI)
+      if (m0 + gI * P.a_nch * 64 < P.Mrows) live_chunks += P.a_nch;
+    const CUtensorMap* map = is_a ? &mapA : &mapG;
+    const bool up2 = P.coord_b < 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int bx = box_begin; bx < box_end; ++bx) {
+      int t = bx;
+      const int tw_i = t % P.tiles_w; t /= P.tiles_w;
+      const int th_i = t % P.tiles_h;
+      const int tb_i = t / P.tiles_h;
+      const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], (live_chunks + Cfg::NB) * Cfg::BOX_BYTES);
+      }
+      __syncwarp();
+      if (active) {
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? lane * P.a_nch : 2) * Cfg::BOX_BYTES;
+        tma_load_5d(dst, map, &full_bar[stage], 0, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0, chunk0);
+      }
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(128, BN, 1, 1);       // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nsteps; ++i) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sg = sa + 2 * Cfg::BOX_BYTES;
+#pragma unroll
+        for (int k = 0; k < Cfg::KP / 16; ++k)                      // 16 pixels = two 8-row swizzle atoms per MMA
+          mma_bf16(tmem_base, smem_desc_sw128(sa + k * 2048, Cfg::BOX_BYTES, 1024),
+                   smem_desc_sw128(sg + k * 2048, Cfg::BOX_BYTES, 1024), idesc, (i | k) != 0);
+        tc_commit(&empty_bar[stage]);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    float* out = P.part + ((size_t)blockIdx.z * P.Mrows + m) * P.N + n0;
+    if (nsteps > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      float v[32];
+      if (nsteps > 0) {
+        tmem_ld32(t_row + ch * 32, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (m < P.Mrows) {
+        float4* op = reinterpret_cast<float4*>(out + ch * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
 }
 
-int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, int B, const float* G, int N,
-                        float* part, size_t part_floats) {
-  if (!tc_reduce_eligible(g, N)) return fail("tc reduce plan: shape not eligible (C=%d N=%d)", g.C, N);
+bool tc_reduce_eligible(const Gather& g, int N, int bf16) {
+  if (!(g.ups == 1 || (g.ups == 2 && g.ntaps == 4))) return false;
+  if (bf16) return g.C % 64 == 0 && N % 64 == 0 && (g.C % 128 == 0 || g.C == 64);
+  return g.C % 32 == 0 && N % 32 == 0;
+}
+
+int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, int B, const void* G, int N,
+                        float* part, size_t part_floats, int bf16) {
+  if (!tc_reduce_eligible(g, N, bf16)) return fail("tc reduce plan: shape not eligible (C=%d N=%d bf16=%d)", g.C, N, bf16);
   TcReduceParams& P = plan->p;
   std::memset(&P, 0, sizeof(P));
+  P.bf16 = bf16;
+  const int EB = bf16 ? 2 : 4, CH = 128 / EB;          // element bytes, channels per 128-byte chunk
   P.Mrows = g.ntaps * g.C;
   P.Ca = g.C;
   P.N = N;
   P.ntaps = g.ntaps;
   P.part = part;
   plan->BN = tc_pick_bn(N);
+  if (bf16 && plan->BN < 64) return fail("tc reduce plan: bf16 needs N %% 64 == 0");
   long long dims[4], strides[3], gdims[4], gstrides[3];
   int box[4];
   int Wg, Hg, Bg;                                      // pixel grid of the contraction
@@ -772,19 +940,19 @@ int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, i
     P.coord_w = 1; P.coord_h = 2; P.coord_b = 3;
     for (int t = 0; t < g.ntaps; ++t) { P.tap_off[t][0] = 0; P.tap_off[t][1] = g.dw[t]; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
     dims[0] = g.C; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
-    strides[0] = (long long)g.C * 4; strides[1] = (long long)g.Ws * g.C * 4; strides[2] = (long long)g.Hs * g.Ws * g.C * 4;
+    strides[0] = (long long)g.C * EB; strides[1] = (long long)g.Ws * g.C * EB; strides[2] = (long long)g.Hs * g.Ws * g.C * EB;
     gdims[0] = N; gdims[1] = Wg; gdims[2] = Hg; gdims[3] = B;
-    gstrides[0] = (long long)N * 4; gstrides[1] = (long long)Wg * N * 4; gstrides[2] = (long long)Hg * Wg * N * 4;
+    gstrides[0] = (long long)N * EB; gstrides[1] = (long long)Wg * N * EB; gstrides[2] = (long long)Hg * Wg * N * EB;
   } else {
     Wg = g.Wo; Hg = B * g.Ho; Bg = 1;
     P.coord_w = 1; P.coord_h = 3; P.coord_b = -1;
     for (int t = 0; t < 4; ++t) { P.tap_off[t][0] = g.dw[t] * g.C; P.tap_off[t][1] = 0; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
     dims[0] = 2LL * g.C; dims[1] = g.Wo; dims[2] = 2; dims[3] = (long long)B * g.Ho;
-    strides[0] = 2LL * g.C * 4; strides[1] = (long long)g.Wo * 2 * g.C * 4; strides[2] = 2LL * g.Wo * 2 * g.C * 4;
+    strides[0] = 2LL * g.C * EB; strides[1] = (long long)g.Wo * 2 * g.C * EB; strides[2] = 2LL * g.Wo * 2 * g.C * EB;
     gdims[0] = N; gdims[1] = Wg; gdims[2] = 1; gdims[3] = Hg;
-    gstrides[0] = (long long)N * 4; gstrides[1] = (long long)Wg * N * 4; gstrides[2] = (long long)Wg * N * 4;
+    gstrides[0] = (long long)N * EB; gstrides[1] = (long long)Wg * N * EB; gstrides[2] = (long long)Wg * N * EB;
   }
-  const int KP = reduce_kp(plan->BN);
+  const int KP = bf16 ? 64 : reduce_kp(plan->BN);
   P.tw = pow2_floor(Wg < KP ? Wg : KP);
   int th_max = KP / P.tw;
   P.th = pow2_floor(Hg < th_max ? Hg : th_max);
@@ -793,29 +961,33 @@ int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, i
   P.tiles_w = cdiv(Wg, P.tw);
   P.tiles_h = cdiv(Hg, P.th);
   P.tiles_b = cdiv(Bg, P.tb);
-  if (g.ups == 1) { box[0] = 32; box[1] = P.tw; box[2] = P.th; box[3] = P.tb; }
-  else { box[0] = 32; box[1] = P.tw; box[2] = 1; box[3] = P.th; }
+  if (g.ups == 1) { box[0] = CH; box[1] = P.tw; box[2] = P.th; box[3] = P.tb; }
+  else { box[0] = CH; box[1] = P.tw; box[2] = 1; box[3] = P.th; }
   // grouped 5-D maps (chunk index slowest) when the 128-row tile splits into whole same-tap groups
   static const bool no_group = getenv("RESDEPTH_NO_GROUPED_TMA") != nullptr;
   P.a_nch = 0;
-  const int a_nch = g.C % 128 == 0 ? 4 : (g.C == 64 ? 2 : (g.C == 32 ? 1 : 0));
+  const int per_tile = 128 / CH;                         // chunks per 128-row M tile: 4 (fp32) or 2 (bf16)
+  const int a_nch = g.C % 128 == 0 ? per_tile : (g.C == 64 ? 64 / CH : (g.C == 32 && !bf16 ? 1 : 0));
   bool grouped = false;
-  if (a_nch > 0 && !no_group) {
+  if (a_nch > 0 && (!no_group || bf16)) {
     long long d5[5], s5[4], gd5[5], gs5[4];
     int b5[5], gb5[5];
     const long long csrc = g.ups == 1 ? g.C : 2LL * g.C;          // channels of one pixel row of the A tensor
-    d5[0] = 32; d5[1] = dims[1]; d5[2] = dims[2]; d5[3] = dims[3]; d5[4] = csrc / 32;
+    d5[0] = CH; d5[1] = dims[1]; d5[2] = dims[2]; d5[3] = dims[3]; d5[4] = csrc / CH;
     s5[0] = strides[0]; s5[1] = strides[1]; s5[2] = strides[2]; s5[3] = 128;
-    b5[0] = 32; b5[1] = box[1]; b5[2] = box[2]; b5[3] = box[3]; b5[4] = a_nch;
-    gd5[0] = 32; gd5[1] = gdims[1]; gd5[2] = gdims[2]; gd5[3] = gdims[3]; gd5[4] = N / 32;
+    b5[0] = CH; b5[1] = box[1]; b5[2] = box[2]; b5[3] = box[3]; b5[4] = a_nch;
+    gd5[0] = CH; gd5[1] = gdims[1]; gd5[2] = gdims[2]; gd5[3] = gdims[3]; gd5[4] = N / CH;
     gs5[0] = gstrides[0]; gs5[1] = gstrides[1]; gs5[2] = gstrides[2]; gs5[3] = 128;
-    gb5[0] = 32; gb5[1] = box[1]; gb5[2] = box[2]; gb5[3] = box[3]; gb5[4] = plan->BN / 32;
-    if (tc_encode_map(&plan->mapA, src, 5, d5, s5, b5, 1) == 0 && tc_encode_map(&plan->mapG, G, 5, gd5, gs5, gb5, 1) == 0) {
+    gb5[0] = CH; gb5[1] = box[1]; gb5[2] = box[2]; gb5[3] = box[3]; gb5[4] = plan->BN / CH;
+    // fp32 MN-major operands need the 32-byte-atom swizzle; bf16 the standard 128-byte swizzle
+    if (tc_encode_map(&plan->mapA, src, 5, d5, s5, b5, bf16 ? 0 : 1, EB) == 0 &&
+        tc_encode_map(&plan->mapG, G, 5, gd5, gs5, gb5, bf16 ? 0 : 1, EB) == 0) {
       grouped = true;
       P.a_nch = a_nch;
-      for (int t = 0; t < g.ntaps; ++t) P.a_chunk_off[t] = P.tap_off[t][0] / 32;
+      for (int t = 0; t < g.ntaps; ++t) P.a_chunk_off[t] = P.tap_off[t][0] / CH;
     }
   }
+  if (bf16 && !grouped) return fail("tc reduce plan: bf16 path needs grouped 5-D tensor maps (C=%d)", g.C);
   if (!grouped) {
     RD_TRY(tc_encode_map(&plan->mapA, src, 4, dims, strides, box, 1));
     RD_TRY(tc_encode_map(&plan->mapG, G, 4, gdims, gstrides, box, 1));
@@ -859,8 +1031,30 @@ static int launch_reduce(const TcReducePlan& plan, cudaStream_t s) {
   return 0;
 }
 
+template <int BN>
+static int launch_reduce_bf16(const TcReducePlan& plan, cudaStream_t s) {
+  using Cfg = ReduceBCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(cudaFuncSetAttribute(gemm_reduce_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid(plan.p.N / BN, cdiv(plan.p.Mrows, 128), plan.splits);
+  gemm_reduce_bf16_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapG, plan.p);
+  RD_LAUNCHED();
+  return 0;
+}
+
 int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s) {
   if (!plan.valid) return fail("tc reduce: plan not built");
+  if (plan.p.bf16) {
+    switch (plan.BN) {
+      case 256: return launch_reduce_bf16<256>(plan, s);
+      case 128: return launch_reduce_bf16<128>(plan, s);
+      case 64: return launch_reduce_bf16<64>(plan, s);
+    }
+    return fail("tc reduce bf16: unsupported BN=%d", plan.BN);
+  }
   switch (plan.BN) {
     case 256: return launch_reduce<256>(plan, s);
     case 128: return launch_reduce<128>(plan, s);

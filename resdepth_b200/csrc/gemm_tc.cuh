@@ -9,7 +9,9 @@ namespace rd {
 
 struct TcRowsParams {
   int N;                 // GEMM N (output channels of the layer / 4*C for the transposed conv)
-  int ntaps, cchunks;    // K = ntaps * cchunks * 32
+  int ntaps, cchunks;    // K = ntaps * cchunks * kchunk
+  int bf16;              // operands are bf16 (tcgen05 kind::f16, backward GEMMs) instead of fp32/TF32
+  int kchunk;            // channels per 128-byte operand row: 32 (fp32) or 64 (bf16)
   int tw, th, tb;        // pixel box of one 128-row tile (tw*th*tb == 128)
   int tiles_w, tiles_h, tiles_b;
   int Wo, Ho, Bo;        // output pixel grid the tile coordinates index
@@ -26,6 +28,7 @@ struct TcRowsParams {
   const float* slope;
   float* pool_out;
   int round_pool;
+  void* out_b;           // optional bf16 copy of `out` (same indexing): operand of a later bf16 GEMM
 };
 
 struct TcRowsPlan {
@@ -49,6 +52,7 @@ struct TcReduceParams {
   // a_nch consecutive chunks of A (same tap) / all BN/32 chunks of G; 0 = one 4-D TMA per chunk
   int a_nch;
   int a_chunk_off[9];    // per tap: chunk offset of the tap inside the A tensor map (2x2 gather: (b*C)/32)
+  int bf16;              // bf16 operands (64-channel chunks, kind::f16); always uses grouped loads
 };
 
 struct TcReducePlan {
@@ -58,18 +62,21 @@ struct TcReducePlan {
   bool valid = false;
 };
 
-bool tc_reduce_eligible(const Gather& g, int N);
+bool tc_reduce_eligible(const Gather& g, int N, int bf16 = 0);
 // src: tensor the gather reads (rows of the result); G: [pixels][N] matrix; part_floats: capacity of the split buffer
-int tc_make_reduce_plan(TcReducePlan* plan, const float* src, const Gather& g, int B, const float* G, int N,
-                        float* part, size_t part_floats);
+// bf16 != 0: src and G point to bf16 tensors
+int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, int B, const void* G, int N,
+                        float* part, size_t part_floats, int bf16 = 0);
 int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s);
 
-bool tc_rows_eligible(const Gather& g, int N);
+bool tc_rows_eligible(const Gather& g, int N, int bf16 = 0);
 int tc_pick_bn(int N);
-int tc_encode_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides_bytes,
-                  const int* box, int swizzle_atom32);
+// strides in BYTES; elem_bytes 4 (fp32) or 2 (bf16)
+int tc_encode_map(CUtensorMap* map, const void* base, int rank, const long long* dims, const long long* strides_bytes,
+                  const int* box, int swizzle_atom32, int elem_bytes = 4);
 // src: activation tensor the gather reads; w_nk: packed weights [N][ntaps*C] (K contiguous)
-int tc_make_rows_plan(TcRowsPlan* plan, const float* src, const Gather& g, int B, const float* w_nk, int N);
+// bf16 != 0: src and w_nk point to bf16 tensors (same logical shapes)
+int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B, const void* w_nk, int N, int bf16 = 0);
 int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partials, cudaStream_t s);
 
 }  // namespace rd

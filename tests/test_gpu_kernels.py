@@ -78,3 +78,49 @@ def test_reduce_kernels(engine, kind, B, H, W, C, N):
     torch.cuda.synchronize()
     err = float((out.cpu().double() - ref).abs().max())
     assert err <= 1e-4 * max(1.0, float(ref.abs().max())), err
+
+
+BF16_ROWS = [(0, 2, 16, 16, 64, 128), (0, 4, 8, 8, 256, 256), (0, 2, 32, 32, 64, 64), (0, 1, 24, 24, 128, 64),
+             (2, 2, 8, 8, 64, 64), (2, 3, 4, 4, 128, 128), (0, 2, 64, 64, 64, 512)]
+
+
+@pytest.mark.parametrize('kind,B,H,W,C,N', BF16_ROWS)
+def test_rows_kernel_bf16(kind, B, H, W, C, N):
+    """tcgen05 kind::f16 path of the backward GEMMs: operands are bf16 tensors, accumulation fp32."""
+    from resdepth_b200 import _native
+    g = torch.Generator().manual_seed(kind * 100 + C + N + H + 3)
+    ups = 2 if kind == 2 else 1
+    src = torch.randn(B, ups * H, ups * W, C, generator=g).bfloat16()
+    ntaps = {0: 9, 1: 1, 2: 4}[kind]
+    w_kn = (torch.randn(ntaps * C, N, generator=g) / (ntaps * C) ** 0.5).bfloat16()
+    ref = _gather_cpu(src.float(), kind, B, H, W, C) @ w_kn.double()
+    d_src, d_nk = src.to(DEV), w_kn.t().contiguous().to(DEV)
+    out = torch.full((B * H * W, N), float('nan'), device=DEV)
+    _native.debug_rows(2, kind, d_src.data_ptr(), B, H, W, C, None, d_nk.data_ptr(), N, out.data_ptr(),
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    err = float((out.cpu().double() - ref).abs().max())
+    assert err <= 2e-5 * max(1.0, float(ref.abs().max())), err
+
+
+BF16_REDUCE = [(0, 4, 8, 8, 64, 128), (0, 2, 16, 16, 128, 64), (0, 2, 32, 32, 64, 64), (2, 2, 8, 8, 64, 64),
+               (2, 3, 4, 4, 128, 128), (0, 2, 64, 64, 64, 256), (0, 4, 8, 8, 256, 512), (1, 2, 32, 32, 64, 64)]
+
+
+@pytest.mark.parametrize('kind,B,H,W,C,N', BF16_REDUCE)
+def test_reduce_kernel_bf16(kind, B, H, W, C, N):
+    from resdepth_b200 import _native
+    g = torch.Generator().manual_seed(kind * 100 + C + N + H + 11)
+    ups = 2 if kind == 2 else 1
+    src = torch.randn(B, ups * H, ups * W, C, generator=g).bfloat16()
+    G = torch.randn(B * H * W, N, generator=g).bfloat16()
+    ntaps = {0: 9, 1: 1, 2: 4}[kind]
+    ref = _gather_cpu(src.float(), kind, B, H, W, C).t() @ G.double()
+    d_src, d_G = src.to(DEV), G.to(DEV)
+    out = torch.full((ntaps * C, N), float('nan'), device=DEV)
+    scratch = torch.zeros(8 << 20, device=DEV)
+    _native.debug_reduce(2, kind, d_src.data_ptr(), B, H, W, C, d_G.data_ptr(), N, out.data_ptr(),
+                         scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    err = float((out.cpu().double() - ref).abs().max())
+    assert err <= 1e-4 * max(1.0, float(ref.abs().max())), err
