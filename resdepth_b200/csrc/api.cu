@@ -2,6 +2,7 @@
 // lib.UNet.UNet (reference lib/UNet.py:104-246), workspace management, and the forward / backward schedules.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,8 +43,11 @@ struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottl
   float *mean = nullptr, *invstd = nullptr, *scale = nullptr, *shift = nullptr;
   float *w_kn = nullptr, *w_nk = nullptr, *wd_kn = nullptr, *wd_nk = nullptr;
   bool tc = false;     // GEMMs of this block run on tcgen05
+  bool bb = false;     // backward GEMMs of this block take bf16 operands (dz, block input, dgrad weights)
   TcRowsPlan tc_fwd, tc_dgrad;
   TcReducePlan tc_wgrad;
+  // bf16 shadows (uint16 storage): a_b / p_b copies of a / p for consumers' bf16 GEMMs, dgrad weights
+  void *a_b = nullptr, *p_b = nullptr, *wd_nk_b = nullptr;
 };
 
 struct UpConv {        // ConvTranspose2d(C, C, 2, 2), or Upsample(bilinear, x2) + Conv2d 1x1 (lib/UNet.py:17-24)
@@ -55,8 +59,10 @@ struct UpConv {        // ConvTranspose2d(C, C, 2, 2), or Upsample(bilinear, x2)
   // transposed: w_kn = [ci][(ab,co)], w_nk = its transpose;  bilinear: w_kn = W^T = [ci][co], w_nk = W = [co][ci]
   float *w_kn = nullptr, *w_nk = nullptr;
   bool tc = false;
+  bool bb = false;     // bf16 backward GEMMs
   TcRowsPlan tc_fwd, tc_dgrad;
   TcReducePlan tc_wgrad;
+  void *u_b = nullptr, *w_kn_b = nullptr;   // bf16 copy of u (next conv's wgrad operand), bf16 dgrad weights
 };
 
 }  // namespace rd
@@ -87,6 +93,12 @@ struct rd_handle {
   float* xcol = nullptr;       // im2col expansion of the input for the first layer's tensor-core wgrad
   int xcol_k = 0;
   float* gt = nullptr;         // bilinear up-mode: gradient at the low-resolution 1x1-conv output
+  // bf16 backward (RESDEPTH_BWD=bf16, default in TF32 mode): dz and the skip gradients as bf16 GEMM operands
+  bool bwd_bf16 = false;
+  void* gy_b = nullptr;
+  std::vector<void*> gs_b;
+  void* xcol_b = nullptr;
+  int xcol_b_k = 0;
   // outer_skip_BN: BatchNorm2d(1) on input channel 0
   long long ob_gamma = -1, ob_beta = -1, ob_rm = -1, ob_rv = -1;
   float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
@@ -205,11 +217,14 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   const int D = h->depth;
   const bool tf = h->tf32();
   size_t max_out = 0, max_pool = 0;
+  const bool bf = bwd && h->bwd_bf16;
   auto block = [&](ConvBlock& b, int H, bool first) {
     const size_t n = (size_t)B * H * H * b.Cout;
     b.z = c.take(n);
     b.a = c.take(n);
     b.p = b.pool ? c.take(n / 4) : nullptr;
+    b.a_b = (bf && !b.pool) ? c.take(n / 2 + 64) : nullptr;
+    b.p_b = (bf && b.pool) ? c.take(n / 8 + 64) : nullptr;
     b.mean = c.take(b.Cout); b.invstd = c.take(b.Cout); b.scale = c.take(b.Cout); b.shift = c.take(b.Cout);
     if (!first) {
       const size_t wn = (size_t)9 * b.Cin * b.Cout;
@@ -217,6 +232,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
       b.wd_kn = c.take(wn);
       b.w_nk = tf ? c.take(wn) : nullptr;
       b.wd_nk = tf ? c.take(wn) : nullptr;
+      b.wd_nk_b = bf ? c.take(wn / 2 + 64) : nullptr;
     }
     if (n > max_out) max_out = n;
     if (b.pool && n / 4 > max_pool) max_pool = n / 4;
@@ -230,6 +246,8 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     u.w_kn = c.take((size_t)4 * u.C * u.C);
     u.w_nk = c.take((size_t)4 * u.C * u.C);
     u.t = u.bilinear ? c.take((size_t)B * (Hout / 2) * (Hout / 2) * u.C) : nullptr;
+    u.u_b = (bf && j < D - 1) ? c.take((size_t)B * Hout * Hout * u.C / 2 + 64) : nullptr;
+    u.w_kn_b = bf ? c.take((size_t)4 * u.C * u.C / 2 + 64) : nullptr;
     if (j < D - 1) block(h->dec[j], Hout, false);
   }
   h->partials_floats = (size_t)2 << 20;
@@ -248,11 +266,19 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     h->gh = c.take(max_out);
     h->gp = c.take(max_pool);
     h->gt = h->cfg.up_mode == RD_UP_BILINEAR ? c.take(max_out / 4 + 64) : nullptr;
+    h->gy_b = bf ? c.take(max_out / 2 + 64) : nullptr;
+    h->gs_b.assign(D, nullptr);
+    if (bf)
+      for (int i = 0; i < D; ++i) h->gs_b[i] = c.take((size_t)B * (T >> i) * (T >> i) * h->enc[i].Cout / 2 + 64);
+    h->xcol_b_k = h->enc[0].Cin * 9 <= 64 ? 64 : 128;
+    h->xcol_b = bf ? c.take((size_t)B * T * T * h->xcol_b_k / 2 + 64) : nullptr;
     h->xcol_k = (h->enc[0].Cin * 9 + 31) / 32 * 32;
-    h->xcol = tf ? c.take((size_t)B * T * T * h->xcol_k) : nullptr;
+    h->xcol = (tf && !bf) ? c.take((size_t)B * T * T * h->xcol_k) : nullptr;
   } else {
     h->xcol = nullptr;
     h->gt = nullptr;
+    h->gy_b = nullptr; h->xcol_b = nullptr;
+    h->gs_b.assign(D, nullptr);
     h->part = nullptr; h->part_floats = 0;
     h->g_skip.assign(D, nullptr);
     h->gy = h->gh = h->gp = nullptr;
@@ -263,32 +289,46 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
 // TMA descriptors + tile plans of every tcgen05 layer for the current workspace layout
 int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
   const int D = h->depth;
-  auto off = [&](ConvBlock& b) { b.tc = false; b.tc_fwd.valid = b.tc_dgrad.valid = b.tc_wgrad.valid = false; };
+  auto off = [&](ConvBlock& b) { b.tc = b.bb = false; b.tc_fwd.valid = b.tc_dgrad.valid = b.tc_wgrad.valid = false; };
   for (auto& b : h->enc) off(b);
   off(h->bott);
   for (auto& b : h->dec) off(b);
-  for (auto& u : h->ups) { u.tc = false; u.tc_fwd.valid = u.tc_dgrad.valid = u.tc_wgrad.valid = false; }
+  for (auto& u : h->ups) { u.tc = u.bb = false; u.tc_fwd.valid = u.tc_dgrad.valid = u.tc_wgrad.valid = false; }
   if (!h->tf32() || !tc_available()) return 0;
-  auto block = [&](ConvBlock& b, const float* src, int H) -> int {
+  const bool bf = bwd && h->gy_b != nullptr;            // bf16 operands for the backward GEMMs
+  auto block = [&](ConvBlock& b, const float* src, const void* src_b, int H) -> int {
     Gather gf = gather_conv3x3(H, H, b.Cin);
     Gather gd = gather_conv3x3(H, H, b.Cout);
     if (!tc_rows_eligible(gf, b.Cout) || !tc_rows_eligible(gd, b.Cin)) return 0;
     RD_TRY(tc_make_rows_plan(&b.tc_fwd, src, gf, B, b.w_nk, b.Cout));
     if (bwd) {
-      RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
-      if (tc_reduce_eligible(gf, b.Cout))
-        RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src, gf, B, h->gy, b.Cout, h->part, h->part_floats));
+      if (bf && src_b && b.wd_nk_b && tc_rows_eligible(gd, b.Cin, 1) && tc_reduce_eligible(gf, b.Cout, 1)) {
+        RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy_b, gd, B, b.wd_nk_b, b.Cin, 1));
+        RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src_b, gf, B, h->gy_b, b.Cout, h->part, h->part_floats, 1));
+        b.bb = true;
+      } else {
+        RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
+        if (tc_reduce_eligible(gf, b.Cout))
+          RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src, gf, B, h->gy, b.Cout, h->part, h->part_floats));
+      }
     }
     b.tc = true;
     return 0;
   };
-  if (bwd && h->xcol && h->enc[0].Cout % 32 == 0) {
-    Gather g0 = gather_plain(T, T, h->xcol_k);
-    if (tc_reduce_eligible(g0, h->enc[0].Cout))
-      RD_TRY(tc_make_reduce_plan(&h->enc[0].tc_wgrad, h->xcol, g0, B, h->gy, h->enc[0].Cout, h->part, h->part_floats));
+  if (bwd && h->enc[0].Cout % 32 == 0) {
+    ConvBlock& b0 = h->enc[0];
+    Gather gb = gather_plain(T, T, h->xcol_b_k);
+    if (bf && h->xcol_b && tc_reduce_eligible(gb, b0.Cout, 1)) {
+      RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, h->gy_b, b0.Cout, h->part, h->part_floats, 1));
+      b0.bb = true;
+    } else if (h->xcol) {
+      Gather g0 = gather_plain(T, T, h->xcol_k);
+      if (tc_reduce_eligible(g0, b0.Cout))
+        RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol, g0, B, h->gy, b0.Cout, h->part, h->part_floats));
+    }
   }
-  for (int i = 1; i < D; ++i) RD_TRY(block(h->enc[i], h->enc[i - 1].p, T >> i));
-  RD_TRY(block(h->bott, h->enc[D - 1].p, T >> D));
+  for (int i = 1; i < D; ++i) RD_TRY(block(h->enc[i], h->enc[i - 1].p, h->enc[i - 1].p_b, T >> i));
+  RD_TRY(block(h->bott, h->enc[D - 1].p, h->enc[D - 1].p_b, T >> D));
   for (int j = 0; j < D; ++j) {
     UpConv& u = h->ups[j];
     const int Hin = T >> (D - j);
@@ -308,13 +348,35 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     } else if (tc_rows_eligible(gf, 4 * u.C) && tc_rows_eligible(gd, u.C)) {
       RD_TRY(tc_make_rows_plan(&u.tc_fwd, src, gf, B, u.w_nk, 4 * u.C));
       if (bwd) {
-        RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
-        if (tc_reduce_eligible(gd, u.C))
-          RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, h->g_skip[D - 1 - j], gd, B, src, u.C, h->part, h->part_floats));
+        const void* src_b = j == 0 ? h->bott.a_b : h->dec[j - 1].a_b;
+        if (bf && src_b && u.w_kn_b && h->gs_b[D - 1 - j] && tc_rows_eligible(gd, u.C, 1) && tc_reduce_eligible(gd, u.C, 1)) {
+          RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->gs_b[D - 1 - j], gd, B, u.w_kn_b, u.C, 1));
+          RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, h->gs_b[D - 1 - j], gd, B, src_b, u.C, h->part, h->part_floats, 1));
+          u.bb = true;
+        } else {
+          RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
+          if (tc_reduce_eligible(gd, u.C))
+            RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, h->g_skip[D - 1 - j], gd, B, src, u.C, h->part, h->part_floats));
+        }
       }
       u.tc = true;
     }
-    if (j < D - 1) RD_TRY(block(h->dec[j], u.u, 2 * Hin));
+    if (j < D - 1) RD_TRY(block(h->dec[j], u.u, u.tc && !u.bilinear ? u.u_b : nullptr, 2 * Hin));
+  }
+  // the bf16 copy of an up-conv's output gradient is written by the tcgen05 dgrad of the decoder conv after it
+  // (level 0: by the last-conv backward); without that producer the up-conv falls back to TF32 operands
+  for (int j = 0; j < D - 1; ++j) {
+    UpConv& u = h->ups[j];
+    if (u.bb && !h->dec[j].tc) {
+      const int Hin = T >> (D - j);
+      const float* src = j == 0 ? h->bott.a : h->dec[j - 1].a;
+      Gather gd = gather_up2(Hin, Hin, u.C);
+      u.bb = false;
+      u.tc_wgrad.valid = false;
+      RD_TRY(tc_make_rows_plan(&u.tc_dgrad, h->g_skip[D - 1 - j], gd, B, u.w_kn, u.C));
+      if (tc_reduce_eligible(gd, u.C))
+        RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, h->g_skip[D - 1 - j], gd, B, src, u.C, h->part, h->part_floats));
+    }
   }
   return 0;
 }
@@ -353,7 +415,8 @@ int pack_weights(rd_handle* h, bool for_backward, cudaStream_t s) {
     if (!b.w_kn) return 0;
     // tcgen05 layers read the [N][K] copies, CUDA-core layers the [K][N] copies: pack only what is used
     return launch_pack_conv3x3(h->P + b.w, b.tc ? nullptr : b.w_kn, b.tc ? b.w_nk : nullptr,
-                               for_backward && !b.tc ? b.wd_kn : nullptr, for_backward && b.tc ? b.wd_nk : nullptr,
+                               for_backward && !b.tc ? b.wd_kn : nullptr,
+                               for_backward && b.tc && !b.bb ? b.wd_nk : nullptr, for_backward && b.bb ? b.wd_nk_b : nullptr,
                                b.Cout, b.Cin, rnd && b.tc, s);
   };
   for (auto& b : h->enc) RD_TRY(block(b));
@@ -361,7 +424,8 @@ int pack_weights(rd_handle* h, bool for_backward, cudaStream_t s) {
   for (auto& b : h->dec) RD_TRY(block(b));
   for (auto& u : h->ups) {
     if (u.bilinear) RD_TRY(launch_pack_conv1x1(h->P + u.w, u.w_nk, u.w_kn, u.C, u.C, rnd && u.tc, s));
-    else RD_TRY(launch_pack_convt(h->P + u.w, u.w_kn, u.w_nk, u.C, u.C, rnd && u.tc, s));
+    else RD_TRY(launch_pack_convt(h->P + u.w, u.w_kn, u.w_nk, for_backward && u.bb ? u.w_kn_b : nullptr, u.C, u.C,
+                                  rnd && u.tc, s));
   }
   return 0;
 }
@@ -405,7 +469,7 @@ int conv_block_forward_fused_eval(rd_handle* h, ConvBlock& b, int B, int H, int 
 
 // BN statistics finalize + fused normalise/activation(/pool) pass of one block
 int bn_act_forward(rd_handle* h, ConvBlock& b, int np, int B, int H, bool train, int round_a, int round_p,
-                   cudaStream_t s) {
+                   bool shadows, cudaStream_t s) {
   BnLayer L = bn_view(h, b);
   {
     ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
@@ -414,7 +478,7 @@ int bn_act_forward(rd_handle* h, ConvBlock& b, int np, int B, int H, bool train,
   const double n = (double)B * H * H * b.Cout;
   ProfScope ps(h, RD_PROF_BN_ACT_POOL, 0.0, 4.0 * n * (b.pool ? 2.25 : 2.0), s);
   return launch_bn_act_pool(b.z, b.scale, b.shift, act_view(h, b), b.a, b.pool ? b.p : nullptr, B, H, H, b.Cout,
-                            round_a, round_p, s);
+                            round_a, round_p, shadows ? b.a_b : nullptr, shadows ? b.p_b : nullptr, s);
 }
 
 }  // namespace
@@ -466,6 +530,10 @@ int rd_create(const rd_config* cfg, int device, rd_handle** out) {
     add_param(h, p + ".bias", C, &h->ups[j].bias);
     if (j < D - 1)
       plan_block(h, h->dec[j], "decoder." + std::to_string(j) + ".1", C, h->widths[D - 2 - j], cfg->act_decoder, false);
+  }
+  {
+    const char* env = getenv("RESDEPTH_BWD");
+    h->bwd_bf16 = cfg->math_mode == RD_MATH_TF32 && !(env && std::string(env) == "tf32");
   }
   add_param(h, "last_layer.weight", (long long)cfg->start_kernel * 9, &h->last_w);
   if (cfg->bias_conv_layer) add_param(h, "last_layer.bias", 1, &h->last_b);
@@ -585,7 +653,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     } else {
       RD_TRY(conv_block_forward(h, b, h->enc[i - 1].p, B, H, stats, &np, s));
     }
-    RD_TRY(bn_act_forward(h, b, np, B, H, train, 0, tf, s));
+    RD_TRY(bn_act_forward(h, b, np, B, H, train, 0, tf, save != 0, s));
   }
   {
     ConvBlock& b = h->bott;
@@ -594,7 +662,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
       RD_TRY(conv_block_forward_fused_eval(h, b, B, H, tf, 0, s));
     } else {
       RD_TRY(conv_block_forward(h, b, h->enc[D - 1].p, B, H, stats, &np, s));
-      RD_TRY(bn_act_forward(h, b, np, B, H, train, tf, 0, s));
+      RD_TRY(bn_act_forward(h, b, np, B, H, train, tf, 0, save != 0, s));
     }
   }
   const float* cur = h->bott.a;
@@ -608,6 +676,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     e.bias = h->P + u.bias;
     e.skip = h->enc[D - 1 - j].a;                       // additive skip, lib/UNet.py:96-101,220,224
     e.round_tf32 = (j < D - 1) ? tf : 0;
+    e.out_b = (save && u.tc && !u.bilinear) ? u.u_b : nullptr;       // bf16 copy: wgrad operand of the next conv
     if (u.bilinear) {
       // conv1x1(upsample(h)) == upsample(conv1x1(h)): 1-tap GEMM at the low resolution, then interpolate + bias + skip
       const double px = (double)B * Hc * Hc;
@@ -631,7 +700,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
         RD_TRY(conv_block_forward_fused_eval(h, b, B, Hc, tf, 0, s));
       } else {
         RD_TRY(conv_block_forward(h, b, u.u, B, Hc, stats, &np, s));
-        RD_TRY(bn_act_forward(h, b, np, B, Hc, train, tf, 0, s));
+        RD_TRY(bn_act_forward(h, b, np, B, Hc, train, tf, 0, save != 0, s));
       }
       cur = b.a;
     }
@@ -677,7 +746,7 @@ namespace {
 // output; src_in: the block's input (NHWC) or, for the first encoder block, the network input x (NCHW).
 int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float* g_pool, int B, int H,
                    const float* src_in, bool first, float* dgrad_out, int round_dgrad, float* dgrad_colsum,
-                   cudaStream_t s) {
+                   void* dgrad_out_b, cudaStream_t s) {
   BnLayer L = bn_view(h, b);
   Act act = act_view(h, b);
   const int do_bn = h->cfg.do_bn;
@@ -693,15 +762,17 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
   }
   {
     ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (2.0 + gin), s);
-    RD_TRY(launch_bn_bwd_apply(g_full, g_pool, b.z, L, act, h->coef, h->gy, B, H, H,
-                               h->tf32() && (b.tc || b.tc_wgrad.valid), s));
+    RD_TRY(launch_bn_bwd_apply(g_full, g_pool, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? h->gy_b : nullptr, B,
+                               H, H, h->tf32() && (b.tc || b.tc_wgrad.valid), s));
   }
   if (first) {
     ProfScope ps(h, RD_PROF_FIRST_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
     if (b.tc_wgrad.valid) {
-      RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, h->xcol_k, 1, s));
+      const int kc = b.bb ? h->xcol_b_k : h->xcol_k;
+      if (b.bb) RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, kc, s));
+      else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, s));
       RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, s));
-      RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, h->xcol_k, s));
+      RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, kc, s));
     } else {
       RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
     }
@@ -727,6 +798,7 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
     e.out = dgrad_out;
     e.partials = h->partials;
     e.round_tf32 = round_dgrad;
+    e.out_b = dgrad_out_b;
     int npart = 0;
     {
       ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
@@ -757,7 +829,8 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
   {
     const double px = (double)B * T * T;
     ProfScope ps(h, RD_PROF_LAST_BWD, 2.0 * 2.0 * 9.0 * C0 * px, 4.0 * px * (2.0 * C0 + 1.0), s);
-    RD_TRY(launch_conv_last_bwd(h->ups[D - 1].u, dy, h->P + h->last_w, h->g_skip[0], h->G + h->last_w,
+    RD_TRY(launch_conv_last_bwd(h->ups[D - 1].u, dy, h->P + h->last_w, h->g_skip[0],
+                                h->ups[D - 1].bb ? h->gs_b[0] : nullptr, h->G + h->last_w,
                                 h->last_b >= 0 ? h->G + h->last_b : nullptr, h->G + h->ups[D - 1].bias, h->scratch,
                                 h->scratch_floats, B, T, T, C0, s));
   }
@@ -822,17 +895,18 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     }
     }
     if (j == 0) {
-      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, nullptr, s));
+      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, nullptr, nullptr, s));
     } else {
       // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded
       RD_TRY(block_backward(h, h->dec[j - 1], h->gh, nullptr, B, Hin, h->ups[j - 1].u, false, h->g_skip[D - j],
-                            h->tf32() && h->ups[j - 1].tc, h->G + h->ups[j - 1].bias, s));
+                            h->tf32() && h->ups[j - 1].tc, h->G + h->ups[j - 1].bias,
+                            h->ups[j - 1].bb && h->dec[j - 1].tc ? h->gs_b[D - j] : nullptr, s));
     }
   }
   for (int i = D - 1; i >= 0; --i) {
     const int H = T >> i;
     RD_TRY(block_backward(h, h->enc[i], h->g_skip[i], h->gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
-                          i == 0 ? nullptr : h->gp, 0, nullptr, s));
+                          i == 0 ? nullptr : h->gp, 0, nullptr, nullptr, s));
   }
   return 0;
 }

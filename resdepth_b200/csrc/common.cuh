@@ -56,9 +56,10 @@ int launch_conv_last_fwd(const float* u, const float* w_oihw, const float* bias,
                          const float* x_affine, float* y, int B, int H, int W, int C, cudaStream_t s);
 // backward of the last conv: du NHWC (written), dW (OIHW [1,C,3,3], written), dbias (written if non-null)
 //   du_channel_sum (optional, [C]): per-channel sums of du = bias gradient of the transposed conv that produced u
-int launch_conv_last_bwd(const float* u, const float* dy, const float* w_oihw, float* du, float* dw, float* dbias,
-                         float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W, int C,
-                         cudaStream_t s);
+//   du_b (optional): bf16 copy of du
+int launch_conv_last_bwd(const float* u, const float* dy, const float* w_oihw, float* du, void* du_b, float* dw,
+                         float* dbias, float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W,
+                         int C, cudaStream_t s);
 
 // ---- elementwise / reduction kernels -----------------------------------------------------------
 struct BnLayer {
@@ -77,8 +78,9 @@ struct BnLayer {
 int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int training,
                        int do_bn, cudaStream_t s);
 // a = act(z*scale+shift)  (+ 2x2 max-pool into p when p != null).  round_*: store TF32-rounded values.
+//   a_b / p_b (optional): bf16 copies of a / p (operands of the bf16 backward GEMMs)
 int launch_bn_act_pool(const float* z, const float* scale, const float* shift, Act act, float* a, float* p,
-                       int B, int H, int W, int C, int round_a, int round_p, cudaStream_t s);
+                       int B, int H, int W, int C, int round_a, int round_p, void* a_b, void* p_b, cudaStream_t s);
 // backward pass 1:  gA = unpool(g_pool, a) + g_full ; gY = gA*act'(y) ; per-block partial sums
 //   partials [nblk][C][3] = (sum gY, sum gY*(z-mean), sum gA*min(y,0))
 int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
@@ -88,8 +90,9 @@ int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, 
                            int batch_stats, float* dgamma, float* dbeta, float* dslope, float* dslope_scratch, void* coef,
                            cudaStream_t s);
 // pass 2:  dz = cs*(gY - c1 - (z-mean)*c2), gY recomputed from the same inputs as pass 1
+//   dz (fp32) and/or dz_b (bf16) receive the result; either may be null
 int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
-                        const void* coef, float* dz, int B, int H, int W, int round_out, cudaStream_t s);
+                        const void* coef, float* dz, void* dz_b, int B, int H, int W, int round_out, cudaStream_t s);
 
 int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
                 float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s);
@@ -105,9 +108,10 @@ int launch_sum_partials(const float* part, int nparts, int n, int row_stride, in
                         cudaStream_t s);
 
 // weight packing (see kernels_elementwise.cu for the layouts); null outputs are skipped
-int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, int Co, int Ci, int round_tf32,
-                        cudaStream_t s);
-int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int round_tf32, cudaStream_t s);
+//   dnk_b / kn_b: bf16 copies of the dgrad weight matrices for the bf16 backward GEMMs
+int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, void* dnk_b, int Co, int Ci,
+                        int round_tf32, cudaStream_t s);
+int launch_pack_convt(const float* w, float* kn, float* nk, void* kn_b, int Ci, int Co, int round_tf32, cudaStream_t s);
 // reduce split partials and un-pack to the PyTorch layouts
 //   conv: part [S][(t,ci)][co] -> dW OIHW ;  convT: part [S][(a,b,co)][ci] -> dW [ci][co][2][2]
 int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s);
@@ -128,6 +132,7 @@ int launch_pack_conv1x1(const float* w, float* w_copy, float* w_t, int Co, int C
 // first-layer wgrad on tensor cores: im2col expansion of the NCHW input and un-packing of the reduce-GEMM result
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int round_tf32,
                         cudaStream_t s);
+int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s);
 int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s);
 // column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)
 int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,

@@ -114,7 +114,7 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
   __syncwarp();
 }
 
-template <int BN, bool HALO>
+template <int BN, bool HALO, bool BF16>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TcRowsParams P) {
@@ -167,14 +167,14 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (warp == 0) {
             mbar_wait(&empty_bar[slot], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[slot], HALO_BYTES);
-            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * P.kchunk, tw_i * P.tw * HALO_SUB - 1,
+            tma_load_4d(smem + slot * HALO_SLOT, &mapA, &full_bar[slot], cc * (BF16 ? 64 : 32), tw_i * P.tw * HALO_SUB - 1,
                         th_i * P.th - 1, tb_i);
             if (++slot == Cfg::A_SLOTS) { slot = 0; phase ^= 1; }
           } else {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&bempty_bar[slot], phase ^ 1);
               mbar_arrive_expect_tx(&bfull_bar[slot], Cfg::B_BYTES);
-              tma_load_2d(bring + slot * Cfg::B_BYTES, &mapB, &bfull_bar[slot], (tap * P.cchunks + cc) * P.kchunk, nt * BN);
+              tma_load_2d(bring + slot * Cfg::B_BYTES, &mapB, &bfull_bar[slot], (tap * P.cchunks + cc) * (BF16 ? 64 : 32), nt * BN);
               if (++slot == Cfg::B_SLOTS) { slot = 0; phase ^= 1; }
             }
           }
@@ -184,7 +184,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (HALO && warp == 1) {
     // ===== halo variant MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = P.bf16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
+      constexpr uint32_t idesc = BF16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int aslot = 0, bslot = 0;
       uint32_t aphase = 0, bphase = 0;
       const uint32_t a_base = smem_u32(smem), b_base = a_base + Cfg::A_SLOTS * HALO_SLOT;
@@ -208,7 +208,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               for (int k = 0; k < 4; ++k) {      // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
                 const uint64_t da = smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128);
                 const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
-                if (P.bf16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
+                if (BF16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
                 else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
               }
             tc_commit(&bempty_bar[bslot]);
@@ -243,9 +243,9 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           __syncwarp();
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           if (lane == 0)
-            tma_load_4d(sa, &mapA, &full_bar[stage], off0 + cc * P.kchunk, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
+            tma_load_4d(sa, &mapA, &full_bar[stage], off0 + cc * (BF16 ? 64 : 32), w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0);
           else if (lane == 1)
-            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * P.kchunk, nt * BN);
+            tma_load_2d(sa + Cfg::A_BYTES, &mapB, &full_bar[stage], (tap * P.cchunks + cc) * (BF16 ? 64 : 32), nt * BN);
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -253,7 +253,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (!HALO && warp == 1) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
-      const uint32_t idesc = P.bf16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
+      constexpr uint32_t idesc = BF16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -270,7 +270,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint64_t db = smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
 #pragma unroll
           for (int k = 0; k < 4; ++k) { // 4 x 32 bytes of K (8 fp32 / 16 bf16) inside the 128-byte swizzle atom
-            if (P.bf16) mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            if (BF16) mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
             else mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
           tc_commit(&empty_bar[stage]);             // frees the smem stage when these MMAs have read it
@@ -522,18 +522,22 @@ int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B,
   return 0;
 }
 
-template <int BN, bool HALO>
-static int launch_rows(const TcRowsPlan& plan, const TcRowsParams& P, int grid, cudaStream_t s) {
+template <int BN, bool HALO, bool BF16>
+static int launch_rows_t(const TcRowsPlan& plan, const TcRowsParams& P, int grid, cudaStream_t s) {
   using Cfg = RowsCfg<BN, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, HALO, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_rows_tc_kernel<BN, HALO><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
+  gemm_rows_tc_kernel<BN, HALO, BF16><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
   RD_LAUNCHED();
   return 0;
+}
+template <int BN, bool HALO>
+static int launch_rows(const TcRowsPlan& plan, const TcRowsParams& P, int grid, cudaStream_t s) {
+  return P.bf16 ? launch_rows_t<BN, HALO, true>(plan, P, grid, s) : launch_rows_t<BN, HALO, false>(plan, P, grid, s);
 }
 
 int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partials, cudaStream_t s) {

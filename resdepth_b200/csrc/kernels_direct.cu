@@ -4,6 +4,8 @@
 //       replaces nn.Conv2d of encoder[0]            (reference lib/UNet.py:158-162, 4-5)
 //   * last  conv  C -> 1 (+bias, +outer residual)     (reference lib/UNet.py:184,227,229-244)
 //   * their weight/input gradients (autograd of the above, reference lib/Trainer.py:179)
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace rd {
@@ -328,8 +330,8 @@ int launch_conv_last_fwd(const float* u, const float* w, const float* bias, cons
 template <int QPL>
 __global__ void __launch_bounds__(256)
 conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ w,
-                     float* __restrict__ du, float* __restrict__ part, int B, int H, int W, int C, int tiles_x,
-                     int tiles_y, int ntiles) {
+                     float* __restrict__ du, __nv_bfloat16* __restrict__ du_b, float* __restrict__ part, int B, int H,
+                     int W, int C, int tiles_x, int tiles_y, int ntiles) {
   __shared__ float dys[HALO_H * HALO_W];
   extern __shared__ float red_dyn[];                  // [16][RS]
   constexpr int NDW = 9 * 4 * 16 * QPL;               // weight-gradient entries, then 64*QPL channel sums of du, then db
@@ -406,6 +408,13 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
               dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
             }
             *reinterpret_cast<float4*>(du + o + c) = d;
+            if (du_b) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+              uint2 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&lo);
+              pk.y = *reinterpret_cast<uint32_t*>(&hi);
+              *reinterpret_cast<uint2*>(du_b + o + c) = pk;
+            }
             dusum[j].x += d.x; dusum[j].y += d.y; dusum[j].z += d.z; dusum[j].w += d.w;
           }
         }
@@ -446,9 +455,9 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
   }
 }
 
-int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float* du, float* dw, float* dbias,
-                         float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W, int C,
-                         cudaStream_t s) {
+int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float* du, void* du_b, float* dw,
+                         float* dbias, float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W,
+                         int C, cudaStream_t s) {
   if (C % 4 || C > 128) return fail("conv_last_bwd: unsupported C=%d", C);
   const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
   const int ntiles = tiles_x * tiles_y * B;
@@ -457,11 +466,13 @@ int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float*
   if ((size_t)grid * PN > scratch_floats) return fail("conv_last_bwd: scratch too small");
   if (C <= 64) {
     const int smem = 16 * (10 * 4 * 16 * 1 + 1) * (int)sizeof(float);
-    conv_last_bwd_kernel<1><<<grid, 256, smem, s>>>(u, dy, w, du, scratch, B, H, W, C, tiles_x, tiles_y, ntiles);
+    conv_last_bwd_kernel<1><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B, H,
+                                                    W, C, tiles_x, tiles_y, ntiles);
   } else {
     const int smem = 16 * (10 * 4 * 16 * 2 + 1) * (int)sizeof(float);
     RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_last_bwd_kernel<2><<<grid, 256, smem, s>>>(u, dy, w, du, scratch, B, H, W, C, tiles_x, tiles_y, ntiles);
+    conv_last_bwd_kernel<2><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B, H,
+                                                    W, C, tiles_x, tiles_y, ntiles);
   }
   RD_LAUNCHED();
   RD_TRY(launch_sum_partials(scratch, grid, C * 9, PN, 1, dw, s));

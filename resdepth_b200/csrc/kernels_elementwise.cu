@@ -6,6 +6,8 @@
 //   * Adam / SGD over a flat arena                              (lib/utils.py:329-334, lib/Trainer.py:218)
 //   * linear-blend accumulation                                 (lib/evaluation.py:484-567)
 //   * weight packing / gradient un-packing for the GEMM-shaped layers
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "../../include/resdepth_b200.h"
 
@@ -24,6 +26,14 @@ __device__ __forceinline__ float4 tf32_rn4(float4 v) {
   return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
 }
 __device__ __forceinline__ float act1(float y, float slope) { return y > 0.f ? y : y * slope; }
+// 4 floats -> 4 bf16 (round to nearest even), one 8-byte store
+__device__ __forceinline__ void st4_bf16(void* base, size_t elem, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem) = pk;
+}
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
@@ -103,7 +113,7 @@ template <bool POOL>
 __global__ void __launch_bounds__(EW_THREADS)
 bn_act_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ slope_p, float* __restrict__ a, float* __restrict__ p, int B, int H,
-                   int W, int C, int round_a, int round_p) {
+                   int W, int C, int round_a, int round_p, void* __restrict__ a_b, void* __restrict__ p_b) {
   const int Q = C >> 2;
   const float slope = *slope_p;
   if (POOL) {
@@ -130,10 +140,13 @@ bn_act_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale,
         r.z = act1(fmaf(v.z, sc.z, sh.z), slope);
         r.w = act1(fmaf(v.w, sc.w, sh.w), slope);
         st4(a + o, round_a ? tf32_rn4(r) : r);
+        if (a_b) st4_bf16(a_b, o, r);
         if (k == 0) m = r;
         else { m.x = fmaxf(m.x, r.x); m.y = fmaxf(m.y, r.y); m.z = fmaxf(m.z, r.z); m.w = fmaxf(m.w, r.w); }
       }
-      st4(p + (((size_t)b * Hp + hp) * Wp + wp) * C + q * 4, round_p ? tf32_rn4(m) : m);
+      const size_t po = (((size_t)b * Hp + hp) * Wp + wp) * C + q * 4;
+      st4(p + po, round_p ? tf32_rn4(m) : m);
+      if (p_b) st4_bf16(p_b, po, m);
     }
   } else {
     const long long total = (long long)B * H * W * Q;
@@ -149,22 +162,23 @@ bn_act_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale,
       r.z = act1(fmaf(v.z, sc.z, sh.z), slope);
       r.w = act1(fmaf(v.w, sc.w, sh.w), slope);
       st4(a + i * 4, round_a ? tf32_rn4(r) : r);
+      if (a_b) st4_bf16(a_b, (size_t)i * 4, r);
     }
   }
 }
 
 int launch_bn_act_pool(const float* z, const float* scale, const float* shift, Act act, float* a, float* p, int B,
-                       int H, int W, int C, int round_a, int round_p, cudaStream_t s) {
+                       int H, int W, int C, int round_a, int round_p, void* a_b, void* p_b, cudaStream_t s) {
   if (C % 4) return fail("bn_act_pool: C=%d not a multiple of 4", C);
   if (p) {
     if ((H | W) & 1) return fail("bn_act_pool: odd size %dx%d cannot be pooled", H, W);
     const long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
     bn_act_pool_kernel<true><<<ew_grid(total), EW_THREADS, 0, s>>>(z, scale, shift, act.slope, a, p, B, H, W, C,
-                                                                    round_a, round_p);
+                                                                    round_a, round_p, a_b, p_b);
   } else {
     const long long total = (long long)B * H * W * (C / 4);
     bn_act_pool_kernel<false><<<ew_grid(total), EW_THREADS, 0, s>>>(z, scale, shift, act.slope, a, p, B, H, W, C,
-                                                                     round_a, round_p);
+                                                                     round_a, round_p, a_b, p_b);
   }
   RD_LAUNCHED();
   return 0;
@@ -187,7 +201,7 @@ __global__ void __launch_bounds__(EW_THREADS, APPLY ? 4 : 2)
 bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool, const float* __restrict__ z,
               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ slope_p,
               const float* __restrict__ mean, const BwdCoef* __restrict__ coef, float* __restrict__ dz,
-              float* __restrict__ partials, int B, int H, int W, int C, int round_out) {
+              float* __restrict__ partials, int B, int H, int W, int C, int round_out, void* __restrict__ dz_b) {
   extern __shared__ float red[];                       // reduce: [PL][C][3]
   const int Q = C >> 2;
   const int PL = EW_THREADS / Q;                       // pixel lanes per block
@@ -261,7 +275,8 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
           for (int k = 0; k < 4; ++k) {
             const size_t o = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
             float4 r = make_float4(out[k][0], out[k][1], out[k][2], out[k][3]);
-            st4(dz + o, round_out ? tf32_rn4(r) : r);
+            if (dz) st4(dz + o, round_out ? tf32_rn4(r) : r);
+            if (dz_b) st4_bf16(dz_b, o, r);
           }
         }
       } else {
@@ -284,7 +299,8 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
         }
         if (APPLY) {
           float4 r = make_float4(out[0], out[1], out[2], out[3]);
-          st4(dz + o, round_out ? tf32_rn4(r) : r);
+          if (dz) st4(dz + o, round_out ? tf32_rn4(r) : r);
+          if (dz_b) st4_bf16(dz_b, o, r);
         }
       }
     }
@@ -324,13 +340,13 @@ int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* 
     grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL);
     RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     bn_bwd_kernel<true, false><<<grid, EW_THREADS, smem, s>>>(g_full, g_pool, z, L.scale, L.shift, act.slope, L.mean,
-                                                              nullptr, nullptr, partials, B, H, W, C, 0);
+                                                              nullptr, nullptr, partials, B, H, W, C, 0, nullptr);
   } else {
     if (!g_full) return fail("bn_bwd: no incoming gradient");
     grid = bwd_grid((long long)B * H * W, PL);
     RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     bn_bwd_kernel<false, false><<<grid, EW_THREADS, smem, s>>>(g_full, nullptr, z, L.scale, L.shift, act.slope,
-                                                               L.mean, nullptr, nullptr, partials, B, H, W, C, 0);
+                                                               L.mean, nullptr, nullptr, partials, B, H, W, C, 0, nullptr);
   }
   RD_LAUNCHED();
   *n_partials = grid;
@@ -409,19 +425,19 @@ int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, 
 }
 
 int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
-                        const void* coef, float* dz, int B, int H, int W, int round_out, cudaStream_t s) {
+                        const void* coef, float* dz, void* dz_b, int B, int H, int W, int round_out, cudaStream_t s) {
   const int C = L.C, Q = C / 4;
   const int PL = EW_THREADS / Q;
   if (g_pool) {
     const int grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL) * 2;
     bn_bwd_kernel<true, true><<<grid, EW_THREADS, 0, s>>>(g_full, g_pool, z, L.scale, L.shift, act.slope, L.mean,
                                                           reinterpret_cast<const BwdCoef*>(coef), dz, nullptr, B, H,
-                                                          W, C, round_out);
+                                                          W, C, round_out, dz_b);
   } else {
     const int grid = bwd_grid((long long)B * H * W, PL) * 2;
     bn_bwd_kernel<false, true><<<grid, EW_THREADS, 0, s>>>(g_full, nullptr, z, L.scale, L.shift, act.slope, L.mean,
                                                            reinterpret_cast<const BwdCoef*>(coef), dz, nullptr, B, H,
-                                                           W, C, round_out);
+                                                           W, C, round_out, dz_b);
   }
   RD_LAUNCHED();
   return 0;
@@ -628,7 +644,8 @@ int launch_fill(float* p, float v, long long n, cudaStream_t s) {
 //     the transpose is also the K x N matrix of the dgrad GEMM (K = (ab,co), N = ci), and kn its N x K form.
 // ----------------------------------------------------------------------------------------------
 __global__ void pack_conv3x3_kernel(const float* __restrict__ w, float* __restrict__ kn, float* __restrict__ nk,
-                                    float* __restrict__ dkn, float* __restrict__ dnk, int Co, int Ci, int rnd) {
+                                    float* __restrict__ dkn, float* __restrict__ dnk, __nv_bfloat16* __restrict__ dnk_b,
+                                    int Co, int Ci, int rnd) {
   const long long total = (long long)Co * Ci * 9;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const int t = (int)(i % 9);
@@ -641,17 +658,19 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, float* __restri
     const int tr = 8 - t;
     if (dkn) dkn[((size_t)tr * Co + co) * Ci + ci] = v;
     if (dnk) dnk[(size_t)ci * 9 * Co + (size_t)tr * Co + co] = v;
+    if (dnk_b) dnk_b[(size_t)ci * 9 * Co + (size_t)tr * Co + co] = __float2bfloat16_rn(w[i]);
   }
 }
-int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, int Co, int Ci, int rnd,
-                        cudaStream_t s) {
-  pack_conv3x3_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(w, kn, nk, dkn, dnk, Co, Ci, rnd);
+int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, void* dnk_b, int Co, int Ci,
+                        int rnd, cudaStream_t s) {
+  pack_conv3x3_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(w, kn, nk, dkn, dnk,
+                                                                      reinterpret_cast<__nv_bfloat16*>(dnk_b), Co, Ci, rnd);
   RD_LAUNCHED();
   return 0;
 }
 
-__global__ void pack_convt_kernel(const float* __restrict__ w, float* __restrict__ kn, float* __restrict__ nk, int Ci,
-                                  int Co, int rnd) {
+__global__ void pack_convt_kernel(const float* __restrict__ w, float* __restrict__ kn, float* __restrict__ nk,
+                                  __nv_bfloat16* __restrict__ kn_b, int Ci, int Co, int rnd) {
   const long long total = (long long)Ci * Co * 4;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
     const int ab = (int)(i % 4);
@@ -660,11 +679,13 @@ __global__ void pack_convt_kernel(const float* __restrict__ w, float* __restrict
     float v = w[i];
     if (rnd) v = tf32_rn(v);
     if (kn) kn[(size_t)ci * 4 * Co + (size_t)ab * Co + co] = v;
+    if (kn_b) kn_b[(size_t)ci * 4 * Co + (size_t)ab * Co + co] = __float2bfloat16_rn(w[i]);
     if (nk) nk[((size_t)ab * Co + co) * Ci + ci] = v;
   }
 }
-int launch_pack_convt(const float* w, float* kn, float* nk, int Ci, int Co, int rnd, cudaStream_t s) {
-  pack_convt_kernel<<<ew_grid((long long)Ci * Co * 4), 256, 0, s>>>(w, kn, nk, Ci, Co, rnd);
+int launch_pack_convt(const float* w, float* kn, float* nk, void* kn_b, int Ci, int Co, int rnd, cudaStream_t s) {
+  pack_convt_kernel<<<ew_grid((long long)Ci * Co * 4), 256, 0, s>>>(w, kn, nk, reinterpret_cast<__nv_bfloat16*>(kn_b), Ci,
+                                                                    Co, rnd);
   RD_LAUNCHED();
   return 0;
 }
@@ -713,7 +734,7 @@ int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co
 // Kc = Cin*9 rounded up to 32) so that dW[co][k] = sum_p xcol[p][k] * dz[p][co] is a plain reduce GEMM.
 // one thread per pixel: reads its 3x3 neighbourhood of every input channel (neighbours hit in L1) and writes the
 // Kc-float row of xcol as full 128-byte lines
-template <int KC>
+template <int KC, bool BF16>
 __global__ void __launch_bounds__(256)
 im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B, int Cin, int H, int W, int rnd) {
   const long long npix = (long long)B * H * W;
@@ -741,17 +762,32 @@ im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B
         }
       }
     }
-    float4* dst = reinterpret_cast<float4*>(xcol + (size_t)p * KC);
+    if (BF16) {
 #pragma unroll
-    for (int j = 0; j < KC / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      for (int j = 0; j < KC / 4; ++j)
+        st4_bf16(xcol, (size_t)p * KC + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    } else {
+      float4* dst = reinterpret_cast<float4*>(xcol + (size_t)p * KC);
+#pragma unroll
+      for (int j = 0; j < KC / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
   }
 }
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int rnd, cudaStream_t s) {
   const int grid = ew_grid((long long)B * H * W);
-  if (Kc == 32) im2col_first_kernel<32><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
-  else if (Kc == 64) im2col_first_kernel<64><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
-  else if (Kc == 96) im2col_first_kernel<96><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  if (Kc == 32) im2col_first_kernel<32, false><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else if (Kc == 64) im2col_first_kernel<64, false><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else if (Kc == 96) im2col_first_kernel<96, false><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
   else return fail("im2col_first: unsupported Kc=%d", Kc);
+  RD_LAUNCHED();
+  return 0;
+}
+// bf16 variant: xcol is a bf16 tensor [B*H*W][Kc] with Kc = 64 (Cin <= 7) or 128
+int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s) {
+  const int grid = ew_grid((long long)B * H * W);
+  if (Kc == 64) im2col_first_kernel<64, true><<<grid, 256, 0, s>>>(x, reinterpret_cast<float*>(xcol), B, Cin, H, W, 0);
+  else if (Kc == 128) im2col_first_kernel<128, true><<<grid, 256, 0, s>>>(x, reinterpret_cast<float*>(xcol), B, Cin, H, W, 0);
+  else return fail("im2col_first_bf16: unsupported Kc=%d", Kc);
   RD_LAUNCHED();
   return 0;
 }
