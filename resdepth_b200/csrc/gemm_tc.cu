@@ -182,8 +182,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
   } else if (HALO && warp == 1) {
-    // ===== halo variant MMA issuer =====
-    if (lane == 0) {
+    // ===== halo variant MMA issuer: the whole warp walks the loop, one elected lane issues =====
+    {
       constexpr uint32_t idesc = BF16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int aslot = 0, bslot = 0;
       uint32_t aphase = 0, bphase = 0;
@@ -202,22 +202,25 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tc_fence_after();
             const uint32_t sa_tap = sa + ((tap / 3) * HALO_W + (tap % 3)) * 128;
             const uint32_t sb = b_base + bslot * Cfg::B_BYTES;
+            if (elect_one()) {
 #pragma unroll
-            for (int sub = 0; sub < HALO_SUB; ++sub)
+              for (int sub = 0; sub < HALO_SUB; ++sub)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {      // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
-                const uint64_t da = smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128);
-                const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
-                if (BF16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
-                else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
-              }
-            tc_commit(&bempty_bar[bslot]);
+                for (int k = 0; k < 4; ++k) {    // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
+                  const uint64_t da = smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128);
+                  const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
+                  if (BF16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
+                  else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
+                }
+              tc_commit(&bempty_bar[bslot]);
+              if (tap == 8) tc_commit(&empty_bar[aslot]);
+              if (tap == 8 && cc == P.cchunks - 1) tc_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
             if (++bslot == Cfg::B_SLOTS) { bslot = 0; bphase ^= 1; }
           }
-          tc_commit(&empty_bar[aslot]);
           if (++aslot == Cfg::A_SLOTS) { aslot = 0; aphase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);
       }
     }
   } else if (!HALO && warp == 0) {
@@ -251,8 +254,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
   } else if (!HALO && warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
+    {
       constexpr uint32_t idesc = BF16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -268,15 +271,18 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint64_t da = smem_desc_sw128(sa, 16, 1024);
           const uint64_t db = smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { // 4 x 32 bytes of K (8 fp32 / 16 bf16) inside the 128-byte swizzle atom
-            if (BF16) mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            else mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) { // 4 x 32 bytes of K (8 fp32 / 16 bf16) inside the 128-byte swizzle atom
+              if (BF16) mma_bf16(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              else mma_tf32(d_tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
+            tc_commit(&empty_bar[stage]);           // frees the smem stage when these MMAs have read it
+            if (kb == kblocks - 1) tc_commit(&tfull_bar[acc]);   // accumulator complete -> epilogue
           }
-          tc_commit(&empty_bar[stage]);             // frees the smem stage when these MMAs have read it
+          __syncwarp();
           if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull_bar[acc]);                 // accumulator complete -> epilogue
       }
     }
   } else if (warp >= 4) {
@@ -720,7 +726,7 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = EXPERIMENT_KMAJOR ? idesc_tf32(128, BN, 0, 0) : idesc_tf32(128, BN, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
@@ -729,6 +735,7 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sg = sa + 4 * Cfg::BOX_BYTES;
+        if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < Cfg::KP / 8; ++k) {                         // 8 pixels = two 4-row swizzle atoms per MMA
           const uint64_t da = EXPERIMENT_KMAJOR ? smem_desc_sw128(sa + k * 32, 16, 1024)
@@ -738,9 +745,11 @@ gemm_reduce_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_con
           mma_tf32(tmem_base, da, dg, idesc, (i | k) != 0);
         }
         tc_commit(&empty_bar[stage]);
+        if (i == nsteps - 1) tc_commit(done_bar);
+        }
+        __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(done_bar);
     }
   } else {
     const int q = warp & 3;
@@ -865,7 +874,7 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = idesc_bf16(128, BN, 1, 1);       // both operands MN-major
       int stage = 0;
       uint32_t phase = 0;
@@ -874,14 +883,17 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sg = sa + 2 * Cfg::BOX_BYTES;
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < Cfg::KP / 16; ++k)                      // 16 pixels = two 8-row swizzle atoms per MMA
-          mma_bf16(tmem_base, smem_desc_sw128(sa + k * 2048, Cfg::BOX_BYTES, 1024),
-                   smem_desc_sw128(sg + k * 2048, Cfg::BOX_BYTES, 1024), idesc, (i | k) != 0);
-        tc_commit(&empty_bar[stage]);
+          for (int k = 0; k < Cfg::KP / 16; ++k)                    // 16 pixels = two 8-row swizzle atoms per MMA
+            mma_bf16(tmem_base, smem_desc_sw128(sa + k * 2048, Cfg::BOX_BYTES, 1024),
+                     smem_desc_sw128(sg + k * 2048, Cfg::BOX_BYTES, 1024), idesc, (i | k) != 0);
+          tc_commit(&empty_bar[stage]);
+          if (i == nsteps - 1) tc_commit(done_bar);
+        }
+        __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
-      tc_commit(done_bar);
     }
   } else {
     const int q = warp & 3;

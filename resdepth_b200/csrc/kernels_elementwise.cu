@@ -197,7 +197,7 @@ struct BwdCoef {            // per channel, built by bn_bwd_finalize
 };
 
 template <bool POOL, bool APPLY>
-__global__ void __launch_bounds__(EW_THREADS, APPLY ? 4 : 2)
+__global__ void __launch_bounds__(EW_THREADS, APPLY ? 4 : 1)
 bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool, const float* __restrict__ z,
               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ slope_p,
               const float* __restrict__ mean, const BwdCoef* __restrict__ coef, float* __restrict__ dz,
