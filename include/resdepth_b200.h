@@ -108,6 +108,22 @@ int rd_sgd_step(float* params, const float* grads, int64_t n, float lr, float we
 int rd_blend_accumulate(const float* tiles, const float* mean, const float* std, const int32_t* geom,
                         int n, int tile, int stride, double* raster, int rows, int cols, void* stream);
 
+/* DsmOrthoDataset.__getitem__ (lib/DsmOrthoDataset.py:161-291, training strategy) for a batch of n tiles, on
+ * rasters resident in device memory: crop at pos (y, x), per-tile masked mean-centring / sigma scaling of the
+ * DSMs, ortho-image gather + normalisation, loss mask, rot90 / flipud / fliplr augmentation
+ * (lib/torch_transforms.py:15-157).  The random decisions are inputs.
+ *   dsm_in, dsm_gt: [rows][cols] f32; orthos: [rows][cols][n_views_total] f32 (NULL when n_ortho == 0)
+ *   pos int32 [n][2] = (y, x); views int32 [n][n_ortho] (already permuted); aug int32 [n][3] = (k, vflip, hflip)
+ *   dsm_mean_in / ortho_mean_in: user-specified means, or NaN to centre every tile on its own mean
+ *   include_dsm: channel 0 of the network input is the DSM ('geom*' configurations)
+ *   outputs: input [n][C][T][T] f32, target [n][1][T][T] f32, mask uint8 [n][1][T][T], dsm_mean_out f32 [n];
+ *   scratch: 2*n floats. */
+int rd_make_tiles(const float* dsm_in, const float* dsm_gt, const float* orthos, int rows, int cols,
+                  int n_views_total, const int32_t* pos, const int32_t* views, const int32_t* aug, int n, int tile,
+                  int n_ortho, int include_dsm, float nodata, float dsm_std, float ortho_std, float dsm_mean_in,
+                  float ortho_mean_in, float* input, float* target, uint8_t* mask, float* dsm_mean_out,
+                  float* scratch, void* stream);
+
 /* Per-category device timing (CUDA events on the launching stream around the library's own launches).
  * rd_profile_enable(h, 1) starts recording; rd_profile_collect synchronises the recorded events and folds
  * them into per-category totals; rd_profile_read returns one category: total milliseconds, algorithmic

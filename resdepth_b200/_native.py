@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = (
     'rd_param_arena_size', 'rd_num_buffers', 'rd_buffer_info', 'rd_buffer_arena_size', 'rd_bind', 'rd_reserve',
     'rd_workspace_bytes', 'rd_forward', 'rd_loss', 'rd_backward', 'rd_adam_step', 'rd_sgd_step',
     'rd_blend_accumulate', 'rd_launch_count', 'rd_math_mode_name', 'rd_profile_enable', 'rd_profile_collect',
-    'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce',
+    'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce', 'rd_make_tiles',
 )
 PROF_NUM = 18                                           # RD_PROF_NUM
 
@@ -90,6 +90,9 @@ def _declare(lib):
     lib.rd_debug_rows.argtypes = [i32, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]
     lib.rd_debug_reduce.restype = i32
     lib.rd_debug_reduce.argtypes = [i32, i32, vp, i32, i32, i32, i32, vp, i32, vp, vp, i64, vp]
+    lib.rd_make_tiles.restype = i32
+    lib.rd_make_tiles.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, f32,
+                                  vp, vp, vp, vp, vp, vp]
     lib.rd_launch_count.restype = i64
     lib.rd_launch_count.argtypes = [i32]
     lib.rd_math_mode_name.restype = C.c_char_p
@@ -214,6 +217,10 @@ def debug_rows(engine, kind, src, batch, h, w, c, w_kn, w_nk, n, out, stream):
 def debug_reduce(engine, kind, src, batch, h, w, c, g, n, out, scratch, scratch_floats, stream):
     check(lib().rd_debug_reduce(engine, kind, src, batch, h, w, c, g, n, out, scratch, scratch_floats, stream),
           'rd_debug_reduce')
+
+
+def make_tiles(*args):
+    check(lib().rd_make_tiles(*args), 'rd_make_tiles')
 
 
 def adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, stream):

@@ -1024,6 +1024,18 @@ int rd_profile_read(const rd_handle* h, int category, char* name64, double* ms, 
   return 0;
 }
 
+int rd_make_tiles(const float* dsm_in, const float* dsm_gt, const float* orthos, int rows, int cols,
+                  int n_views_total, const int32_t* pos, const int32_t* views, const int32_t* aug, int n, int tile,
+                  int n_ortho, int include_dsm, float nodata, float dsm_std, float ortho_std, float dsm_mean_in,
+                  float ortho_mean_in, float* input, float* target, uint8_t* mask, float* dsm_mean_out,
+                  float* scratch, void* stream) {
+  if (!dsm_in || !dsm_gt || !pos || !aug || !input || !target || !mask || !dsm_mean_out || !scratch)
+    return fail("rd_make_tiles: null argument");
+  return launch_make_tiles(dsm_in, dsm_gt, orthos, rows, cols, n_views_total, pos, views, aug, n, tile, n_ortho,
+                           include_dsm, nodata, dsm_std, ortho_std, dsm_mean_in, ortho_mean_in, input, target, mask,
+                           dsm_mean_out, scratch, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int64_t rd_launch_count(int reset) {
   const long long v = g_launch_count;
   if (reset) g_launch_count = 0;

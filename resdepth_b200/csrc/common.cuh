@@ -103,6 +103,12 @@ int launch_sgd(float* p, const float* g, long long n, float lr, float wd, float 
 int launch_blend(const float* tiles, const float* mean, const float* std, const int32_t* geom, int n, int T,
                  int stride, double* raster, int rows, int cols, cudaStream_t s);
 int launch_fill(float* p, float v, long long n, cudaStream_t s);
+// training-tile producer (kernels_tiles.cu); scratch: 2*n floats
+int launch_make_tiles(const float* dsm_in, const float* dsm_gt, const float* orthos, int rows, int cols, int nvt,
+                      const int32_t* pos, const int32_t* views, const int32_t* aug, int n, int T, int n_ortho,
+                      int include_dsm, float nodata, float dsm_std, float ortho_std, float dsm_mean_in,
+                      float ortho_mean_in, float* input, float* target, uint8_t* mask, float* dsm_mean_out,
+                      float* scratch, cudaStream_t s);
 // out[i] = sum over p of part[p*row_stride + i*col_stride], i < n (double accumulation)
 int launch_sum_partials(const float* part, int nparts, int n, int row_stride, int col_stride, float* out,
                         cudaStream_t s);

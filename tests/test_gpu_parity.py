@@ -452,3 +452,58 @@ def test_trainer_with_sgd_and_checkpoint_resume(tmp_path):
     v0 = tr.inference_one_batch(batches[0], 'val')['MAE_metric']
     v1 = tr2.inference_one_batch(batches[0], 'val')['MAE_metric']
     assert abs(v0 - v1) <= 1e-6 * abs(v0)
+
+
+def test_device_tile_producer_matches_reference_golden(golden_dir):
+    """rd_make_tiles against the vectors of the unmodified reference DsmOrthoDataset.__getitem__ (all five channel
+    configurations, every rotation / flip combination that was drawn, user-specified and per-tile means)."""
+    from resdepth_b200.lib.tiles import DeviceTileProducer
+    g = np.load(os.path.join(golden_dir, 'tiles.npz'))
+    pairs = {0: [[0, 1], [2, 3], [1, 3]], 1: [[0, 1], [2, 3]], 2: [[0], [2]], 3: None, 4: [[3, 0]]}
+    for ci, (channels, dmean, omean, n) in enumerate(g['cases']):
+        prod = DeviceTileProducer(g['dsm_in'], g['dsm_gt'], g['orthos'] if pairs[ci] else None, float(g['nodata']),
+                                  int(g['tile']), str(channels), pairs[ci],
+                                  None if dmean == 'None' else float(dmean), 3.5,
+                                  None if omean == 'None' else float(omean), 41.0)
+        metas = [g[f'c{ci}_s{i}_meta'] for i in range(int(n))]
+        batch = prod.make_batch([(int(m[0]), int(m[1])) for m in metas], [[int(v) for v in m[5:]] for m in metas],
+                                [(int(m[2]), int(m[3]), int(m[4])) for m in metas])
+        for i in range(int(n)):
+            key = f'c{ci}_s{i}'
+            np.testing.assert_array_equal(batch['loss_mask'][i].cpu().numpy(), g[key + '_mask'])
+            np.testing.assert_allclose(float(batch['dsm_mean'][i]), float(g[key + '_mean']), rtol=1e-6)
+            np.testing.assert_allclose(batch['input'][i].cpu().numpy(), g[key + '_input'], rtol=0, atol=2e-5)
+            valid = g[key + '_mask']
+            np.testing.assert_allclose(batch['target'][i].cpu().numpy()[valid], g[key + '_target'][valid], rtol=0, atol=2e-5)
+
+
+def test_device_tile_producer_feeds_the_trainer(tmp_path):
+    """Batches produced on the device go straight into Trainer.inference_one_batch (no host round trip)."""
+    from types import SimpleNamespace
+
+    from oracle import tile_oracle as TO
+    from resdepth_b200.lib.tiles import DeviceTileProducer
+    from resdepth_b200.lib.Trainer import Trainer
+    rng = np.random.default_rng(5)
+    rows, cols, T = 160, 200, 64
+    gt = (400 + 3 * rng.standard_normal((rows, cols))).astype(np.float32)
+    din = (gt + rng.standard_normal((rows, cols))).astype(np.float32)
+    orth = (100 + 30 * rng.standard_normal((rows, cols, 2))).astype(np.float32)
+    prod = DeviceTileProducer(din, gt, orth, -9999.0, T, 'geom-stereo', [[0, 1]], None, 3.5, None, 30.0)
+    pos, views, aug = prod.draw(6)
+    batch = prod.make_batch(pos, views, aug)
+    for i in range(6):
+        inp, tgt, mask, mean = TO.make_tile(din, gt, orth, pos[i][0], pos[i][1], T, views[i], -9999.0, 3.5, 30.0,
+                                            'geom-stereo', None, None, aug[i][0], bool(aug[i][1]), bool(aug[i][2]))
+        np.testing.assert_allclose(batch['input'][i].cpu().numpy(), inp, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(batch['target'][i].cpu().numpy(), tgt, rtol=0, atol=2e-5)
+        np.testing.assert_array_equal(batch['loss_mask'][i].cpu().numpy(), mask)
+    model = _model(dict(n_input_channels=3, start_kernel=32, depth=2, bias_conv_layer=True))
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
+    args = SimpleNamespace(trainloader=[batch], valloader=[batch], model=model, optimizer=opt, scheduler=None,
+                           criterion=torch.nn.L1Loss(reduction='mean'), n_epochs=1, evaluate_rate=1, save_model_rate=1,
+                           freq_average_train_loss=1, save_dir=str(tmp_path), log_file=None,
+                           checkpoint_dir=str(tmp_path / 'ckpt'), tboard_log_dir=None, pretrained_path=None)
+    tr = Trainer(args)
+    l0 = tr.inference_one_batch(batch, 'train')['MAE_metric']
+    assert np.isfinite(l0) and l0 > 0
