@@ -254,6 +254,20 @@ def run_native(args):
             return model(infer_x)
     infer_ms, _, _, _, _ = timed(infer_step, K, W)
     model.train()
+    # tier-next figure: the on-device tile producer that feeds the step (DsmOrthoDataset.__getitem__
+    # for 64 tiles per call: geom-stereo, 4 views on a 4096x4096 raster, random positions / pairs / rot90 / flips)
+    from resdepth_b200.lib.tiles import DeviceTileProducer
+    g = torch.Generator(device=dev).manual_seed(11)
+    R = 4096
+    prod = DeviceTileProducer.from_device(
+        400.0 + 3.0 * torch.randn(R, R, device=dev, generator=g), 400.0 + 3.0 * torch.randn(R, R, device=dev, generator=g),
+        100.0 + 30.0 * torch.randn(4, R, R, device=dev, generator=g), -9999.0, T, 'geom-stereo', [[0, 1], [2, 3], [1, 3]],
+        None, 3.5, None, 40.0, permute_images_within_pair=True)
+
+    def producer_step(i):
+        return prod.sample_batch(B)['input']
+    prod_ms, _, _, _, _ = timed(producer_step, K, W)
+    del prod
     ms, launches, prof, clocks, last_loss = timed(device_step, K, W, profile=True)
     loss_value = float(last_loss.item())
     e2e_ms, _, _, e2e_clocks, _ = timed(e2e_step, K, 2)
@@ -309,6 +323,9 @@ def run_native(args):
             'loss': loss_value,
             'inference': {'workload': 'BASELINE configs[1]: eval-mode forward, 3-ch 256x256, depth 5, batch 32/GPU',
                           'value': 32 * world * K / (infer_ms * 1e-3), 'unit': UNIT, 'ms_per_call': infer_ms / K},
+            'tile_producer': {'workload': 'rd_make_tiles: 64 geom-stereo 256x256 training tiles per call from a 4096x4096 '
+                                          'raster with 4 views (host-drawn positions / pairs / rot90 / flips included)',
+                              'value': B * world * K / (prod_ms * 1e-3), 'unit': UNIT, 'ms_per_call': prod_ms / K},
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

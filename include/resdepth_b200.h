@@ -112,7 +112,8 @@ int rd_blend_accumulate(const float* tiles, const float* mean, const float* std,
  * rasters resident in device memory: crop at pos (y, x), per-tile masked mean-centring / sigma scaling of the
  * DSMs, ortho-image gather + normalisation, loss mask, rot90 / flipud / fliplr augmentation
  * (lib/torch_transforms.py:15-157).  The random decisions are inputs.
- *   dsm_in, dsm_gt: [rows][cols] f32; orthos: [rows][cols][n_views_total] f32 (NULL when n_ortho == 0)
+ *   dsm_in, dsm_gt: [rows][cols] f32; orthos: planar [n_views_total][rows][cols] f32 (the reference's
+ *   np.dstack raster, lib/DsmOrthoDataset.py:293-314, transposed once at upload; NULL when n_ortho == 0)
  *   pos int32 [n][2] = (y, x); views int32 [n][n_ortho] (already permuted); aug int32 [n][3] = (k, vflip, hflip)
  *   dsm_mean_in / ortho_mean_in: user-specified means, or NaN to centre every tile on its own mean
  *   include_dsm: channel 0 of the network input is the DSM ('geom*' configurations)

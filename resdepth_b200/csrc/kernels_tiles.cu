@@ -10,7 +10,7 @@ namespace rd {
 
 // per tile: mean of the DSM patch over pixels != nodata, mean of the selected ortho patches
 __global__ void __launch_bounds__(256)
-tile_means_kernel(const float* __restrict__ dsm_in, const float* __restrict__ orthos, int cols, int nvt,
+tile_means_kernel(const float* __restrict__ dsm_in, const float* __restrict__ orthos, int cols, size_t plane_sz,
                   const int32_t* __restrict__ pos, const int32_t* __restrict__ views, int T, int n_ortho, float nodata,
                   float dsm_mean_in, float ortho_mean_in, float* __restrict__ means /*[n][2]*/) {
   __shared__ double r1[256], r2[256], r3[256];
@@ -22,7 +22,7 @@ tile_means_kernel(const float* __restrict__ dsm_in, const float* __restrict__ or
     const size_t o = (size_t)(y + r) * cols + x + c;
     const float v = dsm_in[o];
     if (v != nodata) { ds += (double)v; dc += 1.0; }
-    for (int k = 0; k < n_ortho; ++k) os += (double)orthos[o * nvt + views[t * n_ortho + k]];
+    for (int k = 0; k < n_ortho; ++k) os += (double)orthos[(size_t)views[t * n_ortho + k] * plane_sz + o];
   }
   r1[threadIdx.x] = ds; r2[threadIdx.x] = dc; r3[threadIdx.x] = os;
   __syncthreads();
@@ -41,7 +41,7 @@ tile_means_kernel(const float* __restrict__ dsm_in, const float* __restrict__ or
 // output plane p of tile t: 0 = loss mask, 1 = target, 2.. = network input channels
 __global__ void __launch_bounds__(256)
 tile_gather_kernel(const float* __restrict__ dsm_in, const float* __restrict__ dsm_gt, const float* __restrict__ orthos,
-                   int cols, int nvt, const int32_t* __restrict__ pos, const int32_t* __restrict__ views,
+                   int cols, size_t plane_sz, const int32_t* __restrict__ pos, const int32_t* __restrict__ views,
                    const int32_t* __restrict__ aug, int T, int n_ortho, int include_dsm, float nodata, float dsm_std,
                    float ortho_std, const float* __restrict__ means, float* __restrict__ input, float* __restrict__ target,
                    uint8_t* __restrict__ mask, float* __restrict__ dsm_mean_out) {
@@ -74,7 +74,7 @@ tile_gather_kernel(const float* __restrict__ dsm_in, const float* __restrict__ d
       const int c = plane - 2;
       float v;
       if (include_dsm && c == 0) v = __fdiv_rn(__fsub_rn(dsm_in[o], dmean), dsm_std);
-      else v = __fdiv_rn(__fsub_rn(orthos[o * nvt + views[t * n_ortho + (c - (include_dsm ? 1 : 0))]], omean), ortho_std);
+      else v = __fdiv_rn(__fsub_rn(orthos[(size_t)views[t * n_ortho + (c - (include_dsm ? 1 : 0))] * plane_sz + o], omean), ortho_std);
       input[((size_t)t * C + c) * T * T + i] = v;
     }
   }
@@ -87,14 +87,15 @@ int launch_make_tiles(const float* dsm_in, const float* dsm_gt, const float* ort
                       float* scratch, cudaStream_t s) {
   if (n <= 0) return 0;
   if (T < 1 || T > rows || T > cols) return fail("make_tiles: tile %d does not fit the %dx%d raster", T, rows, cols);
+  (void)nvt;
   if (n_ortho > 0 && (!orthos || !views)) return fail("make_tiles: ortho images requested but not provided");
   if (!include_dsm && n_ortho == 0) return fail("make_tiles: no input channels selected");
-  tile_means_kernel<<<n, 256, 0, s>>>(dsm_in, orthos, cols, nvt, pos, views, T, n_ortho, nodata, dsm_mean_in,
+  tile_means_kernel<<<n, 256, 0, s>>>(dsm_in, orthos, cols, (size_t)rows * cols, pos, views, T, n_ortho, nodata, dsm_mean_in,
                                       ortho_mean_in, scratch);
   RD_LAUNCHED();
   const int C = n_ortho + (include_dsm ? 1 : 0);
   dim3 grid(cdiv((long long)T * T, 256 * 4), C + 2, n);
-  tile_gather_kernel<<<grid, 256, 0, s>>>(dsm_in, dsm_gt, orthos, cols, nvt, pos, views, aug, T, n_ortho, include_dsm,
+  tile_gather_kernel<<<grid, 256, 0, s>>>(dsm_in, dsm_gt, orthos, cols, (size_t)rows * cols, pos, views, aug, T, n_ortho, include_dsm,
                                           nodata, dsm_std, ortho_std, scratch, input, target, mask, dsm_mean_out);
   RD_LAUNCHED();
   return 0;

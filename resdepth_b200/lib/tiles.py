@@ -44,7 +44,9 @@ class DeviceTileProducer:
         if input_channels != 'geom':
             if orthos is None or not image_pairs:
                 raise ValueError("ortho images and image_pairs are required unless input_channels == 'geom'")
-            self.orthos = torch.as_tensor(np.ascontiguousarray(orthos, dtype=np.float32)).to(self.device)
+            # reference layout is [rows, cols, views] (np.dstack); the kernels read planar [views, rows, cols]
+            self.orthos = torch.as_tensor(np.ascontiguousarray(orthos, dtype=np.float32)).to(self.device) \
+                .permute(2, 0, 1).contiguous()
             self.image_pairs = [list(p) for p in image_pairs]
             self.n_ortho = len(self.image_pairs[0])
             if any(len(p) != self.n_ortho for p in self.image_pairs):
@@ -52,6 +54,26 @@ class DeviceTileProducer:
         else:
             self.orthos, self.image_pairs, self.n_ortho = None, None, 0
         self.n_channels = self.n_ortho + (1 if self.include_dsm else 0)
+
+    @classmethod
+    def from_device(cls, dsm_input, dsm_target, orthos_planar, nodata, tile_size, input_channels='geom-stereo',
+                    image_pairs=None, dsm_mean=None, dsm_std=1.0, ortho_mean=None, ortho_std=1.0, augment=True,
+                    permute_images_within_pair=False):
+        """Adopt rasters that already live on the device (orthos planar: [views, rows, cols])."""
+        self = object.__new__(cls)
+        self.device = dsm_input.device
+        self.input_channels, self.tile_size = input_channels, int(tile_size)
+        self.nodata, self.dsm_mean, self.dsm_std = float(nodata), dsm_mean, float(dsm_std)
+        self.ortho_mean, self.ortho_std = ortho_mean, float(ortho_std)
+        self.augment, self.permute = augment, permute_images_within_pair
+        self.dsm_input, self.dsm_target = dsm_input.float().contiguous(), dsm_target.float().contiguous()
+        self.rows, self.cols = self.dsm_input.shape
+        self.include_dsm = input_channels != 'stereo'
+        self.orthos = orthos_planar.float().contiguous() if input_channels != 'geom' else None
+        self.image_pairs = [list(p) for p in image_pairs] if self.orthos is not None else None
+        self.n_ortho = len(self.image_pairs[0]) if self.orthos is not None else 0
+        self.n_channels = self.n_ortho + (1 if self.include_dsm else 0)
+        return self
 
     def draw(self, n: int):
         """Random decisions of one batch, drawn like the reference: uniformly sampled tile origins, one image pair per
@@ -74,12 +96,15 @@ class DeviceTileProducer:
         """positions: n x (y, x); views: n x n_ortho view indices (already permuted); aug: n x (k, vflip, hflip)."""
         n, T, dev = len(positions), self.tile_size, self.device
         pos_t = torch.tensor(np.asarray(positions, dtype=np.int32).reshape(n, 2), device=dev)
-        if np.any(np.asarray(positions)[:, 0] + T > self.rows) or np.any(np.asarray(positions)[:, 1] + T > self.cols) \\
-                or np.any(np.asarray(positions) < 0):
+        pa = np.asarray(positions).reshape(n, 2)
+        if np.any(pa < 0) or np.any(pa[:, 0] + T > self.rows) or np.any(pa[:, 1] + T > self.cols):
             raise ValueError('tile position outside the raster')
         aug_t = torch.tensor(np.asarray(aug if aug is not None else [(0, 0, 0)] * n, dtype=np.int32).reshape(n, 3), device=dev)
         if self.n_ortho:
-            views_t = torch.tensor(np.asarray(views, dtype=np.int32).reshape(n, self.n_ortho), device=dev)
+            va = np.asarray(views, dtype=np.int32).reshape(n, self.n_ortho)
+            if np.any(va < 0) or np.any(va >= self.orthos.shape[0]):
+                raise ValueError('ortho view index outside the raster stack')
+            views_t = torch.tensor(va, device=dev)
         else:
             views_t = None
         inp = torch.empty((n, self.n_channels, T, T), device=dev)
@@ -90,7 +115,7 @@ class DeviceTileProducer:
         with torch.cuda.device(dev):
             _native.make_tiles(self.dsm_input.data_ptr(), self.dsm_target.data_ptr(),
                                self.orthos.data_ptr() if self.orthos is not None else None, self.rows, self.cols,
-                               self.orthos.shape[2] if self.orthos is not None else 0, pos_t.data_ptr(),
+                               self.orthos.shape[0] if self.orthos is not None else 0, pos_t.data_ptr(),
                                views_t.data_ptr() if views_t is not None else None, aug_t.data_ptr(), n, T, self.n_ortho,
                                int(self.include_dsm), self.nodata, self.dsm_std, self.ortho_std,
                                math.nan if self.dsm_mean is None else float(self.dsm_mean),
