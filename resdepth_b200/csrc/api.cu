@@ -90,6 +90,7 @@ struct rd_handle {
   size_t partials_floats = 0, scratch_floats = 0, part_floats = 0;
   std::vector<float*> g_skip;
   float *gy = nullptr, *gh = nullptr, *gp = nullptr;
+  void* gp_b = nullptr;        // bf16 gradient at a pooled tensor (bf16 backward)
   float* xcol = nullptr;       // im2col expansion of the input for the first layer's tensor-core wgrad
   int xcol_k = 0;
   float* gt = nullptr;         // bilinear up-mode: gradient at the low-resolution 1x1-conv output
@@ -267,6 +268,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     h->gp = c.take(max_pool);
     h->gt = h->cfg.up_mode == RD_UP_BILINEAR ? c.take(max_out / 4 + 64) : nullptr;
     h->gy_b = bf ? c.take(max_out / 2 + 64) : nullptr;
+    h->gp_b = bf ? c.take(max_pool / 2 + 64) : nullptr;
     h->gs_b.assign(D, nullptr);
     if (bf)
       for (int i = 0; i < D; ++i) h->gs_b[i] = c.take((size_t)B * (T >> i) * (T >> i) * h->enc[i].Cout / 2 + 64);
@@ -277,7 +279,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   } else {
     h->xcol = nullptr;
     h->gt = nullptr;
-    h->gy_b = nullptr; h->xcol_b = nullptr;
+    h->gy_b = nullptr; h->xcol_b = nullptr; h->gp_b = nullptr;
     h->gs_b.assign(D, nullptr);
     h->part = nullptr; h->part_floats = 0;
     h->g_skip.assign(D, nullptr);
@@ -467,17 +469,24 @@ int conv_block_forward_fused_eval(rd_handle* h, ConvBlock& b, int B, int H, int 
   return launch_gemm_rows_tc(b.tc_fwd, e, nullptr, s);
 }
 
+// encoder level i keeps only z and the pooled tensor: its up-conv (tcgen05, transposed) applies BN + activation to z
+// when it adds the skip.  Only in the saving forward modes (the fused inference path never writes z).
+bool skip_from_z(const rd_handle* h, int i, int save) {
+  const UpConv& u = h->ups[h->depth - 1 - i];
+  return save && h->enc[i].pool && u.tc && !u.bilinear && (h->enc[i].Cout % 32 == 0);
+}
+
 // BN statistics finalize + fused normalise/activation(/pool) pass of one block
 int bn_act_forward(rd_handle* h, ConvBlock& b, int np, int B, int H, bool train, int round_a, int round_p,
-                   bool shadows, cudaStream_t s) {
+                   bool shadows, cudaStream_t s, bool write_a = true) {
   BnLayer L = bn_view(h, b);
   {
     ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
     RD_TRY(launch_bn_finalize(L, h->partials, np, (long long)B * H * H, train, h->cfg.do_bn, s));
   }
   const double n = (double)B * H * H * b.Cout;
-  ProfScope ps(h, RD_PROF_BN_ACT_POOL, 0.0, 4.0 * n * (b.pool ? 2.25 : 2.0), s);
-  return launch_bn_act_pool(b.z, b.scale, b.shift, act_view(h, b), b.a, b.pool ? b.p : nullptr, B, H, H, b.Cout,
+  ProfScope ps(h, RD_PROF_BN_ACT_POOL, 0.0, 4.0 * n * (b.pool ? (write_a ? 2.25 : 1.25) : 2.0), s);
+  return launch_bn_act_pool(b.z, b.scale, b.shift, act_view(h, b), write_a ? b.a : nullptr, b.pool ? b.p : nullptr, B, H, H, b.Cout,
                             round_a, round_p, shadows ? b.a_b : nullptr, shadows ? b.p_b : nullptr, s);
 }
 
@@ -615,6 +624,10 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
   RD_TRY(build_tc_plans(h, batch, tile, with_backward));
   const float consts[4] = {0.f, 0.01f, 1.f, 0.f};          // relu slope, LeakyReLU default slope (lib/UNet.py:30)
   RD_CUDA(cudaMemcpy(h->consts, consts, sizeof(consts), cudaMemcpyHostToDevice));
+  if (h->xcol_b) {                                         // row padding of the bf16 im2col expansion stays zero
+    RD_TRY(launch_im2col_first_bf16_clear(h->xcol_b, (size_t)batch * tile * tile * h->xcol_b_k * 2, nullptr));
+    RD_CUDA(cudaDeviceSynchronize());
+  }
   h->res_batch = batch; h->res_tile = tile; h->res_bwd = with_backward;
   h->fwd_mode = -1;
   return 0;
@@ -653,7 +666,9 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     } else {
       RD_TRY(conv_block_forward(h, b, h->enc[i - 1].p, B, H, stats, &np, s));
     }
-    RD_TRY(bn_act_forward(h, b, np, B, H, train, 0, tf, save != 0, s));
+    // training / saving forward: the full-resolution activated tensor of an encoder level is only ever read as the
+    // additive skip of its up-conv; a tcgen05 transposed conv re-derives it from z in its epilogue, so it is not written
+    RD_TRY(bn_act_forward(h, b, np, B, H, train, 0, tf, save != 0, s, !skip_from_z(h, i, save)));
   }
   {
     ConvBlock& b = h->bott;
@@ -675,6 +690,13 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     e.out = u.u;
     e.bias = h->P + u.bias;
     e.skip = h->enc[D - 1 - j].a;                       // additive skip, lib/UNet.py:96-101,220,224
+    if (skip_from_z(h, D - 1 - j, save)) {
+      ConvBlock& eb = h->enc[D - 1 - j];
+      e.skip = eb.z;
+      e.skip_scale = eb.scale;
+      e.skip_shift = eb.shift;
+      e.skip_slope = act_view(h, eb).slope;
+    }
     e.round_tf32 = (j < D - 1) ? tf : 0;
     e.out_b = (save && u.tc && !u.bilinear) ? u.u_b : nullptr;       // bf16 copy: wgrad operand of the next conv
     if (u.bilinear) {
@@ -742,9 +764,26 @@ int rd_loss(rd_handle* h, const float* y_pred, const float* target, const uint8_
 
 namespace {
 
+// the gradient at u (= skip gradient of encoder level i) lives only in its bf16 copy gs_b[i]: the producer (last-conv
+// backward for level 0, the tcgen05 dgrad of the decoder conv above for the others) and both readers (the up-conv's
+// bf16 GEMMs and the BatchNorm backward of the encoder level) agree on this predicate
+bool skip_grad_bf16(const rd_handle* h, int i) {
+  const int D = h->depth, j = D - 1 - i;               // up-conv whose output gradient this is
+  if (!h->gs_b[i] || !h->ups[j].bb) return false;
+  return i == 0 ? true : h->dec[j].tc;
+}
+
 // backward of one conv block.  g_full: gradient at the (un-pooled) block output, g_pool: gradient at the pooled
 // output; src_in: the block's input (NHWC) or, for the first encoder block, the network input x (NCHW).
-int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float* g_pool, int B, int H,
+struct GradRef {          // a gradient tensor stored as fp32 or as bf16 (the bf16 backward keeps some only in bf16)
+  const void* p = nullptr;
+  int bf16 = 0;
+  GradRef() {}
+  GradRef(const float* f) : p(f), bf16(0) {}
+  GradRef(const void* q, int is_bf16) : p(q), bf16(is_bf16) {}
+};
+
+int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, int B, int H,
                    const float* src_in, bool first, float* dgrad_out, int round_dgrad, float* dgrad_colsum,
                    void* dgrad_out_b, cudaStream_t s) {
   BnLayer L = bn_view(h, b);
@@ -752,17 +791,17 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
   const int do_bn = h->cfg.do_bn;
   int np = 0;
   const double px = (double)B * H * H, n = px * b.Cout;
-  const double gin = (g_full ? 1.0 : 0.0) + (g_pool ? 0.25 : 0.0);
+  const double gin = (g_full.p ? (g_full.bf16 ? 0.5 : 1.0) : 0.0) + (g_pool.p ? (g_pool.bf16 ? 0.125 : 0.25) : 0.0);
   {
     ProfScope ps(h, RD_PROF_BN_BWD_REDUCE, 0.0, 4.0 * n * (1.0 + gin), s);
-    RD_TRY(launch_bn_bwd_reduce(g_full, g_pool, b.z, L, act, h->partials, &np, B, H, H, s));
+    RD_TRY(launch_bn_bwd_reduce(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->partials, &np, B, H, H, s));
     RD_TRY(launch_bn_bwd_finalize(L, h->partials, np, (long long)B * H * H, do_bn, h->fwd_mode == RD_FWD_TRAIN,
                                   do_bn ? h->G + b.gamma : nullptr, h->G + (do_bn ? b.beta : b.bias),
                                   b.slope >= 0 ? h->G + b.slope : nullptr, h->scratch, h->coef, s));
   }
   {
-    ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (2.0 + gin), s);
-    RD_TRY(launch_bn_bwd_apply(g_full, g_pool, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? h->gy_b : nullptr, B,
+    ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (1.0 + (b.bb ? 0.5 : 1.0) + gin), s);
+    RD_TRY(launch_bn_bwd_apply(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? h->gy_b : nullptr, B,
                                H, H, h->tf32() && (b.tc || b.tc_wgrad.valid), s));
   }
   if (first) {
@@ -791,7 +830,7 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
     ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), s);
     RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, 9, s));
   }
-  if (dgrad_out) {
+  if (dgrad_out || dgrad_out_b) {
     Gather g = gather_conv3x3(H, H, b.Cout);
     Epilogue e{};
     e.mode = dgrad_colsum ? EPI_STATS : EPI_PLAIN;       // column sums of dX = bias gradient of the up-conv before it
@@ -801,7 +840,9 @@ int block_backward(rd_handle* h, ConvBlock& b, const float* g_full, const float*
     e.out_b = dgrad_out_b;
     int npart = 0;
     {
-      ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+      ProfScope ps(h, RD_PROF_CONV_DGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px,
+                   px * (b.Cin * (dgrad_out ? 4.0 : 2.0) + b.Cout * (b.bb ? 2.0 : 4.0)), s);
+      if (!dgrad_out && !b.tc) return fail("block_backward: bf16-only gradient output needs the tcgen05 dgrad");
       if (b.tc) RD_TRY(launch_gemm_rows_tc(b.tc_dgrad, e, &npart, s));
       else RD_TRY(launch_gemm_rows_simt(h->gy, g, b.wd_kn, B, b.Cin, e, &npart, s));
     }
@@ -824,12 +865,15 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int B = h->fwd_batch, T = h->fwd_tile, D = h->depth;
   const int C0 = h->cfg.start_kernel;
+  bool gp_bf16 = false;                                  // is the gradient at the current pooled tensor held in gp_b?
 
   // last_layer (lib/UNet.py:184,227): du -> gradient at u_{D-1}, which is also the skip gradient of level 0
   {
     const double px = (double)B * T * T;
     ProfScope ps(h, RD_PROF_LAST_BWD, 2.0 * 2.0 * 9.0 * C0 * px, 4.0 * px * (2.0 * C0 + 1.0), s);
-    RD_TRY(launch_conv_last_bwd(h->ups[D - 1].u, dy, h->P + h->last_w, h->g_skip[0],
+    // when the last up-conv takes bf16 operands, the gradient at u_{D-1} (= skip gradient of level 0) is kept in
+    // bf16 only: its readers are that up-conv's GEMMs and the BatchNorm backward of encoder level 0
+    RD_TRY(launch_conv_last_bwd(h->ups[D - 1].u, dy, h->P + h->last_w, h->ups[D - 1].bb ? nullptr : h->g_skip[0],
                                 h->ups[D - 1].bb ? h->gs_b[0] : nullptr, h->G + h->last_w,
                                 h->last_b >= 0 ? h->G + h->last_b : nullptr, h->G + h->ups[D - 1].bias, h->scratch,
                                 h->scratch_floats, B, T, T, C0, s));
@@ -895,18 +939,26 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     }
     }
     if (j == 0) {
-      RD_TRY(block_backward(h, h->bott, h->gh, nullptr, B, Hin, h->enc[D - 1].p, false, h->gp, 0, nullptr, nullptr, s));
+      gp_bf16 = h->gp_b && h->bott.tc;
+      RD_TRY(block_backward(h, h->bott, h->gh, GradRef(), B, Hin, h->enc[D - 1].p, false, gp_bf16 ? nullptr : h->gp, 0,
+                            nullptr, gp_bf16 ? h->gp_b : nullptr, s));
     } else {
-      // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded
-      RD_TRY(block_backward(h, h->dec[j - 1], h->gh, nullptr, B, Hin, h->ups[j - 1].u, false, h->g_skip[D - j],
-                            h->tf32() && h->ups[j - 1].tc, h->G + h->ups[j - 1].bias,
-                            h->ups[j - 1].bb && h->dec[j - 1].tc ? h->gs_b[D - j] : nullptr, s));
+      // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded (fp32
+      // backward) or only as bf16 (bf16 backward)
+      const bool only_b = skip_grad_bf16(h, D - j);
+      RD_TRY(block_backward(h, h->dec[j - 1], h->gh, GradRef(), B, Hin, h->ups[j - 1].u, false,
+                            only_b ? nullptr : h->g_skip[D - j], h->tf32() && h->ups[j - 1].tc,
+                            h->G + h->ups[j - 1].bias, only_b ? h->gs_b[D - j] : nullptr, s));
     }
   }
   for (int i = D - 1; i >= 0; --i) {
     const int H = T >> i;
-    RD_TRY(block_backward(h, h->enc[i], h->g_skip[i], h->gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
-                          i == 0 ? nullptr : h->gp, 0, nullptr, nullptr, s));
+    const GradRef gs = skip_grad_bf16(h, i) ? GradRef(h->gs_b[i], 1) : GradRef(h->g_skip[i]);
+    const GradRef gp = gp_bf16 ? GradRef(h->gp_b, 1) : GradRef(h->gp);
+    const bool out_b = i > 0 && h->gp_b && h->enc[i].tc;
+    RD_TRY(block_backward(h, h->enc[i], gs, gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
+                          (i == 0 || out_b) ? nullptr : h->gp, 0, nullptr, out_b ? h->gp_b : nullptr, s));
+    gp_bf16 = out_b;
   }
   return 0;
 }

@@ -83,16 +83,18 @@ int launch_bn_act_pool(const float* z, const float* scale, const float* shift, A
                        int B, int H, int W, int C, int round_a, int round_p, void* a_b, void* p_b, cudaStream_t s);
 // backward pass 1:  gA = unpool(g_pool, a) + g_full ; gY = gA*act'(y) ; per-block partial sums
 //   partials [nblk][C][3] = (sum gY, sum gY*(z-mean), sum gA*min(y,0))
-int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
-                         float* partials, int* n_partials, int B, int H, int W, cudaStream_t s);
+// g_full / g_pool: fp32 tensors, or bf16 tensors when the matching *_bf16 flag is set
+int launch_bn_bwd_reduce(const void* g_full, const void* g_pool, int gf_bf16, int gp_bf16, const float* z,
+                         const BnLayer& L, Act act, float* partials, int* n_partials, int B, int H, int W,
+                         cudaStream_t s);
 // finalize: dgamma, dbeta (or conv dbias) -> grads, PReLU slope gradient, coefficients for pass 2 (coef: 4*C floats)
 int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int do_bn,
                            int batch_stats, float* dgamma, float* dbeta, float* dslope, float* dslope_scratch, void* coef,
                            cudaStream_t s);
 // pass 2:  dz = cs*(gY - c1 - (z-mean)*c2), gY recomputed from the same inputs as pass 1
 //   dz (fp32) and/or dz_b (bf16) receive the result; either may be null
-int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
-                        const void* coef, float* dz, void* dz_b, int B, int H, int W, int round_out, cudaStream_t s);
+int launch_bn_bwd_apply(const void* g_full, const void* g_pool, int gf_bf16, int gp_bf16, const float* z,
+                        const BnLayer& L, Act act, const void* coef, float* dz, void* dz_b, int B, int H, int W, int round_out, cudaStream_t s);
 
 int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, const float* mean, const float* std,
                 float* loss_out, float* dy_out, float* scratch, int B, int HW, cudaStream_t s);
@@ -139,6 +141,7 @@ int launch_pack_conv1x1(const float* w, float* w_copy, float* w_t, int Co, int C
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int round_tf32,
                         cudaStream_t s);
 int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s);
+int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s);
 int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s);
 // column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)
 int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,
@@ -160,6 +163,12 @@ struct Epilogue {
   float* partials;        // STATS: [m_tiles][N][2]
   const float* bias;      // CONVT: [N/4]
   const float* skip;      // CONVT: NHWC same shape as out (may be null)
+  // CONVT on tcgen05: when skip_scale != null, `skip` holds the RAW conv output z of the encoder level and the
+  // epilogue applies that level's BatchNorm + activation on the fly: skip value = act(z*scale[c] + shift[c])
+  // (the training forward then never writes the full-resolution activated encoder tensor)
+  const float* skip_scale;
+  const float* skip_shift;
+  const float* skip_slope;   // device scalar
   int round_tf32;         // round the stored values to TF32 (they feed a tcgen05 GEMM)
   // BNACT (eval-mode BatchNorm folded into the conv, tcgen05 kernel only): out = act(acc*scale + shift),
   // optionally also the 2x2 max-pooled tensor

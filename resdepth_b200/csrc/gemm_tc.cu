@@ -71,7 +71,10 @@ struct RowsCfg {
 // skip connection of the decoder).
 __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const float (&v)[32], float* __restrict__ out,
                                                 long long off, bool ok, const float* __restrict__ add, int rnd,
-                                                __nv_bfloat16* __restrict__ outb = nullptr) {
+                                                __nv_bfloat16* __restrict__ outb = nullptr,
+                                                const float* __restrict__ add_scale = nullptr,
+                                                const float* __restrict__ add_shift = nullptr,
+                                                const float* __restrict__ add_slope = nullptr) {
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4)
     *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
@@ -93,6 +96,18 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
 #pragma unroll
     for (int i = 0; i < 8; ++i)
       a[i] = (okm >> i) & 1 ? __ldg(reinterpret_cast<const float4*>(add + o[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (add_scale) {                 // `add` is a raw conv output: BatchNorm + activation of its layer on the fly
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(add_scale) + c4);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(add_shift) + c4);
+      const float sl = __ldg(add_slope);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y0 = fmaf(a[i].x, sc.x, sh.x), y1 = fmaf(a[i].y, sc.y, sh.y);
+        float y2 = fmaf(a[i].z, sc.z, sh.z), y3 = fmaf(a[i].w, sc.w, sh.w);
+        a[i].x = y0 > 0.f ? y0 : y0 * sl; a[i].y = y1 > 0.f ? y1 : y1 * sl;
+        a[i].z = y2 > 0.f ? y2 : y2 * sl; a[i].w = y3 > 0.f ? y3 : y3 * sl;
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -101,7 +116,7 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
     if (add) { val.x += a[i].x; val.y += a[i].y; val.z += a[i].z; val.w += a[i].w; }
     if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
     if ((okm >> i) & 1) {
-      *reinterpret_cast<float4*>(out + o[i]) = val;
+      if (out) *reinterpret_cast<float4*>(out + o[i]) = val;
       if (outb) {
         __nv_bfloat162 lo2 = __floats2bfloat162_rn(val.x, val.y), hi2 = __floats2bfloat162_rn(val.z, val.w);
         uint2 pk;
@@ -112,6 +127,102 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
     }
   }
   __syncwarp();
+}
+
+// Transposed-conv epilogue of one warp for one 128-row (sub-)tile: + bias, + additive skip (optionally BatchNorm +
+// activation of the raw encoder output on the fly), scatter to the 2x2 output sites, optional TF32 rounding and
+// bf16 copy.  The layer is HBM-bound and the skip read sits on the critical path of every store, so the skip rows
+// of the NEXT 32-column chunk are requested before the current chunk is stored (two chunks = 8 KB per warp in
+// flight).  Output offsets split into a row part (shuffled once per tile into the transposed domain: lane -> rows
+// i*4 + lane/8, columns 4*(lane%8)..+3) and a warp-uniform chunk part.
+template <int BN>
+__device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg, int lane, int half, uint32_t t_row,
+                                               int nt, int b, int h, int w, bool valid) {
+  constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
+  const int Co = P.N >> 2;
+  const int c4 = lane & 7;
+  // 32-bit element offsets: the launcher rejects outputs of 2^32 elements or more
+  const unsigned rrow = (unsigned)((((size_t)b * 2 * P.Ho + 2 * h) * 2 * P.Wo + 2 * w) * Co);
+  unsigned R[8];
+  unsigned okm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    R[i] = __shfl_sync(0xffffffffu, rrow, r) + c4 * 4;
+    okm |= (unsigned)__shfl_sync(0xffffffffu, (int)valid, r) << i;
+  }
+  auto chunk_off = [&](int ch, int& co) -> unsigned {
+    const int n = nt * BN + ch * 32;
+    const int ab = n / Co;
+    co = n - ab * Co;
+    return (unsigned)(((ab >> 1) * 2 * P.Wo + (ab & 1)) * Co + co);
+  };
+  const bool has_skip = P.skip != nullptr;
+  float4 a_cur[8], a_nxt[8];
+  auto prefetch = [&](int ch, float4 (&a)[8]) {
+    int co;
+    const unsigned S = chunk_off(ch, co);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      a[i] = (okm >> i) & 1 ? __ldg(reinterpret_cast<const float4*>(P.skip + (size_t)(R[i] + S))) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a_cur[i] = a_nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_skip && half < NCH) prefetch(half, a_cur);
+  __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(P.out_b);
+#pragma unroll
+  for (int ci = 0; ci < NCH2; ++ci) {
+    const int ch = 2 * ci + half;
+    if (ch >= NCH) break;
+    float v[32];
+    tmem_ld32(t_row + ch * 32, v);
+    int co;
+    const unsigned S = chunk_off(ch, co);
+    const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 bv = __ldg(bp + j);
+      *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+          make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
+    }
+    __syncwarp();
+    if (has_skip && ch + 2 < NCH) prefetch(ch + 2, a_nxt);     // v[] is dead here: a_nxt takes its registers
+    if (has_skip && P.skip_scale) {    // the skip tensor is a raw conv output: BatchNorm + activation of its layer
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(P.skip_scale + co) + c4);
+      const float4 sh = __ldg(reinterpret_cast<const float4*>(P.skip_shift + co) + c4);
+      const float sl = __ldg(P.skip_slope);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y0 = fmaf(a_cur[i].x, sc.x, sh.x), y1 = fmaf(a_cur[i].y, sc.y, sh.y);
+        const float y2 = fmaf(a_cur[i].z, sc.z, sh.z), y3 = fmaf(a_cur[i].w, sc.w, sh.w);
+        a_cur[i].x = y0 > 0.f ? y0 : y0 * sl; a_cur[i].y = y1 > 0.f ? y1 : y1 * sl;
+        a_cur[i].z = y2 > 0.f ? y2 : y2 * sl; a_cur[i].w = y3 > 0.f ? y3 : y3 * sl;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      float4 val = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+      val.x += a_cur[i].x; val.y += a_cur[i].y; val.z += a_cur[i].z; val.w += a_cur[i].w;
+      if (P.round_tf32) {
+        val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w);
+      }
+      if ((okm >> i) & 1) {
+        const size_t o = (size_t)(R[i] + S);
+        *reinterpret_cast<float4*>(P.out + o) = val;
+        if (outb) {
+          __nv_bfloat162 lo2 = __floats2bfloat162_rn(val.x, val.y), hi2 = __floats2bfloat162_rn(val.z, val.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+          *reinterpret_cast<uint2*>(outb + o) = pk;
+        }
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a_cur[i] = a_nxt[i];
+  }
 }
 
 template <int BN, bool HALO, bool BF16>
@@ -313,6 +424,10 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const bool valid = (w < P.Wo) && (h < P.Ho) && (b < P.Bo);
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + acc * Cfg::ACC_COLS + sub * BN;
       const size_t pix = ((size_t)b * P.Ho + h) * P.Wo + w;
+      if (P.epi_mode == EPI_CONVT) {
+        convt_epilogue<BN>(P, stg, lane, half, t_row, nt, b, h, w, valid);
+        continue;
+      }
 #pragma unroll
       for (int ci = 0; ci < NCH2; ++ci) {
         const int ch = 2 * ci + half;
@@ -320,19 +435,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         float v[32];
         tmem_ld32(t_row + ch * 32, v);
         const int n = nt * BN + ch * 32;
-        if (P.epi_mode == EPI_CONVT) {
-          // + bias here (row-independent); the additive skip is read in the transposed, coalesced domain
-          const int Co = P.N >> 2;
-          const int ab = n / Co, co = n - ab * Co;
-          const long long o = (long long)(((((size_t)b * 2 * P.Ho + 2 * h + (ab >> 1)) * 2 * P.Wo) + 2 * w + (ab & 1)) * Co + co);
-          const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bv = __ldg(bp + j);
-            v[4 * j] += bv.x; v[4 * j + 1] += bv.y; v[4 * j + 2] += bv.z; v[4 * j + 3] += bv.w;
-          }
-          warp_store_rows(stg, lane, v, P.out, o, valid, P.skip, P.round_tf32, reinterpret_cast<__nv_bfloat16*>(P.out_b));
-        } else if (P.epi_mode == EPI_BNACT) {
+        if (P.epi_mode == EPI_BNACT) {
           // eval-mode BatchNorm folded into the conv: a = act(acc*scale + shift); optional fused 2x2 max-pool
           // (the 2x2 window of a pixel lives in lanes l, l^1, l^tw, l^tw^1 of this warp)
           const float slope = __ldg(P.slope);
@@ -554,6 +657,9 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
   P.partials = e.partials;
   P.bias = e.bias;
   P.skip = e.skip;
+  P.skip_scale = e.skip_scale;
+  P.skip_shift = e.skip_shift;
+  P.skip_slope = e.skip_slope;
   P.round_tf32 = e.round_tf32;
   P.scale = e.scale;
   P.shift = e.shift;
@@ -561,6 +667,8 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
   P.pool_out = e.pool_out;
   P.round_pool = e.round_pool;
   P.out_b = e.out_b;
+  if (e.mode == EPI_CONVT && (double)P.Bo * P.Ho * P.Wo * P.N >= 4294967296.0)
+    return fail("tc rows: transposed-conv output of 2^32 elements or more (reduce the batch)");
   if (e.mode == EPI_BNACT && e.pool_out && (P.tw < 2 || P.th < 2 || (P.Wo & 1) || (P.Ho & 1)))
     return fail("tc rows: fused pooling needs even image sizes and a tile of at least 2x2 pixels");
   const int n_tiles = P.N / plan.BN;

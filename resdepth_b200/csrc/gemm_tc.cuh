@@ -23,6 +23,9 @@ struct TcRowsParams {
   float* partials;
   const float* bias;
   const float* skip;
+  const float* skip_scale;   // see Epilogue
+  const float* skip_shift;
+  const float* skip_slope;
   const float* scale;    // EPI_BNACT
   const float* shift;
   const float* slope;

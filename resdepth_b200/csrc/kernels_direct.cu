@@ -254,6 +254,117 @@ int launch_conv_first_wgrad(const float* x, const float* dz, float* dw, float* s
 // ----------------------------------------------------------------------------------------------
 static constexpr int LT_H = 16, LT_W = 32;                       // output tile of one block
 static constexpr int LH_H = LT_H + 2, LH_W = LT_W + 2;           // with halo
+// phase 2 of both forward variants: one thread per output pixel gathers the 9 partials of its 3x3 neighbourhood
+__device__ __forceinline__ void conv_last_gather(const float (*ts)[9], const float* __restrict__ bias,
+                                                 const float* __restrict__ x0, long long x_bstride,
+                                                 const float* __restrict__ x_affine, float* __restrict__ y, int b,
+                                                 int h0, int w0, int H, int W) {
+  const float bv = bias ? bias[0] : 0.f;
+  for (int o = threadIdx.x; o < LT_H * LT_W; o += 256) {
+    const int lh = o / LT_W, lw = o - lh * LT_W;
+    const int gh = h0 + lh, gw = w0 + lw;
+    if (gh < H && gw < W) {
+      float a = bv;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) a += ts[(lh + r) * LH_W + lw + q][r * 3 + q];
+      if (x0) {
+        const float xv = x0[(size_t)b * x_bstride + (size_t)gh * W + gw];
+        a += x_affine ? fmaf(xv, x_affine[0], x_affine[1]) : xv;
+      }
+      y[((size_t)b * H + gh) * W + gw] = a;
+    }
+  }
+}
+
+// Fast variant for C <= 64.  Phase 1: a half-warp owns four consecutive halo pixels per iteration; lane l holds
+// channels 4l..4l+3 (one coalesced 256-byte row per pixel and half-warp, weights resident in registers), forms
+// the 9 tap partials of each of the 4 pixels over its channels (36 accumulators) and the half-warp reduces them
+// with a transposing butterfly: 35 shuffle+add pairs instead of 144.  The butterfly needs no selects because every
+// lane keeps its accumulators in a lane-specific ORDER: pixel slot i holds pixel i ^ (lane bits 3,2) and tap slot
+// s holds tap kTapPerm[lane bits 1,0][s], so that "keep the low half, send the high half" is the same instruction
+// stream for both partners of every exchange.  Lane l ends with pixel (l>>2)&3 and taps kTapPerm[l&3][0..1]
+// (lane bits 00 also with tap 4).
+__constant__ signed char kTapPerm[4][9] = {{0, 1, 2, 3, 4, 5, 6, 7, 8},
+                                           {2, 3, 0, 1, 4, 7, 8, 5, 6},
+                                           {5, 6, 7, 8, 4, 0, 1, 2, 3},
+                                           {7, 8, 5, 6, 4, 2, 3, 0, 1}};
+__global__ void __launch_bounds__(256, 2)
+conv_last_fwd64_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
+                       const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
+                       float* __restrict__ y, int B, int H, int W, int C, int tiles_x, int tiles_y) {
+  __shared__ float ts[LH_H * LH_W][9];
+  __shared__ float wsm[64 * 9];
+  const int tid = threadIdx.x;
+  const int l16 = tid & 15, hw = tid >> 4;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int h0 = ty * LT_H, w0 = tx * LT_W;
+  const int c0 = l16 * 4;
+  for (int i = tid; i < C * 9; i += 256) wsm[i] = w[i];
+  __syncthreads();
+  const int tsel = l16 & 3;                 // tap order of this lane
+  const int pperm = (l16 >> 2) & 3;         // pixel order of this lane (slot i holds pixel i ^ pperm)
+  int tap[9];
+  float4 wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    tap[k] = kTapPerm[tsel][k];
+    wr[k] = c0 < C ? make_float4(wsm[(c0 + 0) * 9 + tap[k]], wsm[(c0 + 1) * 9 + tap[k]], wsm[(c0 + 2) * 9 + tap[k]],
+                                 wsm[(c0 + 3) * 9 + tap[k]])
+                   : make_float4(0, 0, 0, 0);
+  }
+  const int tap0 = tap[0], tap1 = tap[1];
+  constexpr int NPIX = LH_H * LH_W, NGROUPS = (NPIX + 3) / 4;
+  auto load_group = [&](int g, float4 (&dst)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = g * 4 + (i ^ pperm);
+      const int hh = p / LH_W, ww = p - hh * LH_W;
+      const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+      const bool ok = p < NPIX && (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W && c0 < C;
+      dst[i] = ok ? __ldg(reinterpret_cast<const float4*>(u + (((size_t)b * H + gh) * W + gw) * C + c0))
+                  : make_float4(0, 0, 0, 0);
+    }
+  };
+  float4 uv[4], nx[4];
+  load_group(hw, uv);
+#pragma unroll 1
+  for (int g0 = 0; g0 < NGROUPS; g0 += 16) {
+    const int g = g0 + hw;
+    load_group(g + 16, nx);                            // next iteration's rows are in flight during the butterfly
+    float v[36];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        v[i * 9 + k] = fmaf(uv[i].x, wr[k].x, fmaf(uv[i].y, wr[k].y, fmaf(uv[i].z, wr[k].z, uv[i].w * wr[k].w)));
+#pragma unroll
+    for (int j = 0; j < 18; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 18], 8);     // pixel pairs
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 9], 4);       // pixels
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 5], 2);       // tap groups {0-3|5-8}, 4
+    v[4] += __shfl_xor_sync(0xffffffffu, v[4], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[2], 1);                                       // tap pairs
+    v[1] += __shfl_xor_sync(0xffffffffu, v[3], 1);
+    v[4] += __shfl_xor_sync(0xffffffffu, v[4], 1);
+    const int p = g * 4 + pperm;
+    if (p < NPIX) {
+      ts[p][tap0] = v[0];
+      ts[p][tap1] = v[1];
+      if (tsel == 0) ts[p][4] = v[4];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) uv[i] = nx[i];
+  }
+  __syncthreads();
+  conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
+}
+
 __global__ void __launch_bounds__(256)
 conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
@@ -293,24 +404,7 @@ conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, c
     for (int k = 0; k < 9; ++k) ts[p][k] = acc[k];
   }
   __syncthreads();
-  // phase 2: one thread per output pixel gathers the 9 partials of its 3x3 neighbourhood
-  const float bv = bias ? bias[0] : 0.f;
-  for (int o = tid; o < LT_H * LT_W; o += 256) {
-    const int lh = o / LT_W, lw = o - lh * LT_W;
-    const int gh = h0 + lh, gw = w0 + lw;
-    if (gh < H && gw < W) {
-      float a = bv;
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int q = 0; q < 3; ++q) a += ts[(lh + r) * LH_W + lw + q][r * 3 + q];
-      if (x0) {
-        const float xv = x0[(size_t)b * x_bstride + (size_t)gh * W + gw];
-        a += x_affine ? fmaf(xv, x_affine[0], x_affine[1]) : xv;
-      }
-      y[((size_t)b * H + gh) * W + gw] = a;
-    }
-  }
+  conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
 }
 
 int launch_conv_last_fwd(const float* u, const float* w, const float* bias, const float* x, int x_bstride,
@@ -318,7 +412,10 @@ int launch_conv_last_fwd(const float* u, const float* w, const float* bias, cons
   if (C % 4 || C > 128) return fail("conv_last: unsupported C=%d (needs C%%4==0, C<=128)", C);
   const int tiles_x = cdiv(W, LT_W), tiles_y = cdiv(H, LT_H);
   const int grid = tiles_x * tiles_y * B;
-  conv_last_fwd_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
+  if (C <= 64)
+    conv_last_fwd64_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
+  else
+    conv_last_fwd_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
   RD_LAUNCHED();
   return 0;
 }
@@ -407,7 +504,7 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
               dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
               dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
             }
-            *reinterpret_cast<float4*>(du + o + c) = d;
+            if (du) *reinterpret_cast<float4*>(du + o + c) = d;
             if (du_b) {
               __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
               uint2 pk;

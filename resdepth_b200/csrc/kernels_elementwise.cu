@@ -36,6 +36,13 @@ __device__ __forceinline__ void st4_bf16(void* base, size_t elem, float4 v) {
 }
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// 4 consecutive elements of a gradient tensor stored as fp32 or (bf16 != 0) as bf16
+__device__ __forceinline__ float4 ld4g(const void* base, size_t elem, int bf16) {
+  if (!bf16) return ld4(reinterpret_cast<const float*>(base) + elem);
+  const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + elem);
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u), __uint_as_float(r.y << 16),
+                     __uint_as_float(r.y & 0xffff0000u));
+}
 
 static int ew_grid(long long work_items) {
   long long g = (work_items + EW_THREADS - 1) / EW_THREADS;
@@ -139,7 +146,7 @@ bn_act_pool_kernel(const float* __restrict__ z, const float* __restrict__ scale,
         r.y = act1(fmaf(v.y, sc.y, sh.y), slope);
         r.z = act1(fmaf(v.z, sc.z, sh.z), slope);
         r.w = act1(fmaf(v.w, sc.w, sh.w), slope);
-        st4(a + o, round_a ? tf32_rn4(r) : r);
+        if (a) st4(a + o, round_a ? tf32_rn4(r) : r);      // a == null: consumers re-derive it from z (CONVT epilogue)
         if (a_b) st4_bf16(a_b, o, r);
         if (k == 0) m = r;
         else { m.x = fmaxf(m.x, r.x); m.y = fmaxf(m.y, r.y); m.z = fmaxf(m.z, r.z); m.w = fmaxf(m.w, r.w); }
@@ -196,9 +203,11 @@ struct BwdCoef {            // per channel, built by bn_bwd_finalize
   float mean, cs, c1, c2;
 };
 
-template <bool POOL, bool APPLY>
-__global__ void __launch_bounds__(EW_THREADS, APPLY ? 4 : 1)
-bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool, const float* __restrict__ z,
+// RELU: the activation is a plain ReLU (slope 0, no slope gradient) -- the common case, with a shorter inner loop
+template <bool POOL, bool APPLY, bool RELU>
+__global__ void __launch_bounds__(EW_THREADS, APPLY ? 4 : 3)
+bn_bwd_kernel(const void* __restrict__ g_full, const void* __restrict__ g_pool, int gf_bf16, int gp_bf16,
+              const float* __restrict__ z,
               const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ slope_p,
               const float* __restrict__ mean, const BwdCoef* __restrict__ coef, float* __restrict__ dz,
               float* __restrict__ partials, int B, int H, int W, int C, int round_out, void* __restrict__ dz_b) {
@@ -206,7 +215,7 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
   const int Q = C >> 2;
   const int PL = EW_THREADS / Q;                       // pixel lanes per block
   const int q = threadIdx.x % Q, pl = threadIdx.x / Q;
-  const float slope = *slope_p;
+  const float slope = RELU ? 0.f : *slope_p;
   float s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0}, s3[4] = {0, 0, 0, 0};
   if (pl < PL) {
     const float4 sc4 = ld4(scale + q * 4), sh4 = ld4(shift + q * 4);
@@ -225,9 +234,11 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
     const long long nwin = (long long)B * Hw * Ww;
     for (long long wi = (long long)blockIdx.x * PL + pl; wi < nwin; wi += (long long)gridDim.x * PL) {
       if (POOL) {
-        const int wp = (int)(wi % Ww);
-        const int hp = (int)((wi / Ww) % Hw);
-        const int b = (int)(wi / ((long long)Ww * Hw));
+        const unsigned wiu = (unsigned)wi;             // launchers guarantee B*H*W < 2^32: 32-bit index math
+        const unsigned t_ = wiu / (unsigned)Ww;
+        const int wp = (int)(wiu - t_ * (unsigned)Ww);
+        const int b = (int)(t_ / (unsigned)Hw);
+        const int hp = (int)(t_ - (unsigned)b * (unsigned)Hw);
         const size_t base = (((size_t)b * H + 2 * hp) * W + 2 * wp) * C + q * 4;
         float zz[4][4], yy[4][4], gf[4][4];
 #pragma unroll
@@ -236,13 +247,13 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
           const float4 v = ld4(z + o);
           zz[k][0] = v.x; zz[k][1] = v.y; zz[k][2] = v.z; zz[k][3] = v.w;
           if (g_full) {
-            const float4 g = ld4(g_full + o);
+            const float4 g = ld4g(g_full, o, gf_bf16);
             gf[k][0] = g.x; gf[k][1] = g.y; gf[k][2] = g.z; gf[k][3] = g.w;
           } else {
             gf[k][0] = gf[k][1] = gf[k][2] = gf[k][3] = 0.f;
           }
         }
-        const float4 gp4 = ld4(g_pool + (size_t)wi * C + q * 4);
+        const float4 gp4 = ld4g(g_pool, (size_t)wi * C + q * 4, gp_bf16);
         const float gp[4] = {gp4.x, gp4.y, gp4.z, gp4.w};
         float out[4][4];
 #pragma unroll
@@ -252,21 +263,23 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             yy[k][c] = fmaf(zz[k][c], sc[c], sh[c]);
-            const float av = act1(yy[k][c], slope);
+            // ReLU: the first maximum of max(y,0) is the first maximum of y wherever the window's gradient survives
+            // the ReLU mask (an all-nonpositive window has gY = 0 at every site)
+            const float av = RELU ? yy[k][c] : act1(yy[k][c], slope);
             if (k == 0 || av > best) { best = av; arg = k; }
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float gA = gf[k][c] + (k == arg ? gp[c] : 0.f);
             const float y = yy[k][c];
-            const float gY = y > 0.f ? gA : gA * slope;
+            const float gY = RELU ? (y > 0.f ? gA : 0.f) : (y > 0.f ? gA : gA * slope);
             const float zc = zz[k][c] - mu[c];
             if (APPLY) {
               out[k][c] = cs[c] * (gY - c1[c] - zc * c2[c]);
             } else {
               s1[c] += gY;
               s2[c] = fmaf(gY, zc, s2[c]);
-              s3[c] += y > 0.f ? 0.f : gA * y;
+              if (!RELU) s3[c] += y > 0.f ? 0.f : gA * y;
             }
           }
         }
@@ -281,20 +294,20 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
         }
       } else {
         const size_t o = (size_t)wi * C + q * 4;
-        const float4 v = ld4(z + o), g = ld4(g_full + o);
+        const float4 v = ld4(z + o), g = ld4g(g_full, o, gf_bf16);
         const float zz[4] = {v.x, v.y, v.z, v.w}, gA[4] = {g.x, g.y, g.z, g.w};
         float out[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const float y = fmaf(zz[c], sc[c], sh[c]);
-          const float gY = y > 0.f ? gA[c] : gA[c] * slope;
+          const float gY = RELU ? (y > 0.f ? gA[c] : 0.f) : (y > 0.f ? gA[c] : gA[c] * slope);
           const float zc = zz[c] - mu[c];
           if (APPLY) {
             out[c] = cs[c] * (gY - c1[c] - zc * c2[c]);
           } else {
             s1[c] += gY;
             s2[c] = fmaf(gY, zc, s2[c]);
-            s3[c] += y > 0.f ? 0.f : gA[c] * y;
+            if (!RELU) s3[c] += y > 0.f ? 0.f : gA[c] * y;
           }
         }
         if (APPLY) {
@@ -322,31 +335,48 @@ bn_bwd_kernel(const float* __restrict__ g_full, const float* __restrict__ g_pool
   }
 }
 
-static int bwd_grid(long long nwin, int PL) {
+static int bwd_grid(long long nwin, int PL, int per_sm = 4) {
   long long g = (nwin + PL - 1) / PL;
-  if (g > 148 * 4) g = 148 * 4;
+  if (g > 148 * per_sm) g = 148 * per_sm;
   if (g < 1) g = 1;
   return (int)g;
 }
 
-int launch_bn_bwd_reduce(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
-                         float* partials, int* n_partials, int B, int H, int W, cudaStream_t s) {
+int launch_bn_bwd_reduce(const void* g_full, const void* g_pool, int gf_bf16, int gp_bf16, const float* z,
+                         const BnLayer& L, Act act, float* partials, int* n_partials, int B, int H, int W,
+                         cudaStream_t s) {
   const int C = L.C, Q = C / 4;
   if (C % 4 || Q > EW_THREADS) return fail("bn_bwd: unsupported C=%d", C);
+  if ((long long)B * H * W >= (1LL << 32)) return fail("bn_bwd: more than 2^32 pixels");
   const int PL = EW_THREADS / Q;
   const size_t smem = (size_t)PL * C * 3 * sizeof(float);
   int grid;
+  const bool relu = act.kind == RD_ACT_RELU;
   if (g_pool) {
-    grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL);
-    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    bn_bwd_kernel<true, false><<<grid, EW_THREADS, smem, s>>>(g_full, g_pool, z, L.scale, L.shift, act.slope, L.mean,
-                                                              nullptr, nullptr, partials, B, H, W, C, 0, nullptr);
+    grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL, 3);     // 3 resident CTAs per SM: one wave
+#define RD_BWD_R(RL)                                                                                              \
+  {                                                                                                               \
+    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<true, false, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                 64 * 1024));                                                                     \
+    bn_bwd_kernel<true, false, RL><<<grid, EW_THREADS, smem, s>>>(g_full, g_pool, gf_bf16, gp_bf16, z, L.scale,   \
+                                                                  L.shift, act.slope, L.mean, nullptr, nullptr,   \
+                                                                  partials, B, H, W, C, 0, nullptr);              \
+  }
+    if (relu) RD_BWD_R(true) else RD_BWD_R(false)
+#undef RD_BWD_R
   } else {
     if (!g_full) return fail("bn_bwd: no incoming gradient");
-    grid = bwd_grid((long long)B * H * W, PL);
-    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    bn_bwd_kernel<false, false><<<grid, EW_THREADS, smem, s>>>(g_full, nullptr, z, L.scale, L.shift, act.slope,
-                                                               L.mean, nullptr, nullptr, partials, B, H, W, C, 0, nullptr);
+    grid = bwd_grid((long long)B * H * W, PL, 3);
+#define RD_BWD_R(RL)                                                                                              \
+  {                                                                                                               \
+    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<false, false, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                 64 * 1024));                                                                     \
+    bn_bwd_kernel<false, false, RL><<<grid, EW_THREADS, smem, s>>>(g_full, nullptr, gf_bf16, 0, z, L.scale,       \
+                                                                   L.shift, act.slope, L.mean, nullptr, nullptr,  \
+                                                                   partials, B, H, W, C, 0, nullptr);             \
+  }
+    if (relu) RD_BWD_R(true) else RD_BWD_R(false)
+#undef RD_BWD_R
   }
   RD_LAUNCHED();
   *n_partials = grid;
@@ -424,20 +454,32 @@ int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, 
   return 0;
 }
 
-int launch_bn_bwd_apply(const float* g_full, const float* g_pool, const float* z, const BnLayer& L, Act act,
-                        const void* coef, float* dz, void* dz_b, int B, int H, int W, int round_out, cudaStream_t s) {
+int launch_bn_bwd_apply(const void* g_full, const void* g_pool, int gf_bf16, int gp_bf16, const float* z,
+                        const BnLayer& L, Act act, const void* coef, float* dz, void* dz_b, int B, int H, int W, int round_out, cudaStream_t s) {
   const int C = L.C, Q = C / 4;
   const int PL = EW_THREADS / Q;
+  const bool relu = act.kind == RD_ACT_RELU;
+  const BwdCoef* cf = reinterpret_cast<const BwdCoef*>(coef);
   if (g_pool) {
     const int grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL) * 2;
-    bn_bwd_kernel<true, true><<<grid, EW_THREADS, 0, s>>>(g_full, g_pool, z, L.scale, L.shift, act.slope, L.mean,
-                                                          reinterpret_cast<const BwdCoef*>(coef), dz, nullptr, B, H,
-                                                          W, C, round_out, dz_b);
+    if (relu)
+      bn_bwd_kernel<true, true, true><<<grid, EW_THREADS, 0, s>>>(g_full, g_pool, gf_bf16, gp_bf16, z, L.scale, L.shift,
+                                                                  act.slope, L.mean, cf, dz, nullptr, B, H, W, C,
+                                                                  round_out, dz_b);
+    else
+      bn_bwd_kernel<true, true, false><<<grid, EW_THREADS, 0, s>>>(g_full, g_pool, gf_bf16, gp_bf16, z, L.scale, L.shift,
+                                                                   act.slope, L.mean, cf, dz, nullptr, B, H, W, C,
+                                                                   round_out, dz_b);
   } else {
     const int grid = bwd_grid((long long)B * H * W, PL) * 2;
-    bn_bwd_kernel<false, true><<<grid, EW_THREADS, 0, s>>>(g_full, nullptr, z, L.scale, L.shift, act.slope, L.mean,
-                                                           reinterpret_cast<const BwdCoef*>(coef), dz, nullptr, B, H,
-                                                           W, C, round_out, dz_b);
+    if (relu)
+      bn_bwd_kernel<false, true, true><<<grid, EW_THREADS, 0, s>>>(g_full, nullptr, gf_bf16, 0, z, L.scale, L.shift,
+                                                                   act.slope, L.mean, cf, dz, nullptr, B, H, W, C,
+                                                                   round_out, dz_b);
+    else
+      bn_bwd_kernel<false, true, false><<<grid, EW_THREADS, 0, s>>>(g_full, nullptr, gf_bf16, 0, z, L.scale, L.shift,
+                                                                    act.slope, L.mean, cf, dz, nullptr, B, H, W, C,
+                                                                    round_out, dz_b);
   }
   RD_LAUNCHED();
   return 0;
@@ -734,7 +776,7 @@ int launch_unpack_convt_grad(const float* part, int S, float* dw, int Ci, int Co
 // Kc = Cin*9 rounded up to 32) so that dW[co][k] = sum_p xcol[p][k] * dz[p][co] is a plain reduce GEMM.
 // one thread per pixel: reads its 3x3 neighbourhood of every input channel (neighbours hit in L1) and writes the
 // Kc-float row of xcol as full 128-byte lines
-template <int KC, bool BF16>
+template <int KC>
 __global__ void __launch_bounds__(256)
 im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B, int Cin, int H, int W, int rnd) {
   const long long npix = (long long)B * H * W;
@@ -762,33 +804,70 @@ im2col_first_kernel(const float* __restrict__ x, float* __restrict__ xcol, int B
         }
       }
     }
-    if (BF16) {
+    float4* dst = reinterpret_cast<float4*>(xcol + (size_t)p * KC);
 #pragma unroll
-      for (int j = 0; j < KC / 4; ++j)
-        st4_bf16(xcol, (size_t)p * KC + 4 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
-    } else {
-      float4* dst = reinterpret_cast<float4*>(xcol + (size_t)p * KC);
-#pragma unroll
-      for (int j = 0; j < KC / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    for (int j = 0; j < KC / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
 }
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int rnd, cudaStream_t s) {
   const int grid = ew_grid((long long)B * H * W);
-  if (Kc == 32) im2col_first_kernel<32, false><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
-  else if (Kc == 64) im2col_first_kernel<64, false><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
-  else if (Kc == 96) im2col_first_kernel<96, false><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  if (Kc == 32) im2col_first_kernel<32><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else if (Kc == 64) im2col_first_kernel<64><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
+  else if (Kc == 96) im2col_first_kernel<96><<<grid, 256, 0, s>>>(x, xcol, B, Cin, H, W, rnd);
   else return fail("im2col_first: unsupported Kc=%d", Kc);
   RD_LAUNCHED();
   return 0;
 }
-// bf16 variant: xcol is a bf16 tensor [B*H*W][Kc] with Kc = 64 (Cin <= 7) or 128
+// bf16 variant: xcol is a bf16 tensor [B*H*W][Kc] with Kc = 64 (Cin <= 7) or 128.  One thread per (pixel, 16-byte
+// chunk of 8 k-values): the warp's stores cover whole 32-byte sectors of consecutive rows, and only the
+// ceil(Cin*9/8) chunks that hold data are written -- the padding of every row is zeroed once by rd_reserve
+// (launch_im2col_first_bf16_clear) and never touched again.
+template <int KC>
+__global__ void __launch_bounds__(256)
+im2col_first_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xcol, int B, int Cin, int H, int W,
+                         int chunks) {
+  const int K = Cin * 9;
+  const int per_row = W * chunks;
+  for (int row = blockIdx.x; row < B * H; row += gridDim.x) {          // one image row per iteration: 32-bit math
+    const int b = row / H, h = row - b * H;
+    const float* xb = x + (size_t)b * Cin * H * W;
+    __nv_bfloat16* orow = xcol + (size_t)row * W * KC;
+    for (int t = threadIdx.x; t < per_row; t += 256) {
+      const int w = t / chunks, c = t - w * chunks;
+      uint32_t pk[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = c * 8 + jj * 2 + e;
+          const int ci = k / 9, rs = k - ci * 9;
+          const int r = rs / 3, q = rs - r * 3;
+          const int hh = h + r - 1, ww = w + q - 1;
+          const bool ok = k < K && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+          v[e] = ok ? __ldg(xb + (ci * H + hh) * W + ww) : 0.f;
+        }
+        __nv_bfloat162 bb = __floats2bfloat162_rn(v[0], v[1]);
+        pk[jj] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      *reinterpret_cast<uint4*>(orow + (size_t)w * KC + c * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
 int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s) {
-  const int grid = ew_grid((long long)B * H * W);
-  if (Kc == 64) im2col_first_kernel<64, true><<<grid, 256, 0, s>>>(x, reinterpret_cast<float*>(xcol), B, Cin, H, W, 0);
-  else if (Kc == 128) im2col_first_kernel<128, true><<<grid, 256, 0, s>>>(x, reinterpret_cast<float*>(xcol), B, Cin, H, W, 0);
+  const int chunks = (Cin * 9 + 7) / 8;
+  if (chunks * 8 > Kc) return fail("im2col_first_bf16: Kc=%d too small for Cin=%d", Kc, Cin);
+  const int grid = B * H < 148 * 8 ? B * H : 148 * 8;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(xcol);
+  if (Kc == 64) im2col_first_bf16_kernel<64><<<grid, 256, 0, s>>>(x, out, B, Cin, H, W, chunks);
+  else if (Kc == 128) im2col_first_bf16_kernel<128><<<grid, 256, 0, s>>>(x, out, B, Cin, H, W, chunks);
   else return fail("im2col_first_bf16: unsupported Kc=%d", Kc);
   RD_LAUNCHED();
+  return 0;
+}
+// zero the whole expansion once (rows are only partially rewritten by the kernel above)
+int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s) {
+  RD_CUDA(cudaMemsetAsync(xcol, 0, bytes, s));
   return 0;
 }
 // part [S][Kc][Co] summed over S -> dW [Co][K] (K = Cin*9 <= Kc; OIHW flattening of the first conv)
