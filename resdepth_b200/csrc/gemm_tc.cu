@@ -45,12 +45,16 @@ static constexpr int HALO_W = 18, HALO_H = 18, HALO_SUB = 2;
 static constexpr int HALO_BYTES = HALO_W * HALO_H * 128;             // 41472
 static constexpr int HALO_SLOT = 41 * 1024;                           // 1024-byte aligned slot
 
-template <int BN, bool HALO>
+// RING: transposed-conv variant for HBM-bound up-convs (K = C <= 128): a 2-stage operand ring frees 96 KB of shared
+// memory for per-warp cp.async rings that hold the additive-skip rows of the next chunks (see convt_ring_epilogue)
+static constexpr int RING_SLOTS = 3;
+template <int BN, bool HALO, bool RING = false>
 struct RowsCfg {
   static constexpr int A_BYTES = HALO ? HALO_SLOT : 128 * 128;       // plain: 128 rows x 32 fp32
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // plain variant: one ring of (A, B) stages
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = RING ? 2 : (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static_assert(!RING || (!HALO && BN == 256), "skip-ring variant: plain 256-column tiles only");
   static_assert(!HALO || BN <= 128, "halo variant: two sub-tiles x two accumulator stages x BN columns <= 512");
   static constexpr int A_SLOTS = 2;                                  // halo variant: separate rings
   static constexpr int B_SLOTS = (BN == 128) ? 6 : 8;
@@ -60,7 +64,9 @@ struct RowsCfg {
   static constexpr int NBAR_A = HALO ? A_SLOTS : STAGES;
   static constexpr int NBAR_B = HALO ? B_SLOTS : 0;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
+  static constexpr int RING_OFF = DATA_BYTES + 512 + 8 * 4096;
+  static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/ + 8 * 4096 /*epilogue staging*/ +
+                                    (RING ? 8 * RING_SLOTS * 4096 : 0) /*skip rings*/;
 };
 
 // Epilogue store of one warp's 32 rows x 32 columns.  After tcgen05.ld a lane owns one ROW (32 consecutive floats of
@@ -75,10 +81,11 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
                                                 const float* __restrict__ add_scale = nullptr,
                                                 const float* __restrict__ add_shift = nullptr,
                                                 const float* __restrict__ add_slope = nullptr) {
+  const uint32_t stg_s = smem_u32(stg);
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4)
-    *reinterpret_cast<float4*>(stg + lane * 32 + ((c4 ^ (lane & 7)) << 2)) =
-        make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+    sts128(stg_s + (lane * 32 + ((c4 ^ (lane & 7)) << 2)) * 4,
+             make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
   __syncwarp();
   const int c4 = lane & 7;
   const unsigned off_lo = (unsigned)(off & 0xffffffffu), off_hi = (unsigned)((unsigned long long)off >> 32);
@@ -112,7 +119,7 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3);
-    float4 val = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+    float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
     if (add) { val.x += a[i].x; val.y += a[i].y; val.z += a[i].z; val.w += a[i].w; }
     if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
     if ((okm >> i) & 1) {
@@ -139,6 +146,7 @@ template <int BN>
 __device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg, int lane, int half, uint32_t t_row,
                                                int nt, int b, int h, int w, bool valid) {
   constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
+  const uint32_t stg_s = smem_u32(stg);
   const int Co = P.N >> 2;
   const int c4 = lane & 7;
   // 32-bit element offsets: the launcher rejects outputs of 2^32 elements or more
@@ -182,8 +190,8 @@ __device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 bv = __ldg(bp + j);
-      *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) =
-          make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w);
+      sts128(stg_s + (lane * 32 + ((j ^ (lane & 7)) << 2)) * 4,
+             make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w));
     }
     __syncwarp();
     if (has_skip && ch + 2 < NCH) prefetch(ch + 2, a_nxt);     // v[] is dead here: a_nxt takes its registers
@@ -202,7 +210,7 @@ __device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + (lane >> 3);
-      float4 val = *reinterpret_cast<const float4*>(stg + r * 32 + ((c4 ^ (r & 7)) << 2));
+      float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
       val.x += a_cur[i].x; val.y += a_cur[i].y; val.z += a_cur[i].z; val.w += a_cur[i].w;
       if (P.round_tf32) {
         val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w);
@@ -225,11 +233,153 @@ __device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg
   }
 }
 
-template <int BN, bool HALO, bool BF16>
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t n = pred ? 16u : 0u;                  // src-size 0: the 16 bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Whole epilogue loop of one warp for the skip-ring transposed-conv variant.  The layer is HBM-bound and every
+// output store waits for its skip row, so the skip rows are fetched with cp.async RING_SLOTS-1 chunks (8 KB per
+// warp, 64 KB per SM) ahead of their use -- across tile boundaries, without holding registers.  The copy runs
+// in the transposed domain (lane -> rows i*4 + lane/8, 16-byte column group lane%8): each lane later reads back
+// exactly the 16 bytes it copied, so no cross-lane synchronisation is needed.
+template <int BN>
+__device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8_t* ring, float* stg, int lane, int q,
+                                                    int half, uint32_t tmem_base, uint64_t* tfull_bar,
+                                                    uint64_t* tempty_bar, int num_tiles, int n_tiles) {
+  constexpr int NCH2 = BN / 64;                         // chunks of this warp per tile (even / odd 32-column chunks)
+  const uint32_t stg_s = smem_u32(stg);
+  const int Co = P.N >> 2;
+  const int c4 = lane & 7;
+  const int row = q * 32 + lane;
+  const int iw = row % P.tw, ih = (row / P.tw) % P.th, ib = row / (P.tw * P.th);
+  const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total = my_tiles * NCH2;
+  auto tile_row = [&](int it, int& nt, bool& valid) -> unsigned {      // element offset of this lane's row, tile `it`
+    const int tile = blockIdx.x + it * gridDim.x;
+    nt = tile % n_tiles;
+    int mt = tile / n_tiles;
+    const int tw_i = mt % P.tiles_w; mt /= P.tiles_w;
+    const int th_i = mt % P.tiles_h;
+    const int tb_i = mt / P.tiles_h;
+    const int w = tw_i * P.tw + iw, h = th_i * P.th + ih, b = tb_i * P.tb + ib;
+    valid = (w < P.Wo) && (h < P.Ho) && (b < P.Bo);
+    return (unsigned)((((size_t)b * 2 * P.Ho + 2 * h) * 2 * P.Wo + 2 * w) * Co);
+  };
+  auto chunk_off = [&](int nt, int ch, int& co) -> unsigned {
+    const int n = nt * BN + ch * 32;
+    const int ab = n / Co;
+    co = n - ab * Co;
+    return (unsigned)(((ab >> 1) * 2 * P.Wo + (ab & 1)) * Co + co);
+  };
+  auto issue = [&](int m) {                             // request the skip rows of this warp's m-th chunk
+    if (m < total) {
+      int nt, co;
+      bool valid;
+      const unsigned rrow = tile_row(m / NCH2, nt, valid);
+      const unsigned S = chunk_off(nt, 2 * (m % NCH2) + half, co);
+      uint8_t* slot = ring + (m % RING_SLOTS) * 4096;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        const unsigned o = __shfl_sync(0xffffffffu, rrow, r) + c4 * 4 + S;
+        const bool ok = __shfl_sync(0xffffffffu, (int)valid, r) != 0;
+        cp_async16(slot + (i * 32 + lane) * 16, P.skip + (ok ? (size_t)o : 0), ok);
+      }
+    }
+    cp_async_commit();                                  // empty groups keep the group count uniform
+  };
+#pragma unroll
+  for (int m = 0; m < RING_SLOTS - 1; ++m) issue(m);
+  __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(P.out_b);
+  const float sl = P.skip_scale ? __ldg(P.skip_slope) : 0.f;
+  unsigned R[8];
+  unsigned okm = 0;
+  int nt = 0, acc = 0;
+  for (int m = 0; m < total; ++m) {
+    const int it = m / NCH2, ci = m - it * NCH2;
+    if (ci == 0) {
+      acc = it & 1;
+      bool valid;
+      const unsigned rrow = tile_row(it, nt, valid);
+      okm = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        R[i] = __shfl_sync(0xffffffffu, rrow, r) + c4 * 4;
+        okm |= (unsigned)__shfl_sync(0xffffffffu, (int)valid, r) << i;
+      }
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+    }
+    issue(m + RING_SLOTS - 1);
+    const int ch = 2 * ci + half;
+    int co;
+    const unsigned S = chunk_off(nt, ch, co);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (P.skip_scale) {
+      sc = __ldg(reinterpret_cast<const float4*>(P.skip_scale + co) + c4);
+      sh = __ldg(reinterpret_cast<const float4*>(P.skip_shift + co) + c4);
+    }
+    {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
+      const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bv = __ldg(bp + j);
+        sts128(stg_s + (lane * 32 + ((j ^ (lane & 7)) << 2)) * 4,
+             make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w));
+      }
+    }
+    __syncwarp();
+    cp_async_wait<RING_SLOTS - 1>();                    // this chunk's skip rows have landed
+    const uint32_t slot_s = smem_u32(ring) + (m % RING_SLOTS) * 4096;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      float4 a = lds128(slot_s + (i * 32 + lane) * 16);
+      if (P.skip_scale) {               // the skip tensor is a raw conv output: BatchNorm + activation of its layer
+        const float y0 = fmaf(a.x, sc.x, sh.x), y1 = fmaf(a.y, sc.y, sh.y);
+        const float y2 = fmaf(a.z, sc.z, sh.z), y3 = fmaf(a.w, sc.w, sh.w);
+        a.x = y0 > 0.f ? y0 : y0 * sl; a.y = y1 > 0.f ? y1 : y1 * sl;
+        a.z = y2 > 0.f ? y2 : y2 * sl; a.w = y3 > 0.f ? y3 : y3 * sl;
+      }
+      float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
+      val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
+      if (P.round_tf32) {
+        val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w);
+      }
+      if ((okm >> i) & 1) {
+        const size_t o = (size_t)(R[i] + S);
+        *reinterpret_cast<float4*>(P.out + o) = val;
+        if (outb) {
+          __nv_bfloat162 lo2 = __floats2bfloat162_rn(val.x, val.y), hi2 = __floats2bfloat162_rn(val.z, val.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+          *reinterpret_cast<uint2*>(outb + o) = pk;
+        }
+      }
+    }
+    __syncwarp();
+    if (ci == NCH2 - 1) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  cp_async_wait<0>();
+}
+
+template <int BN, bool HALO, bool BF16, bool RING = false>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                     const TcRowsParams P) {
-  using Cfg = RowsCfg<BN, HALO>;
+  using Cfg = RowsCfg<BN, HALO, RING>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);     // plain: stage ring; halo: A ring
@@ -403,6 +553,10 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     float* stg = reinterpret_cast<float*>(smem + Cfg::DATA_BYTES + 512) + (warp - 4) * 1024;   // 4 KB per warp
+    if constexpr (RING) {
+      convt_ring_epilogue<BN>(P, smem + Cfg::RING_OFF + (warp - 4) * RING_SLOTS * 4096, stg, lane, q, half, tmem_base,
+                              tfull_bar, tempty_bar, num_tiles, n_tiles);
+    } else {
     constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
     float cs1[NCH2], cs2[NCH2];
 #pragma unroll
@@ -498,6 +652,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         dst[col * 2 + 1] = had_tiles ? cs2[ci] : 0.f;
       }
     }
+    }   // !RING
   }
   tc_fence_before();
   __syncthreads();
@@ -631,16 +786,16 @@ int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B,
   return 0;
 }
 
-template <int BN, bool HALO, bool BF16>
+template <int BN, bool HALO, bool BF16, bool RING = false>
 static int launch_rows_t(const TcRowsPlan& plan, const TcRowsParams& P, int grid, cudaStream_t s) {
-  using Cfg = RowsCfg<BN, HALO>;
+  using Cfg = RowsCfg<BN, HALO, RING>;
   static bool attr_set = false;
   if (!attr_set) {
-    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, HALO, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RD_CUDA(cudaFuncSetAttribute(gemm_rows_tc_kernel<BN, HALO, BF16, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  gemm_rows_tc_kernel<BN, HALO, BF16><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
+  gemm_rows_tc_kernel<BN, HALO, BF16, RING><<<grid, ROWS_THREADS, Cfg::SMEM_BYTES, s>>>(plan.mapA, plan.mapB, P);
   RD_LAUNCHED();
   return 0;
 }
@@ -685,7 +840,11 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
     }
   } else {
     switch (plan.BN) {
-      case 256: return launch_rows<256, false>(plan, P, grid, s);
+      case 256:
+        // HBM-bound up-convs (short K): skip rows prefetched through per-warp cp.async rings
+        if (e.mode == EPI_CONVT && e.skip && !P.bf16 && P.ntaps * P.cchunks <= 4)
+          return launch_rows_t<256, false, false, true>(plan, P, grid, s);
+        return launch_rows<256, false>(plan, P, grid, s);
       case 128: return launch_rows<128, false>(plan, P, grid, s);
       case 64: return launch_rows<64, false>(plan, P, grid, s);
       case 32: return launch_rows<32, false>(plan, P, grid, s);
