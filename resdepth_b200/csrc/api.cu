@@ -44,6 +44,7 @@ struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottl
   float *w_kn = nullptr, *w_nk = nullptr, *wd_kn = nullptr, *wd_nk = nullptr;
   bool tc = false;     // GEMMs of this block run on tcgen05
   bool bb = false;     // backward GEMMs of this block take bf16 operands (dz, block input, dgrad weights)
+  int wide = 0;        // weight gradient through the wide-N reduce plan: 1 = rows are ci, 2 = rows are co
   TcRowsPlan tc_fwd, tc_dgrad;
   TcReducePlan tc_wgrad;
   // bf16 shadows (uint16 storage): a_b / p_b copies of a / p for consumers' bf16 GEMMs, dgrad weights
@@ -291,7 +292,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
 // TMA descriptors + tile plans of every tcgen05 layer for the current workspace layout
 int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
   const int D = h->depth;
-  auto off = [&](ConvBlock& b) { b.tc = b.bb = false; b.tc_fwd.valid = b.tc_dgrad.valid = b.tc_wgrad.valid = false; };
+  auto off = [&](ConvBlock& b) { b.tc = b.bb = false; b.wide = 0; b.tc_fwd.valid = b.tc_dgrad.valid = b.tc_wgrad.valid = false; };
   for (auto& b : h->enc) off(b);
   off(h->bott);
   for (auto& b : h->dec) off(b);
@@ -306,7 +307,20 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     if (bwd) {
       if (bf && src_b && b.wd_nk_b && tc_rows_eligible(gd, b.Cin, 1) && tc_reduce_eligible(gf, b.Cout, 1)) {
         RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy_b, gd, B, b.wd_nk_b, b.Cin, 1));
-        RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src_b, gf, B, h->gy_b, b.Cout, h->part, h->part_floats, 1));
+        // narrow output tiles (Cout or Cin of 64 / 128) are L2-bound: use the wide-N formulation where it applies
+        static const bool no_wide = getenv("RESDEPTH_NO_WIDE_WGRAD") != nullptr;
+        b.wide = 0;
+        if (!no_wide && b.Cout <= 128 && tc_reduce_wide_eligible(b.Cin, b.Cout, H, H)) {
+          // D[ci][(t,co)] = sum_q x[q][ci] * dz[q - off(t)][co]
+          if (tc_make_reduce_plan_wide(&b.tc_wgrad, src_b, b.Cin, h->gy_b, b.Cout, -1, B, H, H, h->part, h->part_floats) == 0)
+            b.wide = 1;
+        } else if (!no_wide && b.Cin == 64 && tc_reduce_wide_eligible(b.Cout, b.Cin, H, H)) {
+          // D[co][(t,ci)] = sum_p dz[p][co] * x[p + off(t)][ci]
+          if (tc_make_reduce_plan_wide(&b.tc_wgrad, h->gy_b, b.Cout, src_b, b.Cin, +1, B, H, H, h->part, h->part_floats) == 0)
+            b.wide = 2;
+        }
+        if (!b.wide)
+          RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src_b, gf, B, h->gy_b, b.Cout, h->part, h->part_floats, 1));
         b.bb = true;
       } else {
         RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
@@ -828,7 +842,10 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
       }
     }
     ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), s);
-    RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, 9, s));
+    if (b.wide && b.tc_wgrad.valid)
+      RD_TRY(launch_unpack_conv_grad_wide(h->part, S, b.tc_wgrad.p.N, h->G + b.w, b.Cout, b.Cin, b.wide == 1, s));
+    else
+      RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, 9, s));
   }
   if (dgrad_out || dgrad_out_b) {
     Gather g = gather_conv3x3(H, H, b.Cout);

@@ -141,6 +141,7 @@ int launch_pack_conv1x1(const float* w, float* w_copy, float* w_t, int Co, int C
 int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int W, int Kc, int round_tf32,
                         cudaStream_t s);
 int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s);
+int launch_unpack_conv_grad_wide(const float* part, int S, int ldn, float* dw, int Co, int Ci, int by_ci, cudaStream_t s);
 int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s);
 int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s);
 // column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)

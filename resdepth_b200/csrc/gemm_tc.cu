@@ -47,14 +47,14 @@ static constexpr int HALO_SLOT = 41 * 1024;                           // 1024-by
 
 // RING: transposed-conv variant for HBM-bound up-convs (K = C <= 128): a 2-stage operand ring frees 96 KB of shared
 // memory for per-warp cp.async rings that hold the additive-skip rows of the next chunks (see convt_ring_epilogue)
-static constexpr int RING_SLOTS = 3;
+__host__ __device__ constexpr int ring_slots(int BN) { return BN == 256 ? 3 : 4; }   // per-warp 4 KB slots that fit
 template <int BN, bool HALO, bool RING = false>
 struct RowsCfg {
   static constexpr int A_BYTES = HALO ? HALO_SLOT : 128 * 128;       // plain: 128 rows x 32 fp32
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;              // plain variant: one ring of (A, B) stages
   static constexpr int STAGES = RING ? 2 : (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static_assert(!RING || (!HALO && BN == 256), "skip-ring variant: plain 256-column tiles only");
+  static_assert(!RING || (!HALO && (BN == 256 || BN == 128)), "skip-ring variant: plain 256/128-column tiles only");
   static_assert(!HALO || BN <= 128, "halo variant: two sub-tiles x two accumulator stages x BN columns <= 512");
   static constexpr int A_SLOTS = 2;                                  // halo variant: separate rings
   static constexpr int B_SLOTS = (BN == 128) ? 6 : 8;
@@ -66,7 +66,7 @@ struct RowsCfg {
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
   static constexpr int RING_OFF = DATA_BYTES + 512 + 8 * 4096;
   static constexpr int SMEM_BYTES = DATA_BYTES + 1024 /*alignment slack*/ + 512 /*barriers*/ + 8 * 4096 /*epilogue staging*/ +
-                                    (RING ? 8 * RING_SLOTS * 4096 : 0) /*skip rings*/;
+                                    (RING ? 8 * ring_slots(BN) * 4096 : 0) /*skip rings*/;
 };
 
 // Epilogue store of one warp's 32 rows x 32 columns.  After tcgen05.ld a lane owns one ROW (32 consecutive floats of
@@ -251,6 +251,7 @@ __device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8
                                                     int half, uint32_t tmem_base, uint64_t* tfull_bar,
                                                     uint64_t* tempty_bar, int num_tiles, int n_tiles) {
   constexpr int NCH2 = BN / 64;                         // chunks of this warp per tile (even / odd 32-column chunks)
+  constexpr int RING_SLOTS = ring_slots(BN);
   const uint32_t stg_s = smem_u32(stg);
   const int Co = P.N >> 2;
   const int c4 = lane & 7;
@@ -554,7 +555,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int row = q * 32 + lane;
     float* stg = reinterpret_cast<float*>(smem + Cfg::DATA_BYTES + 512) + (warp - 4) * 1024;   // 4 KB per warp
     if constexpr (RING) {
-      convt_ring_epilogue<BN>(P, smem + Cfg::RING_OFF + (warp - 4) * RING_SLOTS * 4096, stg, lane, q, half, tmem_base,
+      convt_ring_epilogue<BN>(P, smem + Cfg::RING_OFF + (warp - 4) * ring_slots(BN) * 4096, stg, lane, q, half, tmem_base,
                               tfull_bar, tempty_bar, num_tiles, n_tiles);
     } else {
     constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
@@ -737,6 +738,11 @@ int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B,
   P.kchunk = 128 / EB;
   P.cchunks = g.C / P.kchunk;
   plan->BN = tc_pick_bn(N);
+  {
+    // HBM-bound up-conv forward (1 tap, N = 4C, K = C <= 128): 128-column tiles leave room for deeper skip rings
+    static const bool ring128 = getenv("RESDEPTH_RING_BN128") != nullptr;
+    if (ring128 && !bf16 && g.ntaps == 1 && N == 4 * g.C && g.C <= 128 && N % 128 == 0) plan->BN = 128;
+  }
   plan->halo = false;
   long long dims[4], strides[3];
   int box[4];
@@ -845,7 +851,10 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
         if (e.mode == EPI_CONVT && e.skip && !P.bf16 && P.ntaps * P.cchunks <= 4)
           return launch_rows_t<256, false, false, true>(plan, P, grid, s);
         return launch_rows<256, false>(plan, P, grid, s);
-      case 128: return launch_rows<128, false>(plan, P, grid, s);
+      case 128:
+        if (e.mode == EPI_CONVT && e.skip && !P.bf16 && P.ntaps * P.cchunks <= 4)
+          return launch_rows_t<128, false, false, true>(plan, P, grid, s);
+        return launch_rows<128, false>(plan, P, grid, s);
       case 64: return launch_rows<64, false>(plan, P, grid, s);
       case 32: return launch_rows<32, false>(plan, P, grid, s);
     }
@@ -1062,8 +1071,8 @@ struct ReduceBCfg {
   static constexpr int BOX_BYTES = KP * 128;
   static constexpr int NB = BN / 64;
   static constexpr int STAGE_BYTES = (2 + NB) * BOX_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : (BN == 192 ? 256 : BN);     // power of two
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
@@ -1103,7 +1112,7 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
   if (warp == 0) {
     const int groups = 2 / P.a_nch;                    // A: two 64-channel chunks per 128-row tile
     const bool is_a = lane < 4;
-    int chunk0 = 0, off1 = 0, off2 = 0;
+    int chunk0 = 0, off1 = 0, off2 = 0, g_slot = 2;
     bool active;
     if (is_a) {
       const int r = m0 + lane * P.a_nch * 64;
@@ -1112,6 +1121,15 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
       chunk0 = P.a_chunk_off[tap] + (active ? (r % P.Ca) / 64 : 0);
       off1 = P.tap_off[tap][1];
       off2 = P.tap_off[tap][2];
+    } else if (P.g_taps > 0) {
+      // wide mode: lane 4+t fetches tap (N tile * g_taps + t) of the N operand at its own pixel shift; a tap
+      // beyond the ninth is fetched far outside the tensor (zero-filled box, columns never read back)
+      const int tl = lane - 4;
+      active = tl < P.g_taps;
+      const int tap = blockIdx.x * P.g_taps + (active ? tl : 0);
+      off1 = tap < 9 ? P.g_off[tap][0] : (1 << 20);
+      off2 = tap < 9 ? P.g_off[tap][1] : 0;
+      g_slot = 2 + tl * P.g_nch;
     } else {
       active = lane == 4;
       chunk0 = n0 / 64;
@@ -1135,7 +1153,7 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
       }
       __syncwarp();
       if (active) {
-        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? lane * P.a_nch : 2) * Cfg::BOX_BYTES;
+        uint8_t* dst = smem + stage * Cfg::STAGE_BYTES + (is_a ? lane * P.a_nch : g_slot) * Cfg::BOX_BYTES;
         tma_load_5d(dst, map, &full_bar[stage], 0, w0 + off1, up2 ? off2 : h0 + off2, up2 ? h0 : b0, chunk0);
       }
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -1291,6 +1309,65 @@ int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, in
   return 0;
 }
 
+bool tc_reduce_wide_eligible(int Cu, int Cs, int H, int W) {
+  return tc_available() && Cu % 128 == 0 && (Cs == 64 || Cs == 128) && H >= 16 && W >= 16;
+}
+
+int tc_make_reduce_plan_wide(TcReducePlan* plan, const void* U, int Cu, const void* S, int Cs, int sign, int B, int H,
+                             int W, float* part, size_t part_floats) {
+  plan->valid = false;
+  if (!tc_reduce_wide_eligible(Cu, Cs, H, W)) return fail("tc wide reduce plan: shape not eligible (Cu=%d Cs=%d)", Cu, Cs);
+  TcReduceParams& P = plan->p;
+  std::memset(&P, 0, sizeof(P));
+  P.bf16 = 1;
+  const int EB = 2, CH = 64, KP = 64;
+  P.g_nch = Cs / 64;
+  P.g_taps = Cs == 64 ? 3 : 2;                          // N tile: 3 x 64 = 192 or 2 x 128 = 256 columns
+  plan->BN = P.g_taps * Cs;
+  const int n_tiles = cdiv(9, P.g_taps);
+  P.Mrows = Cu;
+  P.Ca = Cu;
+  P.N = n_tiles * plan->BN;                             // padded: taps beyond the ninth are zero columns
+  P.ntaps = 1;
+  P.part = part;
+  P.coord_w = 1; P.coord_h = 2; P.coord_b = 3;
+  for (int t = 0; t < 9; ++t) {
+    P.g_off[t][0] = sign * (t % 3 - 1);
+    P.g_off[t][1] = sign * (t / 3 - 1);
+  }
+  P.tw = pow2_floor(W < KP ? W : KP);
+  const int th_max = KP / P.tw;
+  P.th = pow2_floor(H < th_max ? H : th_max);
+  P.tb = KP / (P.tw * P.th);
+  P.tiles_w = cdiv(W, P.tw);
+  P.tiles_h = cdiv(H, P.th);
+  P.tiles_b = cdiv(B, P.tb);
+  P.a_nch = 2;
+  P.a_chunk_off[0] = 0;
+  long long d5[5], s5[4];
+  int b5[5];
+  d5[0] = CH; d5[1] = W; d5[2] = H; d5[3] = B; d5[4] = Cu / CH;
+  s5[0] = (long long)Cu * EB; s5[1] = (long long)W * Cu * EB; s5[2] = (long long)H * W * Cu * EB; s5[3] = 128;
+  b5[0] = CH; b5[1] = P.tw; b5[2] = P.th; b5[3] = P.tb; b5[4] = 2;
+  RD_TRY(tc_encode_map(&plan->mapA, U, 5, d5, s5, b5, 0, EB));
+  d5[4] = Cs / CH;
+  s5[0] = (long long)Cs * EB; s5[1] = (long long)W * Cs * EB; s5[2] = (long long)H * W * Cs * EB;
+  b5[4] = P.g_nch;
+  RD_TRY(tc_encode_map(&plan->mapG, S, 5, d5, s5, b5, 0, EB));
+  const int total_boxes = P.tiles_w * P.tiles_h * P.tiles_b;
+  const int tiles = (Cu / 128) * n_tiles;
+  int Sp = 148 / tiles;
+  if (Sp > total_boxes / 8) Sp = total_boxes / 8;
+  if (Sp < 1) Sp = 1;
+  const size_t per = (size_t)P.Mrows * P.N;
+  while (Sp > 1 && (size_t)Sp * per > part_floats) --Sp;
+  if ((size_t)Sp * per > part_floats) return fail("tc wide reduce plan: partial buffer too small (%zu floats needed)", per);
+  P.boxes_per_split = cdiv(total_boxes, Sp);
+  plan->splits = cdiv(total_boxes, P.boxes_per_split);
+  plan->valid = true;
+  return 0;
+}
+
 template <int BN>
 static int launch_reduce(const TcReducePlan& plan, cudaStream_t s) {
   using Cfg = ReduceCfg<BN>;
@@ -1333,6 +1410,7 @@ int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s) {
   if (plan.p.bf16) {
     switch (plan.BN) {
       case 256: return launch_reduce_bf16<256>(plan, s);
+      case 192: return launch_reduce_bf16<192>(plan, s);
       case 128: return launch_reduce_bf16<128>(plan, s);
       case 64: return launch_reduce_bf16<64>(plan, s);
     }

@@ -56,6 +56,12 @@ struct TcReduceParams {
   int a_nch;
   int a_chunk_off[9];    // per tap: chunk offset of the tap inside the A tensor map (2x2 gather: (b*C)/32)
   int bf16;              // bf16 operands (64-channel chunks, kind::f16); always uses grouped loads
+  // "wide" 3x3 weight-gradient mode (bf16 only): the M operand is an UNSHIFTED tensor (128-channel tiles), the N
+  // tile is g_taps taps x Cs channels of the other tensor, each tap fetched at its own pixel shift -- a 128 x 192/256
+  // output tile per CTA instead of 128 x 64/128 (the narrow tiles are L2-bandwidth-bound)
+  int g_taps;            // taps per N tile (0: normal mode)
+  int g_nch;             // 64-channel chunks per tap (Cs / 64)
+  int g_off[9][2];       // per tap: (w, h) shift of the N operand
 };
 
 struct TcReducePlan {
@@ -71,6 +77,11 @@ bool tc_reduce_eligible(const Gather& g, int N, int bf16 = 0);
 int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, int B, const void* G, int N,
                         float* part, size_t part_floats, int bf16 = 0);
 int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s);
+// wide 3x3 weight gradient (bf16): D[cu][(tap, cs)] = sum_p U[p][cu] * S[p + sign*off(tap)][cs]; U, S: bf16 NHWC
+// [B,H,W,Cu] / [B,H,W,Cs], Cu % 128 == 0, Cs in {64, 128}.  part: [splits][Cu][ntiles*BN] (see plan->p.N)
+bool tc_reduce_wide_eligible(int Cu, int Cs, int H, int W);
+int tc_make_reduce_plan_wide(TcReducePlan* plan, const void* U, int Cu, const void* S, int Cs, int sign, int B, int H,
+                             int W, float* part, size_t part_floats);
 
 bool tc_rows_eligible(const Gather& g, int N, int bf16 = 0);
 int tc_pick_bn(int N);

@@ -517,13 +517,22 @@ loss_partial_kernel(const float* __restrict__ y_pred, const float* __restrict__ 
   if (threadIdx.x == 0) { part[blockIdx.x * 2] = r1[0]; part[blockIdx.x * 2 + 1] = r2[0]; }
 }
 
-__global__ void loss_finalize_kernel(const double* __restrict__ part, int nparts, float* __restrict__ loss_out,
-                                     float* __restrict__ inv_count) {
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(256)
+loss_finalize_kernel(const double* __restrict__ part, int nparts, float* __restrict__ loss_out,
+                     float* __restrict__ inv_count) {
+  __shared__ double ra[256], rm[256];
   double a = 0.0, m = 0.0;
-  for (int i = 0; i < nparts; ++i) { a += part[i * 2]; m += part[i * 2 + 1]; }
-  loss_out[0] = (float)(a / m);
-  inv_count[0] = (float)(1.0 / m);
+  for (int i = threadIdx.x; i < nparts; i += 256) { a += part[i * 2]; m += part[i * 2 + 1]; }
+  ra[threadIdx.x] = a; rm[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {                  // fixed-order tree: deterministic
+    if (threadIdx.x < o) { ra[threadIdx.x] += ra[threadIdx.x + o]; rm[threadIdx.x] += rm[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    loss_out[0] = (float)(ra[0] / rm[0]);
+    inv_count[0] = (float)(1.0 / rm[0]);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -552,7 +561,7 @@ int launch_loss(const float* y_pred, const float* target, const uint8_t* mask, c
   float* inv_count = scratch + 2 * 2 * nb;
   loss_partial_kernel<<<nb, 256, 0, s>>>(y_pred, target, mask, mean, std, part, B, HW);
   RD_LAUNCHED();
-  loss_finalize_kernel<<<1, 32, 0, s>>>(part, nb, loss_out, inv_count);
+  loss_finalize_kernel<<<1, 256, 0, s>>>(part, nb, loss_out, inv_count);
   RD_LAUNCHED();
   if (dy_out) {
     loss_grad_kernel<<<ew_grid((long long)B * HW), 256, 0, s>>>(y_pred, target, mask, mean, std, inv_count, dy_out, B,
@@ -748,6 +757,30 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ part, int S
 }
 int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s) {
   unpack_conv3x3_grad_kernel<<<ew_grid((long long)Co * Ci * ntaps), 256, 0, s>>>(part, S, dw, Co, Ci, ntaps);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// wide weight-gradient layouts (tc_make_reduce_plan_wide), summed over S -> dW OIHW:
+//   by_ci != 0: part [S][ci][(t, co)] (row stride ldn)     by_ci == 0: part [S][co][(t, ci)]
+__global__ void unpack_conv3x3_grad_wide_kernel(const float* __restrict__ part, int S, int ldn, float* __restrict__ dw,
+                                                int Co, int Ci, int by_ci) {
+  const int Cu = by_ci ? Ci : Co, Cs = by_ci ? Co : Ci;           // row channels, column channels per tap
+  const long long total = (long long)Cu * 9 * Cs;
+  const size_t split = (size_t)Cu * ldn;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += gridDim.x * 256LL) {
+    const int cs = (int)(i % Cs);
+    const int t = (int)((i / Cs) % 9);
+    const int cu = (int)(i / (9LL * Cs));
+    const size_t src = (size_t)cu * ldn + (size_t)t * Cs + cs;
+    float a = 0.f;
+    for (int sp = 0; sp < S; ++sp) a += part[(size_t)sp * split + src];
+    const int co = by_ci ? cs : cu, ci = by_ci ? cu : cs;
+    dw[((size_t)co * Ci + ci) * 9 + t] = a;
+  }
+}
+int launch_unpack_conv_grad_wide(const float* part, int S, int ldn, float* dw, int Co, int Ci, int by_ci, cudaStream_t s) {
+  unpack_conv3x3_grad_wide_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(part, S, ldn, dw, Co, Ci, by_ci);
   RD_LAUNCHED();
   return 0;
 }

@@ -65,6 +65,11 @@ class _NullWriter:
     def close(self): pass
 
 
+class _StagedBatch(dict):
+    """A batch whose tensors already live on the device; ``ready`` = CUDA event recorded after its H2D copies."""
+    ready = None
+
+
 class Trainer(object):
     def __init__(self, args):
         self.config = args
@@ -161,6 +166,42 @@ class Trainer(object):
             t = t.pin_memory()
         return t.to(self.device, dtype=dtype, non_blocking=True)
 
+    def _stage_batch(self, batch):
+        """Enqueue the H2D copies of one host batch on the copy stream and return the device-resident batch
+        (``_StagedBatch``) with the event that marks the copies complete."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        staged = _StagedBatch(batch)
+        with torch.cuda.stream(self._copy_stream):
+            staged['input'] = self._to_device(batch['input'], torch.float32)
+            staged['target'] = self._to_device(batch['target'], torch.float32)
+            staged['loss_mask'] = self._to_device(batch['loss_mask'])
+            staged['dsm_mean'] = self._to_device(torch.flatten(batch['dsm_mean']), torch.float32)
+            staged['dsm_std'] = self._to_device(torch.flatten(batch['dsm_std']), torch.float32)
+            staged.ready = torch.cuda.Event()
+            staged.ready.record(self._copy_stream)
+        for k in ('input', 'target', 'loss_mask', 'dsm_mean', 'dsm_std'):
+            staged[k].record_stream(main)
+        return staged
+
+    def _prefetched(self, loader):
+        """Iterate ``loader`` one batch ahead: the H2D copies of batch i+1 are enqueued (copy stream) before the
+        step of batch i is launched, so they overlap its compute.  Same batches, same order as the plain loop of
+        the reference (lib/Trainer.py:212-213)."""
+        it = iter(loader)
+        try:
+            nxt = self._stage_batch(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur = nxt
+            try:
+                nxt = self._stage_batch(next(it))
+            except StopIteration:
+                nxt = None
+            yield cur
+
     def _compute_denormalized_loss(self, y_pred, y, loss_mask, mean, std, want_grad=False):
         """Fused masked, de-normalised L1 (lib/Trainer.py:87-100).  Returns (loss tensor [1], dy or None)."""
         B, _, T, _ = y_pred.shape
@@ -220,6 +261,12 @@ class Trainer(object):
         train = phase == 'train'
         self.model.train() if train else self.model.eval()
 
+        if isinstance(batch, _StagedBatch):                 # copies already in flight (``_prefetched``)
+            torch.cuda.current_stream(self.device).wait_event(batch.ready)
+            loss = self.device_step(batch['input'], batch['target'], batch['loss_mask'], batch['dsm_mean'],
+                                    batch['dsm_std'], train)
+            return {'MAE_metric': float(loss.item())}
+
         x, y, loss_mask = self._extract_inputs_outputs_loss_masks(batch)
         # the input tiles are needed first: copy them on the compute stream; target / mask / normalisation constants
         # are only needed by the loss, so their copies ride a side stream and overlap the forward pass
@@ -267,7 +314,7 @@ class Trainer(object):
         for param in self.model.parameters():
             param.grad = None
 
-        for c_iter, batch in enumerate(self.loader[phase]):
+        for c_iter, batch in enumerate(self._prefetched(self.loader[phase])):
             stats = self.inference_one_batch(batch, phase)
 
             if phase == 'train':
