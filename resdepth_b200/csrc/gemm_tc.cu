@@ -1427,4 +1427,233 @@ int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s) {
 
 bool tc_available() { return encode_fn() != nullptr; }
 
+// ---------------------------------------------------------------------------------------------
+// First encoder conv (Cin <= 3: K = 9*Cin <= 27, padded to 32) on tcgen05 with a SOFTWARE im2col producer.
+// The layer is HBM-bound (writes 64 channels per pixel, reads 3) but on CUDA cores its 1728 FMAs per pixel made it
+// issue-bound at 2.5x the HBM time.  fp32 accuracy is kept with the 3xTF32 split: x = xh + xl, w = wh + wl (each
+// exactly representable in TF32), D = xh*wh + xl*wh + xh*wl (the dropped xl*wl term is ~2^-22 relative).
+//   warps 0-3: builders -- thread r gathers the 27 input values of pixel r of the tile straight from the NCHW
+//              input (neighbouring threads = neighbouring pixels: coalesced, 9x L1 reuse), splits them and writes
+//              row r of the K-major SWIZZLE_128B operand tiles A_hi / A_lo (generic stores + proxy fence)
+//   warp 4   : TMEM allocator, MMA issuer (12 tcgen05.mma of K = 8 per 128-pixel tile)
+//   warps 5-8: epilogue (TMEM lane quarter = warp % 4... see q below): z rows through the transposing staging
+//              buffer, BatchNorm column sums kept in registers across the CTA's tiles
+// ---------------------------------------------------------------------------------------------
+static constexpr int FIRST_THREADS = 416;         // 4 builder warps, MMA warp, 8 epilogue warps
+static constexpr int FIRST_STAGES = 3;
+template <int N>
+struct FirstCfg {
+  static constexpr int A_BYTES = 128 * 128;                 // one operand tile: 128 rows x 32 fp32
+  static constexpr int STAGE_BYTES = 2 * A_BYTES;           // hi + lo
+  static constexpr int B_BYTES = N * 128;
+  static constexpr int B_OFF = FIRST_STAGES * STAGE_BYTES;  // B_hi, then B_lo
+  static constexpr int STG_OFF = B_OFF + 2 * B_BYTES;       // 8 x 4 KB epilogue staging
+  static constexpr int BAR_OFF = STG_OFF + 8 * 4096;
+  static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
+  static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
+};
+
+// element (row, k) of a K-major SWIZZLE_128B tile: 8-row groups of 1024 bytes, 16-byte chunks XOR-ed with row % 8
+__device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int N>
+__global__ void __launch_bounds__(FIRST_THREADS, 1)
+conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z,
+                     float* __restrict__ partials, int B, int Cin, int H, int W) {
+  using Cfg = FirstCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+  uint64_t* a_empty = a_full + FIRST_STAGES;
+  uint64_t* t_full = a_empty + FIRST_STAGES;
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = Cin * 9;
+  const long long npix = (long long)B * H * W;
+  const int num_tiles = (int)((npix + 127) / 128);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < FIRST_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  // weights [N][K] (OIHW flattening) -> B_hi / B_lo operand tiles, zero-padded to K = 32
+  {
+    const uint32_t bh = smem_u32(smem + Cfg::B_OFF), bl = bh + Cfg::B_BYTES;
+    for (int i = threadIdx.x; i < N * 8; i += FIRST_THREADS) {
+      const int n = i >> 3, c = i & 7;
+      float hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = c * 4 + e;
+        const float v = k < K ? w[(size_t)n * K + k] : 0.f;
+        hi[e] = tf32_round(v);
+        lo[e] = tf32_round(v - hi[e]);
+      }
+      sts128(bh + sw128_off(n, c), make_float4(hi[0], hi[1], hi[2], hi[3]));
+      sts128(bl + sw128_off(n, c), make_float4(lo[0], lo[1], lo[2], lo[3]));
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===== builders =====
+    const int r = threadIdx.x;                              // row of the tile
+    int stage = 0;
+    uint32_t phase = 0;
+    auto gather = [&](int tile, float (&v)[32]) {           // the 27 (padded to 32) input values of this thread's pixel
+      const long long p = (long long)tile * 128 + r;
+      const bool valid = tile < num_tiles && p < npix;
+      const unsigned pu = valid ? (unsigned)p : 0u;         // launcher guarantees npix < 2^32
+      const unsigned t_ = pu / (unsigned)W;
+      const int wq = (int)(pu - t_ * (unsigned)W);
+      const int b = (int)(t_ / (unsigned)H);
+      const int hq = (int)(t_ - (unsigned)b * (unsigned)H);
+      const float* xb = x + (size_t)b * Cin * H * W;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const int ci = k / 9, rs = k - ci * 9;
+        const int dr = rs / 3 - 1, ds = rs - (rs / 3) * 3 - 1;
+        const int hh = hq + dr, ww = wq + ds;
+        const bool ok = valid && k < K && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
+        v[k] = ok ? __ldg(xb + ((size_t)ci * H + hh) * W + ww) : 0.f;
+      }
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      float v[32];
+      gather(tile, v);
+      mbar_wait(&a_empty[stage], phase ^ 1);
+      const uint32_t ah = smem_u32(smem + stage * Cfg::STAGE_BYTES), al = ah + Cfg::A_BYTES;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[e] = tf32_round(v[c * 4 + e]);
+          lo[e] = tf32_round(v[c * 4 + e] - hi[e]);
+        }
+        sts128(ah + sw128_off(r, c), make_float4(hi[0], hi[1], hi[2], hi[3]));
+        sts128(al + sw128_off(r, c), make_float4(lo[0], lo[1], lo[2], lo[3]));
+      }
+      fence_proxy_async();                                  // generic-proxy stores -> visible to tcgen05.mma
+      mbar_arrive(&a_full[stage]);
+      if (++stage == FIRST_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = idesc_tf32(128, N, 0, 0);
+    const uint32_t bh = smem_u32(smem + Cfg::B_OFF), bl = bh + Cfg::B_BYTES;
+    const uint64_t dbh = smem_desc_sw128(bh, 16, 1024), dbl = smem_desc_sw128(bl, 16, 1024);
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1);
+      mbar_wait(&a_full[stage], phase);
+      tc_fence_after();
+      const uint32_t ah = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+      const uint64_t dah = smem_desc_sw128(ah, 16, 1024), dal = smem_desc_sw128(ah + Cfg::A_BYTES, 16, 1024);
+      const uint32_t d_tmem = tmem_base + acc * N;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32(d_tmem, dah + (uint64_t)(k * 2), dbh + (uint64_t)(k * 2), idesc, k != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32(d_tmem, dal + (uint64_t)(k * 2), dbh + (uint64_t)(k * 2), idesc, 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_tf32(d_tmem, dah + (uint64_t)(k * 2), dbl + (uint64_t)(k * 2), idesc, 1);
+        tc_commit(&a_empty[stage]);
+        tc_commit(&t_full[acc]);
+      }
+      __syncwarp();
+      if (++stage == FIRST_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue: warps 5..12; a warp may only read the TMEM lane quarter warp % 4, the two warps of a quarter
+    // take the even / odd 32-column chunk.  BatchNorm sums: every lane keeps per-column running sums of ITS rows
+    // over all tiles of the CTA (64 registers); the cross-lane reduction happens once, after the last tile =====
+    const int q = warp & 3;
+    const int half = (warp - 5) >> 2;
+    const int row = q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + (warp - 5) * 1024;
+    constexpr int NCH = N / 32;
+    static_assert(NCH <= 2, "one 32-column chunk per epilogue warp");
+    const bool has_chunk = half < NCH;
+    float s1[32], s2[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s1[j] = s2[j] = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const long long p = (long long)tile * 128 + row;
+      const bool valid = p < npix;
+      mbar_wait(&t_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (has_chunk) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + half * 32, v);
+        if (partials && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+        }
+        warp_store_rows(stg, lane, v, z, p * N + half * 32, valid, nullptr, 0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[acc]);
+    }
+    if (partials && has_chunk) {
+      const float c1 = warp_colsum32(s1, lane), c2 = warp_colsum32(s2, lane);
+      float* dst = partials + (size_t)(blockIdx.x * 4 + q) * N * 2;
+      dst[(half * 32 + lane) * 2 + 0] = c1;
+      dst[(half * 32 + lane) * 2 + 1] = c2;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+bool conv_first_tc_eligible(int Cin, int Cout) { return tc_available() && Cin * 9 <= 32 && (Cout == 32 || Cout == 64); }
+
+template <int N>
+static int launch_first_t(const float* x, const float* w, float* z, float* partials, int B, int Cin, int H, int W,
+                          int grid, cudaStream_t s) {
+  using Cfg = FirstCfg<N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RD_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  conv_first_tc_kernel<N><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(x, w, z, partials, B, Cin, H, W);
+  RD_LAUNCHED();
+  return 0;
+}
+
+int launch_conv_first_tc(const float* x, const float* w, float* z, float* partials, int* n_partials, int B, int Cin,
+                         int H, int W, int Cout, cudaStream_t s) {
+  if (!conv_first_tc_eligible(Cin, Cout)) return fail("conv_first_tc: unsupported Cin=%d Cout=%d", Cin, Cout);
+  const long long npix = (long long)B * H * W;
+  if (npix >= (1LL << 32)) return fail("conv_first_tc: more than 2^32 pixels");
+  const long long tiles = (npix + 127) / 128;
+  const int grid = tiles < 148 ? (int)tiles : 148;
+  if (n_partials) *n_partials = grid * 4;
+  switch (Cout) {
+    case 32: return launch_first_t<32>(x, w, z, partials, B, Cin, H, W, grid, s);
+    case 64: return launch_first_t<64>(x, w, z, partials, B, Cin, H, W, grid, s);
+  }
+  return fail("conv_first_tc: unsupported Cout=%d", Cout);
+}
+
+
 }  // namespace rd

@@ -83,6 +83,12 @@ bool tc_reduce_wide_eligible(int Cu, int Cs, int H, int W);
 int tc_make_reduce_plan_wide(TcReducePlan* plan, const void* U, int Cu, const void* S, int Cs, int sign, int B, int H,
                              int W, float* part, size_t part_floats);
 
+// first encoder conv (Cin <= 3) on tcgen05: software im2col producer, 3xTF32 split (fp32-equivalent accuracy);
+// x NCHW, w OIHW, z NHWC; partials: [n_partials][Cout][2] BatchNorm column sums (may be null)
+bool conv_first_tc_eligible(int Cin, int Cout);
+int launch_conv_first_tc(const float* x, const float* w, float* z, float* partials, int* n_partials, int B, int Cin,
+                         int H, int W, int Cout, cudaStream_t s);
+
 bool tc_rows_eligible(const Gather& g, int N, int bf16 = 0);
 int tc_pick_bn(int N);
 // strides in BYTES; elem_bytes 4 (fp32) or 2 (bf16)
