@@ -125,6 +125,26 @@ int rd_make_tiles(const float* dsm_in, const float* dsm_gt, const float* orthos,
                   float ortho_mean_in, float* input, float* target, uint8_t* mask, float* dsm_mean_out,
                   float* scratch, void* stream);
 
+/* compute_residuals (lib/evaluation.py:11-37) on device arrays of n elements: a pixel is valid unless
+ * gt == nodata, raster == nodata or (mask_gt != NULL and mask_gt == 0); res = raster - gt (float64; the float32
+ * difference when both inputs are float32, as numpy would).  raster_f64 / gt_f64: element type of the inputs
+ * (0 = float32, 1 = float64).  Outputs: res float64 [n] (0 where invalid), valid uint8 [n]. */
+int rd_residuals(const void* raster, int raster_f64, const void* gt, int gt_f64, const uint8_t* mask_gt, int64_t n,
+                 double nodata, double* res, uint8_t* valid, void* stream);
+
+/* get_statistics (lib/evaluation.py:51-131) over the valid residuals: out16 (HOST memory) = count_total, diff_max,
+ * diff_min, MAE, RMSE, absolute_median, median, NMAD, then count_total, MAE, RMSE, absolute_median, median, NMAD of
+ * the residuals truncated to [-threshold, threshold] (lib/evaluation.py:40-48; NaN when threshold <= 0); medians
+ * are exact order statistics (radix select), even counts average the two middle values like np.ma.median.
+ * Synchronises `stream`. */
+int rd_residual_stats(const double* res, const uint8_t* valid, int64_t n, double threshold, double* out16, void* stream);
+
+/* Per-tile part of compute_local_dsm_std_per_centered_patch (lib/utils.py:111-158): for each of the n tiles at
+ * pos int32 [n][2] = (y, x) of the device raster dsm [rows][cols], the standard deviation of the valid heights
+ * around the tile's own mean, sqrt(sum (x - mean)^2 / (count - 1)), in float64 -> stds [n] (device). */
+int rd_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n, int tile, float nodata, double* stds,
+                 void* stream);
+
 /* Per-category device timing (CUDA events on the launching stream around the library's own launches).
  * rd_profile_enable(h, 1) starts recording; rd_profile_collect synchronises the recorded events and folds
  * them into per-category totals; rd_profile_read returns one category: total milliseconds, algorithmic

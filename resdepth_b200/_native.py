@@ -23,7 +23,8 @@ EXPORTED_SYMBOLS = (
     'rd_param_arena_size', 'rd_num_buffers', 'rd_buffer_info', 'rd_buffer_arena_size', 'rd_bind', 'rd_reserve',
     'rd_workspace_bytes', 'rd_forward', 'rd_loss', 'rd_backward', 'rd_adam_step', 'rd_sgd_step',
     'rd_blend_accumulate', 'rd_launch_count', 'rd_math_mode_name', 'rd_profile_enable', 'rd_profile_collect',
-    'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce', 'rd_make_tiles',
+    'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce', 'rd_make_tiles', 'rd_residuals', 'rd_residual_stats',
+    'rd_tile_stds',
 )
 PROF_NUM = 18                                           # RD_PROF_NUM
 
@@ -40,7 +41,7 @@ def library_path() -> str:
 
 
 def _declare(lib):
-    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     lib.rd_abi_version.restype = i32
     lib.rd_abi_version.argtypes = []
     lib.rd_last_error.restype = C.c_char_p
@@ -93,6 +94,12 @@ def _declare(lib):
     lib.rd_make_tiles.restype = i32
     lib.rd_make_tiles.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, i32, i32, f32, f32, f32, f32, f32,
                                   vp, vp, vp, vp, vp, vp]
+    lib.rd_residuals.restype = i32
+    lib.rd_residuals.argtypes = [vp, i32, vp, i32, vp, i64, f64, vp, vp, vp]
+    lib.rd_residual_stats.restype = i32
+    lib.rd_residual_stats.argtypes = [vp, vp, i64, f64, vp, vp]
+    lib.rd_tile_stds.restype = i32
+    lib.rd_tile_stds.argtypes = [vp, i32, i32, vp, i32, i32, f32, vp, vp]
     lib.rd_launch_count.restype = i64
     lib.rd_launch_count.argtypes = [i32]
     lib.rd_math_mode_name.restype = C.c_char_p
@@ -217,6 +224,20 @@ def debug_rows(engine, kind, src, batch, h, w, c, w_kn, w_nk, n, out, stream):
 def debug_reduce(engine, kind, src, batch, h, w, c, g, n, out, scratch, scratch_floats, stream):
     check(lib().rd_debug_reduce(engine, kind, src, batch, h, w, c, g, n, out, scratch, scratch_floats, stream),
           'rd_debug_reduce')
+
+
+def residuals(*args):
+    check(lib().rd_residuals(*args), 'rd_residuals')
+
+
+def residual_stats(res_ptr, valid_ptr, n, threshold, stream):
+    out = (C.c_double * 16)()
+    check(lib().rd_residual_stats(res_ptr, valid_ptr, n, float(threshold), out, stream), 'rd_residual_stats')
+    return list(out)
+
+
+def tile_stds(*args):
+    check(lib().rd_tile_stds(*args), 'rd_tile_stds')
 
 
 def make_tiles(*args):

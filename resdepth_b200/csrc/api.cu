@@ -1054,6 +1054,24 @@ int rd_debug_reduce(int engine, int kind, const float* src, int batch, int hh, i
   return 0;
 }
 
+int rd_residuals(const void* raster, int raster_f64, const void* gt, int gt_f64, const uint8_t* mask_gt, int64_t n,
+                 double nodata, double* res, uint8_t* valid, void* stream) {
+  if (!raster || !gt || !res || !valid || n < 0) return fail("rd_residuals: bad argument");
+  return launch_residuals(raster, raster_f64, gt, gt_f64, mask_gt, n, nodata, res, valid,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_residual_stats(const double* res, const uint8_t* valid, int64_t n, double threshold, double* out16, void* stream) {
+  if (!res || !valid || !out16 || n < 0) return fail("rd_residual_stats: bad argument");
+  return residual_statistics(res, valid, n, threshold, out16, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n, int tile, float nodata, double* stds,
+                 void* stream) {
+  if (!dsm || !pos || !stds || n < 0 || tile <= 0 || tile > rows || tile > cols) return fail("rd_tile_stds: bad argument");
+  return launch_tile_stds(dsm, rows, cols, pos, n, tile, nodata, stds, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int rd_profile_enable(rd_handle* h, int on) {
   if (!h) return fail("rd_profile_enable: null handle");
   RD_CUDA(cudaSetDevice(h->device));

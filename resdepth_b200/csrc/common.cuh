@@ -142,6 +142,13 @@ int launch_im2col_first(const float* x, float* xcol, int B, int Cin, int H, int 
                         cudaStream_t s);
 int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s);
 int launch_unpack_conv_grad_wide(const float* part, int S, int ldn, float* dw, int Co, int Ci, int by_ci, cudaStream_t s);
+// ---- evaluation-side kernels (kernels_stats.cu) ---------------------------------------------------
+int launch_residuals(const void* raster, int raster_f64, const void* gt, int gt_f64, const uint8_t* mask_gt, long long n,
+                     double nodata, double* res, uint8_t* valid, cudaStream_t s);
+int residual_statistics(const double* res, const uint8_t* valid, long long n, double threshold, double* out16,
+                        cudaStream_t s);
+int launch_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n, int tile, float nodata,
+                     double* stds, cudaStream_t s);
 int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s);
 int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s);
 // column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)

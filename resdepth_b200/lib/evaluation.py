@@ -65,3 +65,91 @@ def predict_linear_blend(dataloader, model):
             y_pred = model(x)
             blend_tiles_into(raster, y_pred, mean, std, geom_d, tile_size, stride)
     return raster.cpu().numpy()
+
+
+# -------------------------------------------------------------------------------------------------
+# Residual statistics on the device (reference lib/evaluation.py:11-131)
+# -------------------------------------------------------------------------------------------------
+class _Stats(dict):
+    """Attribute dictionary with the keys of the reference's EasyDict result."""
+    __getattr__ = dict.__getitem__
+    __setattr__ = dict.__setitem__
+
+
+class DeviceResiduals:
+    """Residual errors ``raster - raster_gt`` held on the device: ``data`` float64, ``valid`` bool (True = unmasked).
+    Stands in for the ``np.ma`` array the reference's ``compute_residuals`` returns; ``to_masked_array()`` gives
+    exactly that array, ``compressed()`` its valid values, slicing returns a view-like ``DeviceResiduals``."""
+
+    def __init__(self, data: torch.Tensor, valid: torch.Tensor):
+        self.data, self.valid = data, valid
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape)
+
+    def __getitem__(self, idx):
+        return DeviceResiduals(self.data[idx], self.valid[idx])
+
+    def to_masked_array(self):
+        return np.ma.masked_array(self.data.cpu().numpy(), mask=~self.valid.cpu().numpy())
+
+    def compressed(self):
+        return self.data[self.valid].cpu().numpy()
+
+
+def _device_array(a, device, allow=(torch.float32, torch.float64)):
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype not in allow:
+        t = t.to(torch.float64)
+    return t.to(device).contiguous()
+
+
+def compute_residuals(raster, raster_gt, nodata, mask_gt=None) -> DeviceResiduals:
+    """Same arguments and masking rules as the reference (numpy arrays or CUDA tensors); the result stays on the
+    device.  A positive error means the predicted height is larger than the reference value."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('resdepth_b200: compute_residuals needs a CUDA device (no CPU fallback)')
+    device = raster.device if isinstance(raster, torch.Tensor) and raster.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    r = _device_array(raster, device)
+    g = _device_array(raster_gt, device)
+    if r.shape != g.shape:
+        raise ValueError('raster and raster_gt must have the same shape')
+    m = None
+    if mask_gt is not None:
+        m = mask_gt if isinstance(mask_gt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(mask_gt))
+        m = (m != 0).to(device).contiguous().view(torch.uint8)
+    res = torch.empty(r.shape, dtype=torch.float64, device=device)
+    valid = torch.empty(r.shape, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _native.residuals(r.data_ptr(), int(r.dtype == torch.float64), g.data_ptr(), int(g.dtype == torch.float64),
+                          m.data_ptr() if m is not None else None, r.numel(), float(nodata), res.data_ptr(),
+                          valid.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    return DeviceResiduals(res, valid.view(torch.bool))
+
+
+def get_statistics(residuals_masked, residual_threshold=None):
+    """Evaluation metrics of the reference's ``get_statistics`` (same keys, same definitions -- including NMAD around
+    the median of the absolute residuals) computed by ``rd_residual_stats``.  Accepts a ``DeviceResiduals`` or a numpy
+    masked array."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('resdepth_b200: get_statistics needs a CUDA device (no CPU fallback)')
+    if isinstance(residuals_masked, DeviceResiduals):
+        data, valid = residuals_masked.data.contiguous(), residuals_masked.valid.contiguous()
+    else:
+        device = torch.device('cuda', torch.cuda.current_device())
+        ma = np.ma.asarray(residuals_masked)
+        data = torch.from_numpy(np.ascontiguousarray(np.ma.filled(ma.astype(np.float64), 0.0))).to(device)
+        valid = torch.from_numpy(np.ascontiguousarray(~np.ma.getmaskarray(ma))).to(device)
+    if data.dtype != torch.float64:
+        data = data.double()
+    with torch.cuda.device(data.device):
+        o = _native.residual_stats(data.data_ptr(), valid.view(torch.uint8).data_ptr(), data.numel(),
+                                   float(residual_threshold) if residual_threshold else 0.0,
+                                   torch.cuda.current_stream().cuda_stream)
+    stats = _Stats(truncation=True if residual_threshold else False, count_total=o[0], diff_max=o[1], diff_min=o[2],
+                   MAE=o[3], RMSE=o[4], absolute_median=o[5], median=o[6], NMAD=o[7])
+    if residual_threshold:
+        stats['truncated'] = _Stats(count_total=o[8], threshold=residual_threshold, MAE=o[9], RMSE=o[10],
+                                    absolute_median=o[11], median=o[12], NMAD=o[13])
+    return stats
