@@ -674,7 +674,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
       const double px = (double)B * H * H;
       ProfScope ps(h, RD_PROF_FIRST_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
       static const bool no_first_tc = getenv("RESDEPTH_NO_FIRST_TC") != nullptr;
-      if (h->tf32() && !no_first_tc && conv_first_tc_eligible(b.Cin, b.Cout))
+      if (h->tf32() && !no_first_tc && conv_first_tc_shape_ok(b.Cin, b.Cout, H, H))
         RD_TRY(launch_conv_first_tc(x, h->P + b.w, b.z, stats ? h->partials : nullptr, &np, B, b.Cin, H, H, b.Cout, s));
       else
         RD_TRY(launch_conv_first_fwd(x, h->P + b.w, b.z, stats ? h->partials : nullptr, &np, B, b.Cin, H, H, b.Cout, s));

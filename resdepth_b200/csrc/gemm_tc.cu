@@ -698,7 +698,8 @@ int tc_encode_map(CUtensorMap* map, const void* base, int rank, const long long*
   CUresult r = fn(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                   (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  swizzle_atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                      : (swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -1432,14 +1433,19 @@ bool tc_available() { return encode_fn() != nullptr; }
 // The layer is HBM-bound (writes 64 channels per pixel, reads 3) but on CUDA cores its 1728 FMAs per pixel made it
 // issue-bound at 2.5x the HBM time.  fp32 accuracy is kept with the 3xTF32 split: x = xh + xl, w = wh + wl (each
 // exactly representable in TF32), D = xh*wh + xl*wh + xh*wl (the dropped xl*wl term is ~2^-22 relative).
-//   warps 0-3: builders -- thread r gathers the 27 input values of pixel r of the tile straight from the NCHW
-//              input (neighbouring threads = neighbouring pixels: coalesced, 9x L1 reuse), splits them and writes
-//              row r of the K-major SWIZZLE_128B operand tiles A_hi / A_lo (generic stores + proxy fence)
+//   warp 13  : TMA producer -- the (tw+2) x (th+2) x Cin halo patch of every 128-pixel tile (tw x th pixels of one
+//              image) straight from the NCHW input, FIRST_XS patches ahead; out-of-image coordinates are zero-filled
+//              by the TMA unit = the convolution padding (a first version gathered the 27 values with global loads
+//              in the builder threads and was bound by one DRAM round trip per tile: ncu long-scoreboard stalls)
+//   warps 0-3: builders -- thread r reads the 27 input values of pixel r from the patch in shared memory, splits
+//              them and writes row r of the K-major SWIZZLE_128B operand tiles A_hi / A_lo (+ proxy fence)
 //   warp 4   : TMEM allocator, MMA issuer (12 tcgen05.mma of K = 8 per 128-pixel tile)
 //   warps 5-8: epilogue (TMEM lane quarter = warp % 4... see q below): z rows through the transposing staging
 //              buffer, BatchNorm column sums kept in registers across the CTA's tiles
 // ---------------------------------------------------------------------------------------------
-static constexpr int FIRST_THREADS = 416;         // 4 builder warps, MMA warp, 8 epilogue warps
+static constexpr int FIRST_THREADS = 448;         // 4 builder warps, MMA warp, 8 epilogue warps, input-TMA warp
+static constexpr int FIRST_XS = 4;                // input halo patches in flight
+static constexpr int FIRST_X_BYTES = 8192;        // slot of one halo patch (Cin x (th+2) x (tw+8) fp32 <= 4896 B)
 static constexpr int FIRST_STAGES = 3;
 template <int N>
 struct FirstCfg {
@@ -1448,7 +1454,8 @@ struct FirstCfg {
   static constexpr int B_BYTES = N * 128;
   static constexpr int B_OFF = FIRST_STAGES * STAGE_BYTES;  // B_hi, then B_lo
   static constexpr int STG_OFF = B_OFF + 2 * B_BYTES;       // 8 x 4 KB epilogue staging
-  static constexpr int BAR_OFF = STG_OFF + 8 * 4096;
+  static constexpr int X_OFF = STG_OFF + 8 * 4096;          // FIRST_XS input halo patches
+  static constexpr int BAR_OFF = X_OFF + FIRST_XS * FIRST_X_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
   static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
 };
@@ -1460,8 +1467,8 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
 
 template <int N>
 __global__ void __launch_bounds__(FIRST_THREADS, 1)
-conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ z,
-                     float* __restrict__ partials, int B, int Cin, int H, int W) {
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ w, float* __restrict__ z,
+                     float* __restrict__ partials, int B, int Cin, int H, int W, int tw, int th) {
   using Cfg = FirstCfg<N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1469,16 +1476,23 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, f
   uint64_t* a_empty = a_full + FIRST_STAGES;
   uint64_t* t_full = a_empty + FIRST_STAGES;
   uint64_t* t_empty = t_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* x_full = t_empty + 2;
+  uint64_t* x_empty = x_full + FIRST_XS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_empty + FIRST_XS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = Cin * 9;
-  const long long npix = (long long)B * H * W;
-  const int num_tiles = (int)((npix + 127) / 128);
+  const int tiles_w = (W + tw - 1) / tw, tiles_h = (H + th - 1) / th;
+  const int num_tiles = tiles_w * tiles_h * B;
+  // halo patch [Cin][BH][BW] floats starting at pixel (w0 - 4, h0 - 1): the innermost TMA coordinate must keep the
+  // global address 16-byte aligned (an unaligned start is an illegal instruction), so the left halo is 4 wide
+  const int BW = tw + 8, BH = th + 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < FIRST_STAGES; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < FIRST_XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
     fence_mbar_init();
+    prefetch_tmap(&mapX);
   }
   if (warp == 4) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   // weights [N][K] (OIHW flattening) -> B_hi / B_lo operand tiles, zero-padded to K = 32
@@ -1506,30 +1520,22 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, f
 
   if (warp < 4) {
     // ===== builders =====
-    const int r = threadIdx.x;                              // row of the tile
-    int stage = 0;
-    uint32_t phase = 0;
-    auto gather = [&](int tile, float (&v)[32]) {           // the 27 (padded to 32) input values of this thread's pixel
-      const long long p = (long long)tile * 128 + r;
-      const bool valid = tile < num_tiles && p < npix;
-      const unsigned pu = valid ? (unsigned)p : 0u;         // launcher guarantees npix < 2^32
-      const unsigned t_ = pu / (unsigned)W;
-      const int wq = (int)(pu - t_ * (unsigned)W);
-      const int b = (int)(t_ / (unsigned)H);
-      const int hq = (int)(t_ - (unsigned)b * (unsigned)H);
-      const float* xb = x + (size_t)b * Cin * H * W;
+    const int r = threadIdx.x;                              // row of the tile = pixel (r % tw, r / tw)
+    const int iw = r % tw, ih = r / tw;
+    int stage = 0, xs = 0;
+    uint32_t phase = 0, xphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&x_full[xs], xphase);
+      const float* patch = reinterpret_cast<const float*>(smem + Cfg::X_OFF + xs * FIRST_X_BYTES);
+      float v[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
         const int ci = k / 9, rs = k - ci * 9;
-        const int dr = rs / 3 - 1, ds = rs - (rs / 3) * 3 - 1;
-        const int hh = hq + dr, ww = wq + ds;
-        const bool ok = valid && k < K && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
-        v[k] = ok ? __ldg(xb + ((size_t)ci * H + hh) * W + ww) : 0.f;
+        const int dr = rs / 3, ds = rs - dr * 3;            // patch origin is pixel (-4, -1) of the tile
+        v[k] = k < K ? patch[(ci * BH + ih + dr) * BW + iw + ds + 3] : 0.f;
       }
-    };
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      float v[32];
-      gather(tile, v);
+      mbar_arrive(&x_empty[xs]);                            // values are in registers: the slot may be refilled
+      if (++xs == FIRST_XS) { xs = 0; xphase ^= 1; }
       mbar_wait(&a_empty[stage], phase ^ 1);
       const uint32_t ah = smem_u32(smem + stage * Cfg::STAGE_BYTES), al = ah + Cfg::A_BYTES;
 #pragma unroll
@@ -1546,6 +1552,23 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, f
       fence_proxy_async();                                  // generic-proxy stores -> visible to tcgen05.mma
       mbar_arrive(&a_full[stage]);
       if (++stage == FIRST_STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 13) {
+    // ===== input TMA producer =====
+    if (lane == 0) {
+      int xs = 0;
+      uint32_t xphase = 0;
+      const uint32_t bytes = (uint32_t)(BW * BH * Cin * 4);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int tw_i = t % tiles_w; t /= tiles_w;
+        const int th_i = t % tiles_h;
+        const int b = t / tiles_h;
+        mbar_wait(&x_empty[xs], xphase ^ 1);
+        mbar_arrive_expect_tx(&x_full[xs], bytes);
+        tma_load_4d(smem + Cfg::X_OFF + xs * FIRST_X_BYTES, &mapX, &x_full[xs], tw_i * tw - 4, th_i * th - 1, 0, b);
+        if (++xs == FIRST_XS) { xs = 0; xphase ^= 1; }
+      }
     }
   } else if (warp == 4) {
     // ===== MMA issuer =====
@@ -1589,11 +1612,17 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, f
     float s1[32], s2[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) s1[j] = s2[j] = 0.f;
+    const int iw = row % tw, ih = row / tw;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      const long long p = (long long)tile * 128 + row;
-      const bool valid = p < npix;
+      int t = tile;
+      const int tw_i = t % tiles_w; t /= tiles_w;
+      const int th_i = t % tiles_h;
+      const int b = t / tiles_h;
+      const int wq = tw_i * tw + iw, hq = th_i * th + ih;
+      const bool valid = wq < W && hq < H;
+      const long long p = ((long long)b * H + hq) * W + wq;
       mbar_wait(&t_full[acc], (it >> 1) & 1);
       tc_fence_after();
       if (has_chunk) {
@@ -1626,31 +1655,44 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, f
 
 bool conv_first_tc_eligible(int Cin, int Cout) { return tc_available() && Cin * 9 <= 32 && (Cout == 32 || Cout == 64); }
 
+// the image must tile into tw x th = 128-pixel boxes of one image (tw a power of two >= 16) and rows must be
+// 16-byte multiples (TMA global strides)
+bool conv_first_tc_shape_ok(int Cin, int Cout, int H, int W) {
+  if (!conv_first_tc_eligible(Cin, Cout) || W < 16 || W % 4 != 0) return false;
+  const int tw = pow2_floor(W < 128 ? W : 128), th = 128 / tw;
+  return H >= th && (long long)H * W < (1LL << 31);
+}
+
 template <int N>
-static int launch_first_t(const float* x, const float* w, float* z, float* partials, int B, int Cin, int H, int W,
-                          int grid, cudaStream_t s) {
+static int launch_first_t(const CUtensorMap& mapX, const float* w, float* z, float* partials, int B, int Cin, int H, int W,
+                          int tw, int th, int grid, cudaStream_t s) {
   using Cfg = FirstCfg<N>;
   static bool attr_set = false;
   if (!attr_set) {
     RD_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_first_tc_kernel<N><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(x, w, z, partials, B, Cin, H, W);
+  conv_first_tc_kernel<N><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(mapX, w, z, partials, B, Cin, H, W, tw, th);
   RD_LAUNCHED();
   return 0;
 }
 
 int launch_conv_first_tc(const float* x, const float* w, float* z, float* partials, int* n_partials, int B, int Cin,
                          int H, int W, int Cout, cudaStream_t s) {
-  if (!conv_first_tc_eligible(Cin, Cout)) return fail("conv_first_tc: unsupported Cin=%d Cout=%d", Cin, Cout);
-  const long long npix = (long long)B * H * W;
-  if (npix >= (1LL << 32)) return fail("conv_first_tc: more than 2^32 pixels");
-  const long long tiles = (npix + 127) / 128;
+  if (!conv_first_tc_shape_ok(Cin, Cout, H, W)) return fail("conv_first_tc: unsupported Cin=%d Cout=%d %dx%d", Cin, Cout, H, W);
+  const int tw = pow2_floor(W < 128 ? W : 128), th = 128 / tw;
+  // one tensor map per call: x is the caller's tensor (a different address every batch)
+  CUtensorMap mapX;
+  const long long dims[4] = {W, H, Cin, B};
+  const long long strides[3] = {(long long)W * 4, (long long)H * W * 4, (long long)Cin * H * W * 4};
+  const int box[4] = {tw + 8, th + 2, Cin, 1};
+  RD_TRY(tc_encode_map(&mapX, x, 4, dims, strides, box, 2));
+  const long long tiles = (long long)cdiv(W, tw) * cdiv(H, th) * B;
   const int grid = tiles < 148 ? (int)tiles : 148;
   if (n_partials) *n_partials = grid * 4;
   switch (Cout) {
-    case 32: return launch_first_t<32>(x, w, z, partials, B, Cin, H, W, grid, s);
-    case 64: return launch_first_t<64>(x, w, z, partials, B, Cin, H, W, grid, s);
+    case 32: return launch_first_t<32>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, s);
+    case 64: return launch_first_t<64>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, s);
   }
   return fail("conv_first_tc: unsupported Cout=%d", Cout);
 }

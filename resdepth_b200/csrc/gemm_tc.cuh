@@ -86,6 +86,7 @@ int tc_make_reduce_plan_wide(TcReducePlan* plan, const void* U, int Cu, const vo
 // first encoder conv (Cin <= 3) on tcgen05: software im2col producer, 3xTF32 split (fp32-equivalent accuracy);
 // x NCHW, w OIHW, z NHWC; partials: [n_partials][Cout][2] BatchNorm column sums (may be null)
 bool conv_first_tc_eligible(int Cin, int Cout);
+bool conv_first_tc_shape_ok(int Cin, int Cout, int H, int W);
 int launch_conv_first_tc(const float* x, const float* w, float* z, float* partials, int* n_partials, int B, int Cin,
                          int H, int W, int Cout, cudaStream_t s);
 
