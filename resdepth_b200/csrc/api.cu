@@ -45,6 +45,8 @@ struct ConvBlock {     // conv3x3 (+BN) + activation (+pool): conv_block / bottl
   bool tc = false;     // GEMMs of this block run on tcgen05
   bool bb = false;     // backward GEMMs of this block take bf16 operands (dz, block input, dgrad weights)
   int wide = 0;        // weight gradient through the wide-N reduce plan: 1 = rows are ci, 2 = rows are co
+  void* gyb = nullptr; // bf16 dz buffer of this block (gy_b or gy_b2)
+  int par = 0;         // its parity
   TcRowsPlan tc_fwd, tc_dgrad;
   TcReducePlan tc_wgrad;
   // bf16 shadows (uint16 storage): a_b / p_b copies of a / p for consumers' bf16 GEMMs, dgrad weights
@@ -98,7 +100,15 @@ struct rd_handle {
   // bf16 backward (RESDEPTH_BWD=bf16, default in TF32 mode): dz and the skip gradients as bf16 GEMM operands
   bool bwd_bf16 = false;
   void* gy_b = nullptr;
+  void* gy_b2 = nullptr;       // second dz buffer: consecutive blocks alternate so a weight gradient on the side
+                               // stream can still read block k's dz while block k+1's BatchNorm backward writes its own
   std::vector<void*> gs_b;
+  // weight gradients overlap the rest of the backward pass on a side stream (tensor-bound GEMMs next to the
+  // HBM-bound BatchNorm backward kernels); only when every GEMM of the backward runs the bf16 tcgen05 path
+  bool overlap = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_main = nullptr, ev_join = nullptr, ev_wg[2] = {nullptr, nullptr};
+  bool wg_pending[2] = {false, false};
   void* xcol_b = nullptr;
   int xcol_b_k = 0;
   // outer_skip_BN: BatchNorm2d(1) on input channel 0
@@ -269,6 +279,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     h->gp = c.take(max_pool);
     h->gt = h->cfg.up_mode == RD_UP_BILINEAR ? c.take(max_out / 4 + 64) : nullptr;
     h->gy_b = bf ? c.take(max_out / 2 + 64) : nullptr;
+    h->gy_b2 = bf ? c.take(max_out / 2 + 64) : nullptr;
     h->gp_b = bf ? c.take(max_pool / 2 + 64) : nullptr;
     h->gs_b.assign(D, nullptr);
     if (bf)
@@ -280,7 +291,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   } else {
     h->xcol = nullptr;
     h->gt = nullptr;
-    h->gy_b = nullptr; h->xcol_b = nullptr; h->gp_b = nullptr;
+    h->gy_b = nullptr; h->gy_b2 = nullptr; h->xcol_b = nullptr; h->gp_b = nullptr;
     h->gs_b.assign(D, nullptr);
     h->part = nullptr; h->part_floats = 0;
     h->g_skip.assign(D, nullptr);
@@ -299,6 +310,15 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
   for (auto& u : h->ups) { u.tc = u.bb = false; u.tc_fwd.valid = u.tc_dgrad.valid = u.tc_wgrad.valid = false; }
   if (!h->tf32() || !tc_available()) return 0;
   const bool bf = bwd && h->gy_b != nullptr;            // bf16 operands for the backward GEMMs
+  h->overlap = false;
+  {
+    // dz buffers alternate in the order the backward pass visits the blocks: dec[D-2..0], bottleneck, enc[D-1..0]
+    int ord = 0;
+    auto assign = [&](ConvBlock& b) { b.par = ord & 1; b.gyb = b.par ? h->gy_b2 : h->gy_b; ++ord; };
+    for (int j = D - 2; j >= 0; --j) assign(h->dec[j]);
+    assign(h->bott);
+    for (int i = D - 1; i >= 0; --i) assign(h->enc[i]);
+  }
   auto block = [&](ConvBlock& b, const float* src, const void* src_b, int H) -> int {
     Gather gf = gather_conv3x3(H, H, b.Cin);
     Gather gd = gather_conv3x3(H, H, b.Cout);
@@ -306,21 +326,21 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     RD_TRY(tc_make_rows_plan(&b.tc_fwd, src, gf, B, b.w_nk, b.Cout));
     if (bwd) {
       if (bf && src_b && b.wd_nk_b && tc_rows_eligible(gd, b.Cin, 1) && tc_reduce_eligible(gf, b.Cout, 1)) {
-        RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy_b, gd, B, b.wd_nk_b, b.Cin, 1));
+        RD_TRY(tc_make_rows_plan(&b.tc_dgrad, b.gyb, gd, B, b.wd_nk_b, b.Cin, 1));
         // narrow output tiles (Cout or Cin of 64 / 128) are L2-bound: use the wide-N formulation where it applies
         static const bool no_wide = getenv("RESDEPTH_NO_WIDE_WGRAD") != nullptr;
         b.wide = 0;
         if (!no_wide && b.Cout <= 128 && tc_reduce_wide_eligible(b.Cin, b.Cout, H, H)) {
           // D[ci][(t,co)] = sum_q x[q][ci] * dz[q - off(t)][co]
-          if (tc_make_reduce_plan_wide(&b.tc_wgrad, src_b, b.Cin, h->gy_b, b.Cout, -1, B, H, H, h->part, h->part_floats) == 0)
+          if (tc_make_reduce_plan_wide(&b.tc_wgrad, src_b, b.Cin, b.gyb, b.Cout, -1, B, H, H, h->part, h->part_floats) == 0)
             b.wide = 1;
         } else if (!no_wide && b.Cin == 64 && tc_reduce_wide_eligible(b.Cout, b.Cin, H, H)) {
           // D[co][(t,ci)] = sum_p dz[p][co] * x[p + off(t)][ci]
-          if (tc_make_reduce_plan_wide(&b.tc_wgrad, h->gy_b, b.Cout, src_b, b.Cin, +1, B, H, H, h->part, h->part_floats) == 0)
+          if (tc_make_reduce_plan_wide(&b.tc_wgrad, b.gyb, b.Cout, src_b, b.Cin, +1, B, H, H, h->part, h->part_floats) == 0)
             b.wide = 2;
         }
         if (!b.wide)
-          RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src_b, gf, B, h->gy_b, b.Cout, h->part, h->part_floats, 1));
+          RD_TRY(tc_make_reduce_plan(&b.tc_wgrad, src_b, gf, B, b.gyb, b.Cout, h->part, h->part_floats, 1));
         b.bb = true;
       } else {
         RD_TRY(tc_make_rows_plan(&b.tc_dgrad, h->gy, gd, B, b.wd_nk, b.Cin));
@@ -335,7 +355,7 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     ConvBlock& b0 = h->enc[0];
     Gather gb = gather_plain(T, T, h->xcol_b_k);
     if (bf && h->xcol_b && tc_reduce_eligible(gb, b0.Cout, 1)) {
-      RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, h->gy_b, b0.Cout, h->part, h->part_floats, 1));
+      RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, b0.gyb, b0.Cout, h->part, h->part_floats, 1));
       b0.bb = true;
     } else if (h->xcol) {
       Gather g0 = gather_plain(T, T, h->xcol_k);
@@ -393,6 +413,18 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
       if (tc_reduce_eligible(gd, u.C))
         RD_TRY(tc_make_reduce_plan(&u.tc_wgrad, h->g_skip[D - 1 - j], gd, B, src, u.C, h->part, h->part_floats));
     }
+  }
+  // side-stream weight gradients: every reduce GEMM must be a bf16 tcgen05 plan (they share the split buffer, which
+  // then belongs to the side stream alone, and read only bf16 tensors that the main stream no longer rewrites)
+  static const bool no_overlap = getenv("RESDEPTH_NO_OVERLAP") != nullptr;
+  if (bwd && bf && !no_overlap && h->side) {
+    bool all = true;
+    auto ok = [&](const ConvBlock& b) { return b.bb && b.tc_wgrad.valid && b.tc_wgrad.p.bf16; };
+    for (auto& b : h->enc) all = all && ok(b);
+    for (auto& b : h->dec) all = all && ok(b);
+    all = all && ok(h->bott);
+    for (auto& u : h->ups) all = all && u.bb && u.tc_wgrad.valid && !u.bilinear;
+    h->overlap = all;
   }
   return 0;
 }
@@ -570,6 +602,14 @@ int rd_create(const rd_config* cfg, int device, rd_handle** out) {
   return 0;
 }
 
+static void destroy_side(rd_handle* h) {
+  if (h->side) cudaStreamDestroy(h->side);
+  for (cudaEvent_t e : {h->ev_main, h->ev_join, h->ev_wg[0], h->ev_wg[1]})
+    if (e) cudaEventDestroy(e);
+  h->side = nullptr;
+  h->ev_main = h->ev_join = h->ev_wg[0] = h->ev_wg[1] = nullptr;
+}
+
 int rd_destroy(rd_handle* h) {
   if (!h) return 0;
   if (h->slab) {
@@ -578,6 +618,7 @@ int rd_destroy(rd_handle* h) {
   }
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto& e : h->event_pool) cudaEventDestroy(e);
+  destroy_side(h);
   delete h;
   return 0;
 }
@@ -635,6 +676,11 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
     RD_CUDA(cudaDeviceSynchronize());   // re-carving a live slab: wait for in-flight work
   }
   carve(h, h->slab, batch, tile, with_backward);
+  if (with_backward && !h->side) {                          // side stream + events of the overlapped weight gradients
+    RD_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&h->ev_main, &h->ev_join, &h->ev_wg[0], &h->ev_wg[1]})
+      RD_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
   RD_TRY(build_tc_plans(h, batch, tile, with_backward));
   const float consts[4] = {0.f, 0.01f, 1.f, 0.f};          // relu slope, LeakyReLU default slope (lib/UNet.py:30)
   RD_CUDA(cudaMemcpy(h->consts, consts, sizeof(consts), cudaMemcpyHostToDevice));
@@ -817,19 +863,31 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
                                   do_bn ? h->G + b.gamma : nullptr, h->G + (do_bn ? b.beta : b.bias),
                                   b.slope >= 0 ? h->G + b.slope : nullptr, h->scratch, h->coef, s));
   }
+  // weight gradients go to the side stream (h->overlap): fork after dz is written, join at the end of rd_backward;
+  // the dz buffer of this parity may still be read by the weight gradient launched two blocks ago
+  const bool ov = h->overlap;
+  cudaStream_t ws = ov ? h->side : s;
+  if (ov && h->wg_pending[b.par]) {
+    RD_CUDA(cudaStreamWaitEvent(s, h->ev_wg[b.par], 0));
+    h->wg_pending[b.par] = false;
+  }
   {
     ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (1.0 + (b.bb ? 0.5 : 1.0) + gin), s);
-    RD_TRY(launch_bn_bwd_apply(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? h->gy_b : nullptr, B,
+    RD_TRY(launch_bn_bwd_apply(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? b.gyb : nullptr, B,
                                H, H, h->tf32() && (b.tc || b.tc_wgrad.valid), s));
   }
+  if (ov) {
+    RD_CUDA(cudaEventRecord(h->ev_main, s));
+    RD_CUDA(cudaStreamWaitEvent(ws, h->ev_main, 0));
+  }
   if (first) {
-    ProfScope ps(h, RD_PROF_FIRST_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+    ProfScope ps(h, RD_PROF_FIRST_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), ws);
     if (b.tc_wgrad.valid) {
       const int kc = b.bb ? h->xcol_b_k : h->xcol_k;
-      if (b.bb) RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, kc, s));
-      else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, s));
-      RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, s));
-      RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, kc, s));
+      if (b.bb) RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, kc, ws));
+      else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, ws));
+      RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, ws));
+      RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, kc, ws));
     } else {
       RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
     }
@@ -837,19 +895,23 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
     Gather g = gather_conv3x3(H, H, b.Cin);
     int S = 0;
     {
-      ProfScope ps(h, RD_PROF_CONV_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
+      ProfScope ps(h, RD_PROF_CONV_WGRAD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), ws);
       if (b.tc_wgrad.valid) {
-        RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, s));
+        RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, ws));
         S = b.tc_wgrad.splits;
       } else {
-        RD_TRY(launch_gemm_reduce_simt(src_in, g, h->gy, B, b.Cout, h->part, h->part_floats, &S, s));
+        RD_TRY(launch_gemm_reduce_simt(src_in, g, h->gy, B, b.Cout, h->part, h->part_floats, &S, ws));
       }
     }
-    ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), s);
+    ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 9.0 * b.Cin * b.Cout * (S + 1.0), ws);
     if (b.wide && b.tc_wgrad.valid)
-      RD_TRY(launch_unpack_conv_grad_wide(h->part, S, b.tc_wgrad.p.N, h->G + b.w, b.Cout, b.Cin, b.wide == 1, s));
+      RD_TRY(launch_unpack_conv_grad_wide(h->part, S, b.tc_wgrad.p.N, h->G + b.w, b.Cout, b.Cin, b.wide == 1, ws));
     else
-      RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, 9, s));
+      RD_TRY(launch_unpack_conv_grad(h->part, S, h->G + b.w, b.Cout, b.Cin, 9, ws));
+  }
+  if (ov) {
+    RD_CUDA(cudaEventRecord(h->ev_wg[b.par], ws));
+    h->wg_pending[b.par] = true;
   }
   if (dgrad_out || dgrad_out_b) {
     Gather g = gather_conv3x3(H, H, b.Cout);
@@ -937,18 +999,23 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     } else {
     Gather g4 = gather_up2(Hin, Hin, u.C);
     int S = 0;
+    cudaStream_t ws = h->overlap ? h->side : s;         // the gradient at u_j (bf16) is complete on the main stream here
+    if (h->overlap) {
+      RD_CUDA(cudaEventRecord(h->ev_main, s));
+      RD_CUDA(cudaStreamWaitEvent(ws, h->ev_main, 0));
+    }
     {
-      ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
+      ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, ws);
       if (u.tc_wgrad.valid) {
-        RD_TRY(launch_gemm_reduce_tc(u.tc_wgrad, s));
+        RD_TRY(launch_gemm_reduce_tc(u.tc_wgrad, ws));
         S = u.tc_wgrad.splits;
       } else {
-        RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, s));
+        RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, ws));
       }
     }
     {
-      ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 4.0 * cc * (S + 1.0), s);
-      RD_TRY(launch_unpack_convt_grad(h->part, S, h->G + u.w, u.C, u.C, s));
+      ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 4.0 * cc * (S + 1.0), ws);
+      RD_TRY(launch_unpack_convt_grad(h->part, S, h->G + u.w, u.C, u.C, ws));
     }
     Epilogue e{};
     e.mode = EPI_PLAIN;
@@ -980,6 +1047,11 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     RD_TRY(block_backward(h, h->enc[i], gs, gp, B, H, i == 0 ? x : h->enc[i - 1].p, i == 0,
                           (i == 0 || out_b) ? nullptr : h->gp, 0, nullptr, out_b ? h->gp_b : nullptr, s));
     gp_bf16 = out_b;
+  }
+  if (h->overlap) {                                       // the caller's stream continues only after every weight gradient
+    RD_CUDA(cudaEventRecord(h->ev_join, h->side));
+    RD_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+    h->wg_pending[0] = h->wg_pending[1] = false;
   }
   return 0;
 }

@@ -5,6 +5,7 @@
 //   * last  conv  C -> 1 (+bias, +outer residual)     (reference lib/UNet.py:184,227,229-244)
 //   * their weight/input gradients (autograd of the above, reference lib/Trainer.py:179)
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -424,8 +425,11 @@ int launch_conv_last_fwd(const float* u, const float* w, const float* bias, cons
 // last conv backward: for input pixel q and channel c, with n[r][s] = dy[q - (r-1, s-1)]:
 //   du[q,c] = sum_{r,s} n[r][s] W[c,r,s];   dW[c,r,s] += u[q,c] n[r][s];   db += dy[q]
 // ----------------------------------------------------------------------------------------------
-template <int QPL>
-__global__ void __launch_bounds__(256)
+// MODE 0: everything in one pass (default); MODE 1: du (+ its channel sums, db) only; MODE 2: dW only.  The split
+// pair (RESDEPTH_LAST_BWD_SPLIT=1) was tried against the fused pass's register pressure (126 registers, 2 CTAs per
+// SM, ncu: 37 % DRAM) and measured slower on B200: 0.29 + 0.34 ms against 0.55 ms.
+template <int QPL, int MODE>
+__global__ void __launch_bounds__(256, MODE == 0 ? 2 : 3)
 conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ w,
                      float* __restrict__ du, __nv_bfloat16* __restrict__ du_b, float* __restrict__ part, int B, int H,
                      int W, int C, int tiles_x, int tiles_y, int ntiles) {
@@ -442,7 +446,7 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
     const int c = (lane16 + 16 * j) * 4;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
-      if (c < C) wr[j][k] = make_float4(w[(c + 0) * 9 + k], w[(c + 1) * 9 + k], w[(c + 2) * 9 + k], w[(c + 3) * 9 + k]);
+      if (MODE != 2 && c < C) wr[j][k] = make_float4(w[(c + 0) * 9 + k], w[(c + 1) * 9 + k], w[(c + 2) * 9 + k], w[(c + 3) * 9 + k]);
       else wr[j][k] = make_float4(0, 0, 0, 0);
       dwacc[j][k] = make_float4(0, 0, 0, 0);
     }
@@ -475,7 +479,7 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
 #pragma unroll
         for (int j = 0; j < QPL; ++j) {
           const int c = (lane16 + 16 * j) * 4;
-          uvs[i][j] = (okp[i] && c < C) ? __ldg(reinterpret_cast<const float4*>(u + o + c)) : make_float4(0, 0, 0, 0);
+          uvs[i][j] = (MODE != 1 && okp[i] && c < C) ? __ldg(reinterpret_cast<const float4*>(u + o + c)) : make_float4(0, 0, 0, 0);
         }
       }
 #pragma unroll
@@ -489,7 +493,7 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * HALO_W + (lw + 1 - (s2 - 1))];
-        if (lane16 == 0) dbacc += n[4];
+        if (MODE != 2 && lane16 == 0) dbacc += n[4];
         const size_t o = (((size_t)b * H + gh) * W + gw) * C;
 #pragma unroll
         for (int j = 0; j < QPL; ++j) {
@@ -499,11 +503,16 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
             float4 d = make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
-              d.x = fmaf(n[k], wr[j][k].x, d.x); d.y = fmaf(n[k], wr[j][k].y, d.y);
-              d.z = fmaf(n[k], wr[j][k].z, d.z); d.w = fmaf(n[k], wr[j][k].w, d.w);
-              dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
-              dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
+              if (MODE != 2) {
+                d.x = fmaf(n[k], wr[j][k].x, d.x); d.y = fmaf(n[k], wr[j][k].y, d.y);
+                d.z = fmaf(n[k], wr[j][k].z, d.z); d.w = fmaf(n[k], wr[j][k].w, d.w);
+              }
+              if (MODE != 1) {
+                dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
+                dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
+              }
             }
+            if (MODE == 2) continue;
             if (du) *reinterpret_cast<float4*>(du + o + c) = d;
             if (du_b) {
               __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
@@ -540,11 +549,11 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
 #pragma unroll
     for (int g = 0; g < 16; ++g) a += red_dyn[g * RS + i];
     if (i == RS - 1) {
-      part[prow + C * 9] = a;
+      if (MODE != 2) part[prow + C * 9] = a;
     } else if (i >= NDW) {
       const int c = i - NDW;
-      if (c < C) part[prow + C * 9 + 1 + c] = a;
-    } else {
+      if (MODE != 2 && c < C) part[prow + C * 9 + 1 + c] = a;
+    } else if (MODE != 1) {
       const int cc = i & 3, k = (i >> 2) % 9, ql = (i >> 2) / 9;   // ql = j*16 + lane16 = channel quad
       const int c = ql * 4 + cc;
       if (c < C) part[prow + c * 9 + k] = a;
@@ -561,15 +570,24 @@ int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float*
   int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
   const int PN = C * 10 + 1;
   if ((size_t)grid * PN > scratch_floats) return fail("conv_last_bwd: scratch too small");
-  if (C <= 64) {
+  static const bool split = getenv("RESDEPTH_LAST_BWD_SPLIT") != nullptr;
+  if (C <= 64 && split) {
+    // two passes (same grid, disjoint columns of the same partial rows): du + channel sums + db, then dW
     const int smem = 16 * (10 * 4 * 16 * 1 + 1) * (int)sizeof(float);
-    conv_last_bwd_kernel<1><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B, H,
-                                                    W, C, tiles_x, tiles_y, ntiles);
+    conv_last_bwd_kernel<1, 1><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch,
+                                                       B, H, W, C, tiles_x, tiles_y, ntiles);
+    RD_LAUNCHED();
+    conv_last_bwd_kernel<1, 2><<<grid, 256, smem, s>>>(u, dy, w, nullptr, nullptr, scratch, B, H, W, C, tiles_x, tiles_y,
+                                                       ntiles);
+  } else if (C <= 64) {
+    const int smem = 16 * (10 * 4 * 16 * 1 + 1) * (int)sizeof(float);
+    conv_last_bwd_kernel<1, 0><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B,
+                                                       H, W, C, tiles_x, tiles_y, ntiles);
   } else {
     const int smem = 16 * (10 * 4 * 16 * 2 + 1) * (int)sizeof(float);
-    RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_last_bwd_kernel<2><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B, H,
-                                                    W, C, tiles_x, tiles_y, ntiles);
+    RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_last_bwd_kernel<2, 0><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B,
+                                                       H, W, C, tiles_x, tiles_y, ntiles);
   }
   RD_LAUNCHED();
   RD_TRY(launch_sum_partials(scratch, grid, C * 9, PN, 1, dw, s));
