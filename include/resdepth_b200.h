@@ -145,6 +145,11 @@ int rd_residual_stats(const double* res, const uint8_t* valid, int64_t n, double
 int rd_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n, int tile, float nodata, double* stds,
                  void* stream);
 
+/* rd_backward runs the weight-gradient GEMMs on a handle-owned side stream (forked after each dz, joined before it
+ * returns control of `stream`) when every GEMM of the backward pass takes the bf16 tcgen05 path.  on = 0 serialises
+ * everything on the caller's stream (used by the per-kernel profile of bench.py); default 1. */
+int rd_set_overlap(rd_handle* h, int on);
+
 /* Per-category device timing (CUDA events on the launching stream around the library's own launches).
  * rd_profile_enable(h, 1) starts recording; rd_profile_collect synchronises the recorded events and folds
  * them into per-category totals; rd_profile_read returns one category: total milliseconds, algorithmic

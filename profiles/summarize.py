@@ -66,8 +66,45 @@ def ncu(paths):
         print()
 
 
+def step(md_path):
+    """Re-format the table written by `summarize.py ncu` for a --metrics capture of one whole step (run on the GPU box,
+    only the small .md travels back) into the committed per-launch + per-kernel summary."""
+    rows = [l for l in open(md_path).read().splitlines() if l.startswith('| `')]
+    hdr = ['kernel', 'grid', 'time us', 'DRAM rd MB', 'DRAM wr MB', 'DRAM %', 'tensor pipe %', 'SM %', 'L2 hit %', 'regs',
+           'warps active %', 'dyn smem KB']
+    print('# ncu metrics of every kernel launch of one train step (batch 64, 3-ch 256x256, depth 5)\n')
+    print('Command (on the B200 box): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,'
+          'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,'
+          'sm__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,launch__registers_per_thread,'
+          'sm__warps_active.avg.pct_of_peak_sustained_active,launch__shared_mem_per_block_dynamic --clock-control none -s 138 '
+          '-c 138 -o /tmp/step python profiles/one_step.py 2`, then `summarize.py ncu /tmp/step.ncu-rep` there and '
+          '`summarize.py step` here.  138 consecutive launches = one full step (the window starts at the second step). '
+          'ncu times are cold-cache and serialised: compare SHARES with `bench.py`, not absolutes.\n')
+    print('| # | ' + ' | '.join(hdr) + ' |')
+    print('|---:|---|---|' + '---:|' * 10)
+    agg, tot = OrderedDict(), 0.0
+    for i, l in enumerate(rows):
+        c = [x.strip() for x in l.strip('|').split('|')]
+        name = c[0].replace('rd::', '')
+        t, rd, wr = float(c[2]), float(c[3]) * 1e3, float(c[4]) * 1e3
+        vals = [name, c[1], f'{t:.1f}', f'{rd:.1f}', f'{wr:.1f}', f'{float(c[5]):.1f}', f'{float(c[6]):.1f}',
+                f'{float(c[7]):.1f}', f'{float(c[8]):.1f}', c[9], f'{float(c[10]):.1f}', f'{float(c[11]):.1f}']
+        print(f'| {i} | ' + ' | '.join(vals) + ' |')
+        a = agg.setdefault(name.replace('`', ''), [0, 0.0, 0.0, 0.0, 0.0])
+        a[0] += 1; a[1] += t; a[2] += rd + wr; a[3] += float(c[6]) * t; a[4] += float(c[5]) * t
+        tot += t
+    print('\n## Per kernel\n')
+    print('| kernel | launches | total us | share | DRAM traffic MB / launch | time-weighted tensor pipe % | time-weighted DRAM % |')
+    print('|---|---:|---:|---:|---:|---:|---:|')
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f'| `{k}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / tot:.1f} % | {a[2] / a[0]:.1f} | {a[3] / a[1]:.1f} | {a[4] / a[1]:.1f} |')
+    print(f'\nTotal {tot / 1e3:.2f} ms over {len(rows)} launches.')
+
+
 if __name__ == '__main__':
     if sys.argv[1] == 'launches':
         launches(sys.argv[2])
+    elif sys.argv[1] == 'step':
+        step(sys.argv[2])
     else:
         ncu(sys.argv[2:])

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = (
     'rd_workspace_bytes', 'rd_forward', 'rd_loss', 'rd_backward', 'rd_adam_step', 'rd_sgd_step',
     'rd_blend_accumulate', 'rd_launch_count', 'rd_math_mode_name', 'rd_profile_enable', 'rd_profile_collect',
     'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce', 'rd_make_tiles', 'rd_residuals', 'rd_residual_stats',
-    'rd_tile_stds',
+    'rd_tile_stds', 'rd_set_overlap',
 )
 PROF_NUM = 18                                           # RD_PROF_NUM
 
@@ -100,6 +100,8 @@ def _declare(lib):
     lib.rd_residual_stats.argtypes = [vp, vp, i64, f64, vp, vp]
     lib.rd_tile_stds.restype = i32
     lib.rd_tile_stds.argtypes = [vp, i32, i32, vp, i32, i32, f32, vp, vp]
+    lib.rd_set_overlap.restype = i32
+    lib.rd_set_overlap.argtypes = [vp, i32]
     lib.rd_launch_count.restype = i64
     lib.rd_launch_count.argtypes = [i32]
     lib.rd_math_mode_name.restype = C.c_char_p
@@ -195,6 +197,10 @@ class Handle:
 
     def backward(self, x_ptr, dy_ptr, stream):
         check(self._lib.rd_backward(self._h, x_ptr, dy_ptr, stream), 'rd_backward')
+
+    def set_overlap(self, on: bool):
+        """Side-stream weight gradients in rd_backward on (default) / off (everything on the caller's stream)."""
+        check(self._lib.rd_set_overlap(self._h, 1 if on else 0), 'rd_set_overlap')
 
     def profile_enable(self, on: bool):
         check(self._lib.rd_profile_enable(self._h, 1 if on else 0), 'rd_profile_enable')

@@ -106,6 +106,7 @@ struct rd_handle {
   // weight gradients overlap the rest of the backward pass on a side stream (tensor-bound GEMMs next to the
   // HBM-bound BatchNorm backward kernels); only when every GEMM of the backward runs the bf16 tcgen05 path
   bool overlap = false;
+  bool overlap_allowed = true; // rd_set_overlap
   cudaStream_t side = nullptr;
   cudaEvent_t ev_main = nullptr, ev_join = nullptr, ev_wg[2] = {nullptr, nullptr};
   bool wg_pending[2] = {false, false};
@@ -865,7 +866,7 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
   }
   // weight gradients go to the side stream (h->overlap): fork after dz is written, join at the end of rd_backward;
   // the dz buffer of this parity may still be read by the weight gradient launched two blocks ago
-  const bool ov = h->overlap;
+  const bool ov = h->overlap && h->overlap_allowed;
   cudaStream_t ws = ov ? h->side : s;
   if (ov && h->wg_pending[b.par]) {
     RD_CUDA(cudaStreamWaitEvent(s, h->ev_wg[b.par], 0));
@@ -999,8 +1000,9 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     } else {
     Gather g4 = gather_up2(Hin, Hin, u.C);
     int S = 0;
-    cudaStream_t ws = h->overlap ? h->side : s;         // the gradient at u_j (bf16) is complete on the main stream here
-    if (h->overlap) {
+    const bool ov = h->overlap && h->overlap_allowed;
+    cudaStream_t ws = ov ? h->side : s;                 // the gradient at u_j (bf16) is complete on the main stream here
+    if (ov) {
       RD_CUDA(cudaEventRecord(h->ev_main, s));
       RD_CUDA(cudaStreamWaitEvent(ws, h->ev_main, 0));
     }
@@ -1048,7 +1050,7 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
                           (i == 0 || out_b) ? nullptr : h->gp, 0, nullptr, out_b ? h->gp_b : nullptr, s));
     gp_bf16 = out_b;
   }
-  if (h->overlap) {                                       // the caller's stream continues only after every weight gradient
+  if (h->overlap && h->overlap_allowed) {                 // the caller's stream continues only after every weight gradient
     RD_CUDA(cudaEventRecord(h->ev_join, h->side));
     RD_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
     h->wg_pending[0] = h->wg_pending[1] = false;
@@ -1142,6 +1144,12 @@ int rd_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n
                  void* stream) {
   if (!dsm || !pos || !stds || n < 0 || tile <= 0 || tile > rows || tile > cols) return fail("rd_tile_stds: bad argument");
   return launch_tile_stds(dsm, rows, cols, pos, n, tile, nodata, stds, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_set_overlap(rd_handle* h, int on) {
+  if (!h) return fail("rd_set_overlap: null handle");
+  h->overlap_allowed = on != 0;
+  return 0;
 }
 
 int rd_profile_enable(rd_handle* h, int on) {
