@@ -712,8 +712,57 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, float* __restri
     if (dnk_b) dnk_b[(size_t)ci * 9 * Co + (size_t)tr * Co + co] = __float2bfloat16_rn(w[i]);
   }
 }
+// Tiled variant (Co multiple of 32, Ci multiple of 8): one block stages a 32 co x 8 ci x 9 tap tile in shared memory
+// (coalesced 288-byte pieces of the OIHW rows) and writes every requested layout with the layout's own fastest index
+// across the lanes (full 32-byte sectors or better) -- the element-wise kernel above scatters 4-byte (2-byte) stores
+// over 32 sectors per warp.  Small tiles on purpose: the layers are small and the grid must fill the chip.
+constexpr int PK_CI = 8, PK_ROW = PK_CI * 9;            // 72 floats per co row of the tile
+__global__ void __launch_bounds__(256)
+pack_conv3x3_tiled_kernel(const float* __restrict__ w, float* __restrict__ kn, float* __restrict__ nk,
+                          float* __restrict__ dkn, float* __restrict__ dnk, __nv_bfloat16* __restrict__ dnk_b, int Co,
+                          int Ci, int rnd) {
+  __shared__ float tl[32][PK_ROW + 1];
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * PK_CI;
+  for (int idx = threadIdx.x; idx < 32 * PK_ROW; idx += 256) {
+    const int r = idx / PK_ROW, c = idx - r * PK_ROW;
+    tl[r][c] = w[((size_t)(co0 + r) * Ci + ci0) * 9 + c];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * PK_ROW; idx += 256) {
+    {                                                                 // ci fastest: (ci, t, co)
+      const int ci = idx % PK_CI, t = (idx / PK_CI) % 9, co = idx / PK_ROW;
+      if (nk) {                                                       // nk[co][(t,ci)]
+        const float v = tl[co][ci * 9 + t];
+        nk[(size_t)(co0 + co) * 9 * Ci + (size_t)t * Ci + ci0 + ci] = rnd ? tf32_rn(v) : v;
+      }
+      if (dkn) {                                                      // dkn[(tr,co)][ci]
+        const float v = tl[co][ci * 9 + (8 - t)];
+        dkn[((size_t)t * Co + co0 + co) * Ci + ci0 + ci] = rnd ? tf32_rn(v) : v;
+      }
+    }
+    {                                                                 // co fastest: (co, t, ci)
+      const int co = idx & 31, t = (idx >> 5) % 9, ci = idx / 288;
+      if (kn) {                                                       // kn[(t,ci)][co]
+        const float v = tl[co][ci * 9 + t];
+        kn[((size_t)t * Ci + ci0 + ci) * Co + co0 + co] = rnd ? tf32_rn(v) : v;
+      }
+      if (dnk || dnk_b) {                                             // dnk[ci][(tr,co)]
+        const float v = tl[co][ci * 9 + (8 - t)];
+        const size_t o = (size_t)(ci0 + ci) * 9 * Co + (size_t)t * Co + co0 + co;
+        if (dnk) dnk[o] = rnd ? tf32_rn(v) : v;
+        if (dnk_b) dnk_b[o] = __float2bfloat16_rn(v);
+      }
+    }
+  }
+}
 int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, void* dnk_b, int Co, int Ci,
                         int rnd, cudaStream_t s) {
+  if (Co % 32 == 0 && Ci % PK_CI == 0) {
+    pack_conv3x3_tiled_kernel<<<dim3(Ci / PK_CI, Co / 32), 256, 0, s>>>(w, kn, nk, dkn, dnk,
+                                                                   reinterpret_cast<__nv_bfloat16*>(dnk_b), Co, Ci, rnd);
+    RD_LAUNCHED();
+    return 0;
+  }
   pack_conv3x3_kernel<<<ew_grid((long long)Co * Ci * 9), 256, 0, s>>>(w, kn, nk, dkn, dnk,
                                                                       reinterpret_cast<__nv_bfloat16*>(dnk_b), Co, Ci, rnd);
   RD_LAUNCHED();
@@ -755,6 +804,9 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ part, int S
     dw[((size_t)co * Ci + ci) * ntaps + t] = a;
   }
 }
+// (A shared-memory tiled un-pack, the mirror image of pack_conv3x3_tiled_kernel, was measured slower -- 0.31 vs 0.26 ms
+// per step: the split partials are read S times, so the element-wise kernels' full-chip parallelism on the reads matters
+// more than their scattered 4-byte stores.)
 int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s) {
   unpack_conv3x3_grad_kernel<<<ew_grid((long long)Co * Ci * ntaps), 256, 0, s>>>(part, S, dw, Co, Ci, ntaps);
   RD_LAUNCHED();
