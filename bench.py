@@ -278,7 +278,8 @@ def run_native(args):
     handle.set_overlap(True)
     # end to end through the public API the reference's train.py drives: Trainer.inference_one_epoch over a loader of
     # K pinned HOST batches (per step: H2D copies of that step's inputs -- enqueued one batch ahead so they overlap
-    # the previous step's compute --, forward, loss, backward, optimizer.step, loss.item()).  The un-pipelined
+    # the previous step's compute --, forward, loss, backward, optimizer.step, D2H of the loss, consumed by the host
+    # one iteration later so the GPU never waits for the host).  The un-pipelined
     # per-call figure (inference_one_batch on a host batch: copy, then compute) is kept beside it.
     def e2e_epoch(i):
         tr.loader['train'] = [host[j % N_INPUT_SETS] for j in range(K)]
@@ -328,8 +329,9 @@ def run_native(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'ms_per_step': e2e_ms / K,
-                    'api': 'resdepth_b200.lib.Trainer.inference_one_epoch over K pinned host batches (H2D one batch '
-                           'ahead, inference_one_batch, optimizer.step, loss.item() every step)',
+                    'api': 'resdepth_b200.lib.Trainer.inference_one_epoch over K pinned host batches (per step: H2D of '
+                           'the batch -- enqueued one batch ahead --, forward, loss, backward, optimizer.step, 4-byte D2H '
+                           'of the loss into pinned memory, read by the host one iteration later)',
                     'unpipelined_per_call': {'value': tiles / (e2e_call_ms * 1e-3), 'unit': UNIT,
                                              'api': 'Trainer.inference_one_batch(host batch) + optimizer.step'},
                     'clocks': e2e_clocks},

@@ -257,15 +257,19 @@ class Trainer(object):
 
     # ---------------------------------------------------------------------------------------------
     def inference_one_batch(self, batch, phase):
+        return {'MAE_metric': float(self._launch_batch(batch, phase).item())}
+
+    def _launch_batch(self, batch, phase):
+        """``inference_one_batch`` without the host synchronisation: enqueues the step and returns the loss as a
+        device tensor [1]."""
         assert phase in ['train', 'val']
         train = phase == 'train'
         self.model.train() if train else self.model.eval()
 
         if isinstance(batch, _StagedBatch):                 # copies already in flight (``_prefetched``)
             torch.cuda.current_stream(self.device).wait_event(batch.ready)
-            loss = self.device_step(batch['input'], batch['target'], batch['loss_mask'], batch['dsm_mean'],
+            return self.device_step(batch['input'], batch['target'], batch['loss_mask'], batch['dsm_mean'],
                                     batch['dsm_std'], train)
-            return {'MAE_metric': float(loss.item())}
 
         x, y, loss_mask = self._extract_inputs_outputs_loss_masks(batch)
         # the input tiles are needed first: copy them on the compute stream; target / mask / normalisation constants
@@ -285,9 +289,7 @@ class Trainer(object):
         for t in (y, loss_mask, mean, std):
             t.record_stream(main)
 
-        loss = self.device_step(x, y, loss_mask, mean, std, train, wait_before_loss=copied)
-
-        return {'MAE_metric': float(loss.item())}
+        return self.device_step(x, y, loss_mask, mean, std, train, wait_before_loss=copied)
 
     def device_step(self, x, y, loss_mask, mean, std, train, wait_before_loss=None):
         """The step on device-resident tensors: forward, fused loss (+ gradient seed), backward, gradient
@@ -314,17 +316,14 @@ class Trainer(object):
         for param in self.model.parameters():
             param.grad = None
 
-        for c_iter, batch in enumerate(self._prefetched(self.loader[phase])):
-            stats = self.inference_one_batch(batch, phase)
-
-            if phase == 'train':
-                self.optimizer.step()
-                for param in self.model.parameters():
-                    param.grad = None
-
-            for key, value in stats.items():
-                stats_meter[key].update(value)
-
+        # Same loop as the reference (lib/Trainer.py:212-238), software-pipelined: batch i+1 is copied to the device
+        # while batch i computes (``_prefetched``), and the loss of batch i is read back (4 bytes, pinned memory) only
+        # after batch i+1 has been enqueued, so the GPU never waits for the host between steps.  Every batch's
+        # MAE_metric reaches the meters / the log exactly as in the reference, one iteration later.
+        def consume(pending):
+            host, ev, c_iter = pending
+            ev.synchronize()
+            stats_meter['MAE_metric'].update(float(host.item()))
             if phase == 'train' and (c_iter + 1) % self.freq_average_train_loss == 0:
                 curr_iter = num_iter * epoch + (c_iter + 1)
                 message = f'{phase}:\tEpoch: {epoch} [{c_iter + 1}/{num_iter}]\t'
@@ -334,6 +333,25 @@ class Trainer(object):
                     stats_meter[key].reset()
                 self.logger.info(message)
                 self.writer.add_scalar("train/learning_rate", self._get_lr(), curr_iter)
+
+        pending = None
+        for c_iter, batch in enumerate(self._prefetched(self.loader[phase])):
+            loss = self._launch_batch(batch, phase)
+
+            if phase == 'train':
+                self.optimizer.step()
+                for param in self.model.parameters():
+                    param.grad = None
+
+            host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            host.copy_(loss, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            if pending is not None:
+                consume(pending)
+            pending = (host, ev, c_iter)
+        if pending is not None:
+            consume(pending)
 
         return stats_meter
 
