@@ -44,6 +44,23 @@ def shard_batch(batch: Dict[str, torch.Tensor], rank: int, world_size: int) -> D
     return out
 
 
+def owns_batch(batch_index: int, rank: int, world_size: int) -> bool:
+    """Tiled inference shards the DataLoader's batches round-robin over ranks (tiles are independent; the partial
+    rasters are summed once at the end, ``sum_partial_rasters``)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f'bad rank/world_size {rank}/{world_size}')
+    return batch_index % world_size == rank
+
+
+def sum_partial_rasters(raster: torch.Tensor) -> torch.Tensor:
+    """Blended float64 raster of one rank -> the complete raster on every rank (one all-reduce; no-op on one rank).
+    Linear blending is a sum of weighted tiles, so the partial rasters of disjoint tile subsets simply add."""
+    _, world_size = world()
+    if world_size > 1:
+        dist.all_reduce(raster, op=dist.ReduceOp.SUM)
+    return raster
+
+
 def allreduce_gradients(flat_grads: torch.Tensor) -> float:
     """Sums the flat gradient arena over all ranks in place (the ONE collective of the path) and returns the
     scale the optimizer must apply to turn the sum into the data-parallel mean."""

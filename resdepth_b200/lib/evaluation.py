@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from .. import _native
+from .distributed import owns_batch, sum_partial_rasters, world
 from .UNet import UNet
 
 
@@ -49,8 +50,11 @@ def predict_linear_blend(dataloader, model):
     tile_size, stride = dataset.tile_size, dataset.stride
     raster = torch.zeros((rows, cols), dtype=torch.float64, device=device)
 
+    rank, world_size = world()          # one process per GPU: every rank blends its share of the batches
     with torch.no_grad():
-        for batch in dataloader:
+        for bi, batch in enumerate(dataloader):
+            if not owns_batch(bi, rank, world_size):
+                continue
             x = batch['input']
             if not x.is_cuda and not x.is_pinned():
                 x = x.pin_memory()
@@ -64,7 +68,7 @@ def predict_linear_blend(dataloader, model):
             std = torch.flatten(batch['dsm_std']).to(device, dtype=torch.float32, non_blocking=True)
             y_pred = model(x)
             blend_tiles_into(raster, y_pred, mean, std, geom_d, tile_size, stride)
-    return raster.cpu().numpy()
+    return sum_partial_rasters(raster).cpu().numpy()
 
 
 # -------------------------------------------------------------------------------------------------

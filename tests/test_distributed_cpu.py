@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from resdepth_b200.lib.distributed import allreduce_gradients, shard_batch, shard_bounds, world
+from resdepth_b200.lib.distributed import (allreduce_gradients, owns_batch, shard_batch, shard_bounds,
+                                            sum_partial_rasters, world)
 
 
 def _free_port():
@@ -35,7 +36,14 @@ def _worker(rank, world_size, port, out_dir):
         expect = sum(full['input'][i].sum() for i in range(5)) * torch.arange(16.)
         assert abs(scale - 1.0 / world_size) < 1e-12
         assert torch.allclose(grads, expect, rtol=1e-5, atol=1e-5)
-        torch.save({'grads': grads, 'scale': scale}, os.path.join(out_dir, f'rank{rank}.pt'))
+        # tiled inference: batches round-robin over ranks, partial float64 rasters summed by one all-reduce
+        weights = torch.arange(1, 8, dtype=torch.float64)             # 7 "batches", each adds its weight to the raster
+        raster = torch.zeros(4, 6, dtype=torch.float64)
+        for bi in range(7):
+            if owns_batch(bi, rank, world_size):
+                raster[bi % 4, bi % 6] += weights[bi]
+        raster = sum_partial_rasters(raster)
+        torch.save({'grads': grads, 'scale': scale, 'raster': raster}, os.path.join(out_dir, f'rank{rank}.pt'))
     finally:
         dist.destroy_process_group()
 
@@ -46,6 +54,19 @@ def test_two_rank_gradient_allreduce_gloo(tmp_path):
     a = torch.load(tmp_path / 'rank0.pt')
     b = torch.load(tmp_path / 'rank1.pt')
     assert torch.equal(a['grads'], b['grads']) and a['scale'] == b['scale'] == 0.5
+    expect = torch.zeros(4, 6, dtype=torch.float64)
+    for bi in range(7):
+        expect[bi % 4, bi % 6] += bi + 1
+    assert torch.equal(a['raster'], expect) and torch.equal(b['raster'], expect)
+
+
+def test_owns_batch_partitions_the_loader():
+    for w in (1, 2, 3, 8):
+        owners = [[r for r in range(w) if owns_batch(bi, r, w)] for bi in range(20)]
+        assert all(len(o) == 1 for o in owners)
+    with pytest.raises(ValueError):
+        owns_batch(0, 3, 2)
+    assert torch.equal(sum_partial_rasters(torch.ones(2, 2, dtype=torch.float64)), torch.ones(2, 2, dtype=torch.float64))
 
 
 def test_shard_bounds_cover_the_batch():

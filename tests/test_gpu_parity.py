@@ -382,6 +382,59 @@ def test_predict_linear_blend_matches_oracle(math_mode):
     np.testing.assert_allclose(out, ref, rtol=0, atol=2e-4 if math_mode == 'fp32' else 5e-3)
 
 
+def test_evaluation_pipeline_blend_residuals_statistics(math_mode):
+    """test.py's evaluation chain on the device -- predict_linear_blend -> compute_residuals -> get_statistics --
+    against the oracle chain (UNet oracle -> blending oracle -> numpy masked statistics)."""
+    from types import SimpleNamespace
+
+    from oracle import stats_oracle as SO
+    from resdepth_b200.lib.evaluation import compute_residuals, get_statistics, predict_linear_blend
+    kwargs = dict(n_input_channels=1, start_kernel=32, depth=2, bias_conv_layer=True)
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    rows, cols, tile, stride = 64, 96, 32, 16
+    pos, box = O.regular_grid((0, cols - 1), (0, rows - 1), tile, stride)
+    gen = torch.Generator().manual_seed(21)
+    n = len(pos)
+    x = torch.randn(n, 1, tile, tile, generator=gen)
+    mean = 400 + torch.randn(n, generator=gen)
+    std = torch.full((n,), 2.0)
+    with torch.no_grad():
+        y_ref = O.unet_forward(sd, x, spec, training=False).numpy()
+    ref_raster = O.linear_blend(y_ref, mean.numpy(), std.numpy(), pos, box, rows, cols, tile, stride)
+    batches = []
+    for i in range(0, n, 4):
+        sl = slice(i, min(i + 4, n))
+        batches.append({'input': x[sl], 'dsm_mean': mean[sl], 'dsm_std': std[sl],
+                        'patch_offset_y': torch.tensor([p[0] for p in pos[sl]]),
+                        'patch_offset_x': torch.tensor([p[1] for p in pos[sl]]),
+                        'patch_valid_pixels_uly': torch.tensor([b[0] for b in box[sl]]),
+                        'patch_valid_pixels_ulx': torch.tensor([b[1] for b in box[sl]]),
+                        'patch_valid_pixels_lry': torch.tensor([b[2] for b in box[sl]]),
+                        'patch_valid_pixels_lrx': torch.tensor([b[3] for b in box[sl]])})
+
+    class Loader(list):
+        pass
+    loader = Loader(batches)
+    loader.dataset = SimpleNamespace(dsm_input_gdal=SimpleNamespace(RasterXSize=cols, RasterYSize=rows),
+                                     tile_size=tile, stride=stride)
+    raster = predict_linear_blend(loader, model)
+    rng = np.random.default_rng(4)
+    nodata = -9999.0
+    gt = (ref_raster + rng.standard_normal((rows, cols))).astype(np.float32)
+    gt[rng.random((rows, cols)) < 0.05] = nodata
+    mask_gt = rng.random((rows, cols)) > 0.1
+    st = get_statistics(compute_residuals(raster, gt, nodata, mask_gt), 2.0)
+    o = SO.get_statistics(SO.compute_residuals(ref_raster, gt, nodata, mask_gt), 2.0)
+    tol = 2e-4 if math_mode == 'fp32' else 5e-3                      # metres: the blended prediction's own tolerance
+    assert st.count_total == o['count_total']
+    for k in ('MAE', 'RMSE', 'absolute_median', 'median', 'NMAD', 'diff_max', 'diff_min'):
+        assert abs(st[k] - o[k]) <= tol, (k, st[k], o[k])
+    for k in ('MAE', 'RMSE', 'absolute_median', 'median', 'NMAD'):
+        assert abs(st.truncated[k] - o['truncated'][k]) <= 4 * tol, (k, st.truncated[k], o['truncated'][k])
+
+
 EXTRA_SHAPES = [
     # kwargs, B, T  -- shapes the golden table does not cover: non-power-of-two tiles (masked partial GEMM tiles),
     # batch 1, wider inputs, channel counts that are multiples of 32 but not powers of two
