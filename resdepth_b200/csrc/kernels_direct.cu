@@ -11,6 +11,18 @@
 
 namespace rd {
 
+// Packed fp32x2 FMA (FFMA2, sm_100): the two thin-end kernels of the network are issue-bound on CUDA cores, and one
+// FFMA2 does the work of two FFMAs.  Same rounding as fmaf per component.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+
 static constexpr int TH = 8, TW = 32;          // pixel tile of one block
 static constexpr int HALO_W = TW + 2, HALO_H = TH + 2;
 
@@ -339,10 +351,21 @@ conv_last_fwd64_kernel(const float* __restrict__ u, const float* __restrict__ w,
     load_group(g + 16, nx);                            // next iteration's rows are in flight during the butterfly
     float v[36];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4; ++i) {
+      const float2 ux = make_float2(uv[i].x, uv[i].x), uy = make_float2(uv[i].y, uv[i].y);
+      const float2 uz = make_float2(uv[i].z, uv[i].z), uw = make_float2(uv[i].w, uv[i].w);
 #pragma unroll
-      for (int k = 0; k < 9; ++k)
-        v[i * 9 + k] = fmaf(uv[i].x, wr[k].x, fmaf(uv[i].y, wr[k].y, fmaf(uv[i].z, wr[k].z, uv[i].w * wr[k].w)));
+      for (int k = 0; k < 8; k += 2) {                   // two tap slots per FFMA2, same summation order as the scalar form
+        float2 acc = make_float2(uv[i].w * wr[k].w, uv[i].w * wr[k + 1].w);
+        acc = ffma2(uz, make_float2(wr[k].z, wr[k + 1].z), acc);
+        acc = ffma2(uy, make_float2(wr[k].y, wr[k + 1].y), acc);
+        acc = ffma2(ux, make_float2(wr[k].x, wr[k + 1].x), acc);
+        v[i * 9 + k] = acc.x;
+        v[i * 9 + k + 1] = acc.y;
+      }
+      (void)uw;
+      v[i * 9 + 8] = fmaf(uv[i].x, wr[8].x, fmaf(uv[i].y, wr[8].y, fmaf(uv[i].z, wr[8].z, uv[i].w * wr[8].w)));
+    }
 #pragma unroll
     for (int j = 0; j < 18; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 18], 8);     // pixel pairs
 #pragma unroll
@@ -503,13 +526,16 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
             float4 d = make_float4(0, 0, 0, 0);
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
+              const float2 nk = make_float2(n[k], n[k]);
               if (MODE != 2) {
-                d.x = fmaf(n[k], wr[j][k].x, d.x); d.y = fmaf(n[k], wr[j][k].y, d.y);
-                d.z = fmaf(n[k], wr[j][k].z, d.z); d.w = fmaf(n[k], wr[j][k].w, d.w);
+                const float2 lo = ffma2(nk, make_float2(wr[j][k].x, wr[j][k].y), make_float2(d.x, d.y));
+                const float2 hi = ffma2(nk, make_float2(wr[j][k].z, wr[j][k].w), make_float2(d.z, d.w));
+                d = make_float4(lo.x, lo.y, hi.x, hi.y);
               }
               if (MODE != 1) {
-                dwacc[j][k].x = fmaf(uv.x, n[k], dwacc[j][k].x); dwacc[j][k].y = fmaf(uv.y, n[k], dwacc[j][k].y);
-                dwacc[j][k].z = fmaf(uv.z, n[k], dwacc[j][k].z); dwacc[j][k].w = fmaf(uv.w, n[k], dwacc[j][k].w);
+                const float2 lo = ffma2(make_float2(uv.x, uv.y), nk, make_float2(dwacc[j][k].x, dwacc[j][k].y));
+                const float2 hi = ffma2(make_float2(uv.z, uv.w), nk, make_float2(dwacc[j][k].z, dwacc[j][k].w));
+                dwacc[j][k] = make_float4(lo.x, lo.y, hi.x, hi.y);
               }
             }
             if (MODE == 2) continue;
