@@ -451,12 +451,14 @@ int launch_conv_last_fwd(const float* u, const float* w, const float* bias, cons
 // MODE 0: everything in one pass (default); MODE 1: du (+ its channel sums, db) only; MODE 2: dW only.  The split
 // pair (RESDEPTH_LAST_BWD_SPLIT=1) was tried against the fused pass's register pressure (126 registers, 2 CTAs per
 // SM, ncu: 37 % DRAM) and measured slower on B200: 0.29 + 0.34 ms against 0.55 ms.
+// pixel tile of one block iteration: large, so that the two block-wide barriers around the dy halo load amortise
+static constexpr int LB_TH = 32, LB_TW = 32, LB_HH = LB_TH + 2, LB_HW = LB_TW + 2;
 template <int QPL, int MODE>
 __global__ void __launch_bounds__(256, MODE == 0 ? 2 : 3)
 conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ w,
                      float* __restrict__ du, __nv_bfloat16* __restrict__ du_b, float* __restrict__ part, int B, int H,
                      int W, int C, int tiles_x, int tiles_y, int ntiles) {
-  __shared__ float dys[HALO_H * HALO_W];
+  __shared__ float dys[LB_HH * LB_HW];
   extern __shared__ float red_dyn[];                  // [16][RS]
   constexpr int NDW = 9 * 4 * 16 * QPL;               // weight-gradient entries, then 64*QPL channel sums of du, then db
   constexpr int RS = NDW + 4 * 16 * QPL + 1;
@@ -480,24 +482,24 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
     const int b = t / tiles_y;
-    const int h0 = ty * TH, w0 = tx * TW;
+    const int h0 = ty * LB_TH, w0 = tx * LB_TW;
     __syncthreads();
-    for (int i = tid; i < HALO_H * HALO_W; i += 256) {
-      const int hh = i / HALO_W, ww = i % HALO_W;
+    for (int i = tid; i < LB_HH * LB_HW; i += 256) {
+      const int hh = i / LB_HW, ww = i % LB_HW;
       const int gh = h0 + hh - 1, gw = w0 + ww - 1;
       dys[i] = (gh >= 0 && gh < H && gw >= 0 && gw < W) ? dy[((size_t)b * H + gh) * W + gw] : 0.f;
     }
     __syncthreads();
     // four pixels per iteration: their u loads are issued together (memory-level parallelism), then consumed
-    for (int p0 = grp; p0 < TH * TW; p0 += 64) {
+    for (int p0 = grp; p0 < LB_TH * LB_TW; p0 += 64) {
       float4 uvs[4][QPL];
       bool okp[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int p = p0 + 16 * i;
-        const int lh = p / TW, lw = p % TW;
+        const int lh = p / LB_TW, lw = p % LB_TW;
         const int gh = h0 + lh, gw = w0 + lw;
-        okp[i] = p < TH * TW && gh < H && gw < W;
+        okp[i] = p < LB_TH * LB_TW && gh < H && gw < W;
         const size_t o = (((size_t)b * H + gh) * W + gw) * C;
 #pragma unroll
         for (int j = 0; j < QPL; ++j) {
@@ -509,13 +511,13 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
       for (int i = 0; i < 4; ++i) {
         if (!okp[i]) continue;
         const int p = p0 + 16 * i;
-        const int lh = p / TW, lw = p % TW;
+        const int lh = p / LB_TW, lw = p % LB_TW;
         const int gh = h0 + lh, gw = w0 + lw;
         float n[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * HALO_W + (lw + 1 - (s2 - 1))];
+          for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * LB_HW + (lw + 1 - (s2 - 1))];
         if (MODE != 2 && lane16 == 0) dbacc += n[4];
         const size_t o = (((size_t)b * H + gh) * W + gw) * C;
 #pragma unroll
@@ -591,7 +593,7 @@ int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float*
                          float* dbias, float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W,
                          int C, cudaStream_t s) {
   if (C % 4 || C > 128) return fail("conv_last_bwd: unsupported C=%d", C);
-  const int tiles_x = cdiv(W, TW), tiles_y = cdiv(H, TH);
+  const int tiles_x = cdiv(W, LB_TW), tiles_y = cdiv(H, LB_TH);
   const int ntiles = tiles_x * tiles_y * B;
   int grid = ntiles < 148 * 4 ? ntiles : 148 * 4;
   const int PN = C * 10 + 1;
