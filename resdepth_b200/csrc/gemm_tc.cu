@@ -464,13 +464,18 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             tc_fence_after();
             const uint32_t sa_tap = sa + ((tap / 3) * HALO_W + (tap % 3)) * 128;
             const uint32_t sb = b_base + bslot * Cfg::B_BYTES;
+            // descriptors are built once per tap; (sub-tile, k) only add a constant to the 16-byte address field (no
+            // carry out of its 14 bits: shared memory ends below 256 KB) -- with N = 64 an MMA lasts 32 cycles, so the
+            // issuing thread's instruction count per MMA is what the tensor pipe waits for
+            const uint64_t da_tap = smem_desc_sw128(sa_tap, 16, HALO_W * 128);
+            const uint64_t db_tap = smem_desc_sw128(sb, 16, 1024);
             if (elect_one()) {
 #pragma unroll
               for (int sub = 0; sub < HALO_SUB; ++sub)
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {    // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
-                  const uint64_t da = smem_desc_sw128(sa_tap + sub * 8 * 128 + k * 32, 16, HALO_W * 128);
-                  const uint64_t db = smem_desc_sw128(sb + k * 32, 16, 1024);
+                  const uint64_t da = da_tap + (uint64_t)((sub * 8 * 128 + k * 32) >> 4);
+                  const uint64_t db = db_tap + (uint64_t)((k * 32) >> 4);
                   if (BF16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
                   else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
                 }
