@@ -1174,11 +1174,11 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sg = sa + 2 * Cfg::BOX_BYTES;
+        const uint64_t da0 = smem_desc_sw128(sa, Cfg::BOX_BYTES, 1024), dg0 = smem_desc_sw128(sg, Cfg::BOX_BYTES, 1024);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < Cfg::KP / 16; ++k)                    // 16 pixels = two 8-row swizzle atoms per MMA
-            mma_bf16(tmem_base, smem_desc_sw128(sa + k * 2048, Cfg::BOX_BYTES, 1024),
-                     smem_desc_sw128(sg + k * 2048, Cfg::BOX_BYTES, 1024), idesc, (i | k) != 0);
+            mma_bf16(tmem_base, da0 + (uint64_t)(k * (2048 >> 4)), dg0 + (uint64_t)(k * (2048 >> 4)), idesc, (i | k) != 0);
           tc_commit(&empty_bar[stage]);
           if (i == nsteps - 1) tc_commit(done_bar);
         }
