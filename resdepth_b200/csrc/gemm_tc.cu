@@ -57,10 +57,14 @@ struct RowsCfg {
   static_assert(!RING || (!HALO && (BN == 256 || BN == 128)), "skip-ring variant: plain 256/128-column tiles only");
   static_assert(!HALO || BN <= 128, "halo variant: two sub-tiles x two accumulator stages x BN columns <= 512");
   static constexpr int A_SLOTS = 2;                                  // halo variant: separate rings
-  static constexpr int B_SLOTS = (BN == 128) ? 6 : 8;
+  // halo variant: one weight slot = the tiles of 3 taps (one 3-D TMA, one barrier round trip per 24 MMAs: with N = 64 an
+  // MMA lasts 32 cycles and the per-tap wait / commit of the issuing warp was what the tensor pipe waited for)
+  static constexpr int B_TAPS = 3;
+  static constexpr int B_SLOT_BYTES = B_TAPS * B_BYTES;
+  static constexpr int B_SLOTS = (BN == 128) ? 2 : 4;
   static constexpr int SUB = HALO ? HALO_SUB : 1;                    // 128-row sub-tiles per CTA tile
   static constexpr int ACC_COLS = SUB * BN;                          // TMEM columns of one accumulator stage
-  static constexpr int DATA_BYTES = HALO ? A_SLOTS * HALO_SLOT + B_SLOTS * B_BYTES : STAGES * STAGE_BYTES;
+  static constexpr int DATA_BYTES = HALO ? A_SLOTS * HALO_SLOT + B_SLOTS * B_SLOT_BYTES : STAGES * STAGE_BYTES;
   static constexpr int NBAR_A = HALO ? A_SLOTS : STAGES;
   static constexpr int NBAR_B = HALO ? B_SLOTS : 0;
   static constexpr int TMEM_COLS = (2 * ACC_COLS < 32) ? 32 : 2 * ACC_COLS;
@@ -433,10 +437,11 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                         th_i * P.th - 1, tb_i);
             if (++slot == Cfg::A_SLOTS) { slot = 0; phase ^= 1; }
           } else {
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tg = 0; tg < 9 / Cfg::B_TAPS; ++tg) {      // mapB is 3-D here: (k inside the tap, n, tap)
               mbar_wait(&bempty_bar[slot], phase ^ 1);
-              mbar_arrive_expect_tx(&bfull_bar[slot], Cfg::B_BYTES);
-              tma_load_2d(bring + slot * Cfg::B_BYTES, &mapB, &bfull_bar[slot], (tap * P.cchunks + cc) * (BF16 ? 64 : 32), nt * BN);
+              mbar_arrive_expect_tx(&bfull_bar[slot], Cfg::B_SLOT_BYTES);
+              tma_load_3d(bring + slot * Cfg::B_SLOT_BYTES, &mapB, &bfull_bar[slot], cc * (BF16 ? 64 : 32), nt * BN,
+                          tg * Cfg::B_TAPS);
               if (++slot == Cfg::B_SLOTS) { slot = 0; phase ^= 1; }
             }
           }
@@ -459,29 +464,33 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int cc = 0; cc < P.cchunks; ++cc) {
           mbar_wait(&full_bar[aslot], aphase);
           const uint32_t sa = a_base + aslot * HALO_SLOT;
-          for (int tap = 0; tap < 9; ++tap) {
+          for (int tg = 0; tg < 9 / Cfg::B_TAPS; ++tg) {
             mbar_wait(&bfull_bar[bslot], bphase);
             tc_fence_after();
-            const uint32_t sa_tap = sa + ((tap / 3) * HALO_W + (tap % 3)) * 128;
-            const uint32_t sb = b_base + bslot * Cfg::B_BYTES;
             // descriptors are built once per tap; (sub-tile, k) only add a constant to the 16-byte address field (no
-            // carry out of its 14 bits: shared memory ends below 256 KB) -- with N = 64 an MMA lasts 32 cycles, so the
-            // issuing thread's instruction count per MMA is what the tensor pipe waits for
-            const uint64_t da_tap = smem_desc_sw128(sa_tap, 16, HALO_W * 128);
-            const uint64_t db_tap = smem_desc_sw128(sb, 16, 1024);
+            // carry out of its 14 bits: shared memory ends below 256 KB)
+            uint64_t da_tap[Cfg::B_TAPS], db_tap[Cfg::B_TAPS];
+#pragma unroll
+            for (int t = 0; t < Cfg::B_TAPS; ++t) {
+              const int tap = tg * Cfg::B_TAPS + t;
+              da_tap[t] = smem_desc_sw128(sa + ((tap / 3) * HALO_W + (tap % 3)) * 128, 16, HALO_W * 128);
+              db_tap[t] = smem_desc_sw128(b_base + bslot * Cfg::B_SLOT_BYTES + t * Cfg::B_BYTES, 16, 1024);
+            }
             if (elect_one()) {
 #pragma unroll
-              for (int sub = 0; sub < HALO_SUB; ++sub)
+              for (int t = 0; t < Cfg::B_TAPS; ++t)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {    // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
-                  const uint64_t da = da_tap + (uint64_t)((sub * 8 * 128 + k * 32) >> 4);
-                  const uint64_t db = db_tap + (uint64_t)((k * 32) >> 4);
-                  if (BF16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
-                  else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tap | k) != 0);
-                }
+                for (int sub = 0; sub < HALO_SUB; ++sub)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K: 8 fp32 (kind::tf32) or 16 bf16 (kind::f16)
+                    const uint64_t da = da_tap[t] + (uint64_t)((sub * 8 * 128 + k * 32) >> 4);
+                    const uint64_t db = db_tap[t] + (uint64_t)((k * 32) >> 4);
+                    if (BF16) mma_bf16(d_tmem + sub * BN, da, db, idesc, (cc | tg | t | k) != 0);
+                    else mma_tf32(d_tmem + sub * BN, da, db, idesc, (cc | tg | t | k) != 0);
+                  }
               tc_commit(&bempty_bar[bslot]);
-              if (tap == 8) tc_commit(&empty_bar[aslot]);
-              if (tap == 8 && cc == P.cchunks - 1) tc_commit(&tfull_bar[acc]);
+              if (tg == 9 / Cfg::B_TAPS - 1) tc_commit(&empty_bar[aslot]);
+              if (tg == 9 / Cfg::B_TAPS - 1 && cc == P.cchunks - 1) tc_commit(&tfull_bar[acc]);
             }
             __syncwarp();
             if (++bslot == Cfg::B_SLOTS) { bslot = 0; bphase ^= 1; }
@@ -793,7 +802,14 @@ int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B,
   const long long K = (long long)g.ntaps * g.C;
   long long wd[2] = {K, N}, ws[1] = {K * EB};
   int wb[2] = {P.kchunk, plan->BN};
-  RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb, 0, EB));
+  if (plan->halo) {
+    // weights [N][(tap, c)] as a 3-D tensor (c, n, tap): one box = the tiles of 3 consecutive taps, back to back
+    long long wd3[3] = {g.C, N, 9}, ws3[2] = {K * EB, (long long)g.C * EB};
+    int wb3[3] = {P.kchunk, plan->BN, 3};
+    RD_TRY(tc_encode_map(&plan->mapB, w_nk, 3, wd3, ws3, wb3, 0, EB));
+  } else {
+    RD_TRY(tc_encode_map(&plan->mapB, w_nk, 2, wd, ws, wb, 0, EB));
+  }
   plan->valid = true;
   return 0;
 }
