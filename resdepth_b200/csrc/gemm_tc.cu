@@ -536,6 +536,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint64_t da0 = smem_desc_sw128(smem_u32(smem), 16, 1024);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);
@@ -544,9 +545,9 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = smem_desc_sw128(sa + Cfg::A_BYTES, 16, 1024);
+          // stage descriptors differ only in the 16-byte address field (no carry: shared memory ends below 256 KB)
+          const uint64_t da = da0 + (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t db = da + (uint64_t)(Cfg::A_BYTES >> 4);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) { // 4 x 32 bytes of K (8 fp32 / 16 bf16) inside the 128-byte swizzle atom
