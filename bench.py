@@ -137,8 +137,10 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': tps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'ResDepth-stereo training step: 3-ch 256x256, depth 5, Adam+L1 (BASELINE configs[2])',
-                   'tiles_per_step': sample_tiles, 'device': 'host CPU'},
+        'config': {'workload': 'ResDepth-stereo training step: 3-ch 256x256, depth 5, batch 64/GPU, Adam+L1 '
+                               '(BASELINE configs[2]; configs[3] at 8 GPUs)',
+                   'tile': TILE, 'sample_tiles_per_step': sample_tiles, 'device': 'host CPU',
+                   'note': 'each step is a bounded sample of the 64-tile batch (same network, tile size, loss, optimizer)'},
         'cpu_baseline': {'value': tps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': f'{steps} train steps of {sample_tiles} tiles (of the 64-tile batch) after '
                                    f'{warmup} warm-up, oracle port of lib/UNet.py + lib/Trainer.py step + '
