@@ -114,3 +114,25 @@ def test_average_meter_and_denormalize_helpers():
     assert torch.equal(out[1], x[1] * 3 + 20)
     np.testing.assert_array_equal(denormalize_numpy(x, mean, std), out.numpy())
     assert torch.equal(denormalize_torch(x, 1.0, 2.0), x * 2 + 1)
+
+
+def test_epoch_prefetcher_keeps_order_and_stages_one_batch_ahead():
+    """Trainer._prefetched yields the loader's batches in order and has batch i+1 staged (its H2D copies enqueued)
+    before batch i is handed to the step -- checked with a recording stand-in for the CUDA staging."""
+    from resdepth_b200.lib.Trainer import Trainer
+    tr = Trainer.__new__(Trainer)
+    events = []
+
+    def fake_stage(batch):
+        events.append(('stage', batch))
+        return {'staged': batch}
+    tr._stage_batch = fake_stage
+    seen = []
+    for b in tr._prefetched(iter([10, 11, 12, 13])):
+        events.append(('step', b['staged']))
+        seen.append(b['staged'])
+    assert seen == [10, 11, 12, 13]
+    assert events == [('stage', 10), ('stage', 11), ('step', 10), ('stage', 12), ('step', 11), ('stage', 13),
+                      ('step', 12), ('step', 13)]
+    assert list(tr._prefetched(iter([]))) == []
+    assert [b['staged'] for b in tr._prefetched([7])] == [7]
