@@ -8,8 +8,13 @@
 //   * B tiles: TMA 2-D boxes (32 k x BN) of the packed weights [N][K] (K-major).
 //   * tcgen05.mma kind::tf32, M = 128, N = BN, K = 8 per instruction, fp32 accumulators in TMEM, two
 //     accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-//     (tcgen05.ld 32 lanes x 32 columns -> registers -> fused epilogue -> 128-byte row stores).
+//   * warp roles (384 threads): warp 0 = activation-TMA producer, warp 1 = TMEM allocator + MMA issuer, warp 2 =
+//     weight-TMA producer of the halo variant, warps 4..11 = epilogue (tcgen05.ld 32 lanes x 32 columns -> registers ->
+//     fused epilogue -> transposition through swizzled shared memory -> 128-byte row stores).
+//   * variants: HALO (3x3 layers with N <= 128: one 18 x 18 halo patch per channel chunk serves all nine taps and two
+//     sub-tiles; weight tiles of three taps per slot), RING (HBM-bound up-convs: skip rows by per-warp cp.async rings),
+//     BF16 (backward GEMMs, kind::f16).  The file also holds the reduce kernels (weight gradients, incl. the wide-N
+//     formulation) and the first-conv kernel (software im2col producer, 3xTF32).
 //   * persistent CTAs, static tile schedule with a fixed N tile per CTA so BatchNorm column sums accumulate in
 //     registers across all of a CTA's tiles (one partial row per CTA-warp instead of one per tile).
 #include <cuda.h>
