@@ -956,18 +956,27 @@ int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s) {
   return 0;
 }
 // part [S][Kc][Co] summed over S -> dW [Co][K] (K = Cin*9 <= Kc; OIHW flattening of the first conv)
-__global__ void unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co, int K,
-                                         int Kc) {
-  const int total = Co * K;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-    const int co = i % Co, k = i / Co;
-    float a = 0.f;
-    for (int sp = 0; sp < S; ++sp) a += part[((size_t)sp * Kc + k) * Co + co];
+// 32 consecutive outputs per block (coalesced 128-byte reads of every split), the splits spread over the 8 warps and
+// combined in a fixed order: the one-wave reduce GEMM of this layer produces ~148 splits of only Co*K values each
+__global__ void __launch_bounds__(256)
+unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co, int K, int Kc) {
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane, total = Co * K;
+  const int co = i % Co, k = i / Co;
+  float a = 0.f;
+  if (i < total)
+    for (int sp = w; sp < S; sp += 8) a += part[((size_t)sp * Kc + k) * Co + co];
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && i < total) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) a += red[j][lane];
     dw[(size_t)co * K + k] = a;
   }
 }
 int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s) {
-  unpack_first_grad_kernel<<<cdiv(Co * K, 256), 256, 0, s>>>(part, S, dw, Co, K, Kc);
+  unpack_first_grad_kernel<<<cdiv(Co * K, 32), 256, 0, s>>>(part, S, dw, Co, K, Kc);
   RD_LAUNCHED();
   return 0;
 }
