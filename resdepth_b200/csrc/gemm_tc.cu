@@ -82,14 +82,11 @@ struct RowsCfg {
 // one pixel); storing that directly makes every warp-level STG.128 touch 32 different 128-byte lines (32 L1 wavefronts
 // for 512 bytes).  The tile is therefore transposed through 4 KB of XOR-swizzled shared memory so that 8 lanes
 // cover one row: each warp-level access then touches 4 rows x 128 contiguous bytes (4 wavefronts).  `off` is the
-// element offset of the lane's row, `add` an optional tensor added element-wise at the same offsets (the additive
-// skip connection of the decoder).
+// element offset of the lane's row.  (The transposed-conv epilogues, which also add the skip tensor, have their own
+// versions of this: convt_epilogue / convt_ring_epilogue.)
 __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const float (&v)[32], float* __restrict__ out,
-                                                long long off, bool ok, const float* __restrict__ add, int rnd,
-                                                __nv_bfloat16* __restrict__ outb = nullptr,
-                                                const float* __restrict__ add_scale = nullptr,
-                                                const float* __restrict__ add_shift = nullptr,
-                                                const float* __restrict__ add_slope = nullptr) {
+                                                long long off, bool ok, int rnd,
+                                                __nv_bfloat16* __restrict__ outb = nullptr) {
   const uint32_t stg_s = smem_u32(stg);
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4)
@@ -107,29 +104,10 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
     okm |= (unsigned)__shfl_sync(0xffffffffu, (int)ok, r) << i;
     o[i] = (long long)(((unsigned long long)hi << 32) | lo) + c4 * 4;
   }
-  float4 a[8];
-  if (add) {                         // all eight loads in flight before any dependent store
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      a[i] = (okm >> i) & 1 ? __ldg(reinterpret_cast<const float4*>(add + o[i])) : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (add_scale) {                 // `add` is a raw conv output: BatchNorm + activation of its layer on the fly
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(add_scale) + c4);
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(add_shift) + c4);
-      const float sl = __ldg(add_slope);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float y0 = fmaf(a[i].x, sc.x, sh.x), y1 = fmaf(a[i].y, sc.y, sh.y);
-        float y2 = fmaf(a[i].z, sc.z, sh.z), y3 = fmaf(a[i].w, sc.w, sh.w);
-        a[i].x = y0 > 0.f ? y0 : y0 * sl; a[i].y = y1 > 0.f ? y1 : y1 * sl;
-        a[i].z = y2 > 0.f ? y2 : y2 * sl; a[i].w = y3 > 0.f ? y3 : y3 * sl;
-      }
-    }
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3);
     float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
-    if (add) { val.x += a[i].x; val.y += a[i].y; val.z += a[i].z; val.w += a[i].w; }
     if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
     if ((okm >> i) & 1) {
       if (out) *reinterpret_cast<float4*>(out + o[i]) = val;
@@ -626,7 +604,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             v[4 * j + 2] = y2 > 0.f ? y2 : y2 * slope;
             v[4 * j + 3] = y3 > 0.f ? y3 : y3 * slope;
           }
-          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, nullptr, P.round_tf32);
+          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32);
           if (P.pool_out) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -634,7 +612,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
               v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, P.tw));
             }
             const size_t pp = ((size_t)b * (P.Ho >> 1) + (h >> 1)) * (P.Wo >> 1) + (w >> 1);
-            warp_store_rows(stg, lane, v, P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1), nullptr,
+            warp_store_rows(stg, lane, v, P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1),
                             P.round_pool);
           }
         } else {
@@ -648,7 +626,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             cs1[ci] += warp_colsum32(sv, lane);
             cs2[ci] += warp_colsum32(sq, lane);
           }
-          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, nullptr, P.round_tf32,
+          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
                           reinterpret_cast<__nv_bfloat16*>(P.out_b));
         }
       }
@@ -1659,7 +1637,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
 #pragma unroll
           for (int j = 0; j < 32; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
         }
-        warp_store_rows(stg, lane, v, z, p * N + half * 32, valid, nullptr, 0);
+        warp_store_rows(stg, lane, v, z, p * N + half * 32, valid, 0);
       }
       tc_fence_before();
       __syncwarp();
