@@ -3,10 +3,13 @@
 
     python bench.py --gpus N --steps K --warmup W            # our CUDA path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+    python bench.py --impl cudnn --steps K ...               # the same network through stock PyTorch / cuDNN on the GPU
+    python bench.py --config cfg5 --gpus N ...               # BASELINE configs[4] as the headline workload
 
-Workload (N=1): BASELINE.json configs[2] -- ResDepth-stereo training step: 3-ch 256x256 tiles, U-Net depth 5,
+Workload (default): BASELINE.json configs[2] -- ResDepth-stereo training step: 3-ch 256x256 tiles, U-Net depth 5,
 batch 64 per GPU, Adam + masked L1; one "step" = forward + loss + backward (+ gradient all-reduce) + Adam.
-Metric: 256x256 3-ch DSM tiles/sec per train step, whole job (all ranks).  Weak scaling: 64 tiles per GPU.
+Metric: 256x256 3-ch DSM tiles/sec per train step, whole job (all ranks).  Weak scaling: 64 tiles per GPU
+(configs[3] = 8 GPUs, global batch 512).
 """
 from __future__ import annotations
 
@@ -25,10 +28,19 @@ if ROOT not in sys.path:
 
 METRIC = '256x256 3-ch DSM tiles/sec per train step'
 UNIT = 'tiles/s'
-MODEL_KW = dict(n_input_channels=3, start_kernel=64, depth=5, bias_conv_layer=True)
-TILE = 256
 N_INPUT_SETS = 4          # distinct resident batches cycled through (4 x 71 MB of inputs > 126 MB L2)
-TRAIN_GFLOP_PER_TILE = 59.165   # fwd + dgrad + wgrad, cfg A
+
+# name -> (constructor arguments, tile, default tiles per GPU, train GFLOP per tile, description)
+CONFIGS = {
+    'cfg3': (dict(n_input_channels=3, start_kernel=64, depth=5, bias_conv_layer=True), 256, 64, 59.165,
+             'ResDepth-stereo training step: 3-ch 256x256, depth 5, batch 64/GPU, Adam+L1 '
+             '(BASELINE configs[2]; configs[3] at 8 GPUs)'),
+    'cfg5': (dict(n_input_channels=3, start_kernel=64, depth=6, bias_conv_layer=True), 512, 32, 241.59,
+             'ResDepth-stereo_generalized training step: 3-ch 512x512, depth 6, batch 32/GPU, Adam+L1 '
+             '(BASELINE configs[4]: global batch 256 at 8 GPUs)'),
+    'cfg1': (dict(n_input_channels=1, start_kernel=64, depth=3, bias_conv_layer=True), 64, 4, 2.364,
+             'ResDepth-0 training step: 1-ch 64x64, depth 3, batch 4 (BASELINE configs[0]; launch-latency-bound)'),
+}
 
 
 def peaks():
@@ -93,58 +105,76 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def make_host_batches(B, C, T, seed, n_sets, pin=True):
+    """Synthetic batches of the SURVEY 8d recipe, generated on the host (e2e starts from pinned host memory)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_sets):
+        x = torch.randn(B, C, T, T, generator=g)
+        b = {'input': x, 'target': x[:, :1] + 0.1 * torch.randn(B, 1, T, T, generator=g),
+             'loss_mask': torch.rand(B, 1, T, T, generator=g) > 0.05,
+             'dsm_mean': torch.full((B,), 400.0), 'dsm_std': torch.full((B,), 3.5)}
+        out.append({k: (v.pin_memory() if pin else v) for k, v in b.items()})
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port of lib/UNet.py + lib/Trainer.py step + torch.optim.Adam)
 # --------------------------------------------------------------------------------------------------------
-def cpu_train_steps(batch_tiles: int, steps: int, warmup: int, threads: int):
-    """Times `steps` CPU train steps (after `warmup`) on `batch_tiles` tiles of the benchmark workload.
-    Returns (tiles/s, seconds per step).  Uses oracle/ only as the reported baseline."""
+def cpu_train_steps(cfg: str, batch_tiles: int, steps: int, warmup: int, threads: int, budget_s: float = 1e9):
+    """Times up to `steps` CPU train steps (after `warmup`) on `batch_tiles` tiles of the benchmark workload; stops
+    early once `budget_s` seconds of timed steps have run.  Returns (tiles/s, seconds per step, steps timed).
+    Uses oracle/ only as the reported baseline."""
     import torch
     from oracle import unet_oracle as O
     from resdepth_b200.lib.UNet import UNet           # parameter container only (ordinary nn modules on the CPU)
+    kw, tile = CONFIGS[cfg][0], CONFIGS[cfg][1]
     torch.set_num_threads(threads)
     torch.manual_seed(0)
-    model = UNet(**MODEL_KW)
+    model = UNet(**kw)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     pkeys = [k for k, _ in model.named_parameters()]
     for k in pkeys:
         sd[k].requires_grad_(True)
     opt = torch.optim.Adam([sd[k] for k in pkeys], lr=2e-4, weight_decay=1e-5)
-    spec = O.NetSpec(**MODEL_KW)
-    batch = O.synthetic_batch(batch_tiles, MODEL_KW['n_input_channels'], TILE)
+    spec = O.NetSpec(**kw)
+    batch = O.synthetic_batch(batch_tiles, kw['n_input_channels'], tile)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         O.train_step(sd, pkeys, batch, spec, opt)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
+            if sum(times) > budget_s:
+                break
     total = sum(times)
-    return batch_tiles * len(times) / total, total / len(times)
+    return batch_tiles * len(times) / total, total / len(times), len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
         return 0
+    kw, tile, default_b, _, workload = CONFIGS[args.config]
+    B = args.batch or default_b
     threads = os.cpu_count() or 1
-    sample_tiles = 8
-    steps, warmup = args.steps, max(1, min(args.warmup, 2))
-    # bound the run to a few minutes: a CPU step on 8 tiles takes 1-3 s
-    steps = max(1, min(steps, 20))
+    # full-size steps (the same 64-tile batch the GPU arm runs), the requested step / warm-up counts; the timed part is
+    # cut once it has used its share of "a few minutes" (a 64-tile CPU step takes ~4 s on the box's 16 cores)
+    steps, warmup = args.steps, args.warmup
     t0 = time.perf_counter()
-    tps, sec = cpu_train_steps(sample_tiles, steps, warmup, threads)
+    tps, sec, done = cpu_train_steps(args.config, B, steps, warmup, threads, budget_s=150.0)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': tps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'impl': 'reference', 'metric': METRIC, 'value': tps, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': done,
         'warmup': warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'ResDepth-stereo training step: 3-ch 256x256, depth 5, batch 64/GPU, Adam+L1 '
-                               '(BASELINE configs[2]; configs[3] at 8 GPUs)',
-                   'tile': TILE, 'sample_tiles_per_step': sample_tiles, 'device': 'host CPU',
-                   'note': 'each step is a bounded sample of the 64-tile batch (same network, tile size, loss, optimizer)'},
+        'config': {'workload': workload, 'tiles_per_gpu': B, 'global_batch': B, 'tile': tile, 'device': 'host CPU',
+                   'parallelism': f'{threads} host threads',
+                   'note': 'full-size steps of the GPU arm\'s batch on the host cores'
+                           + ('' if done == steps else f'; stopped after {done} of {steps} steps (150 s budget)')},
         'cpu_baseline': {'value': tps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                         'sample': f'{steps} train steps of {sample_tiles} tiles (of the 64-tile batch) after '
-                                   f'{warmup} warm-up, oracle port of lib/UNet.py + lib/Trainer.py step + '
-                                   'torch.optim.Adam on all host threads'},
+                         'sample': f'{done} train steps of {B} tiles after {warmup} warm-up, oracle port of '
+                                   'lib/UNet.py + lib/Trainer.py step + torch.optim.Adam on all host threads'},
         'e2e': {'value': tps, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'wall_s': time.perf_counter() - t0,
     }
@@ -153,16 +183,168 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------------
+# Library baseline on the same GPU: stock PyTorch modules (cuDNN convolutions) + torch.optim.Adam
+# --------------------------------------------------------------------------------------------------------
+def cudnn_numbers(cfg, B, steps, warmup, dev, resident=None, with_inference=True):
+    """tiles/s of baseline/torch_unet.py (never touches resdepth_b200's kernels) for both library variants."""
+    import torch
+    from baseline import torch_unet as TU
+    kw, tile = CONFIGS[cfg][0], CONFIGS[cfg][1]
+    mkw = dict(n_input_channels=kw['n_input_channels'], start_kernel=kw['start_kernel'], depth=kw['depth'])
+    if resident is None:
+        resident = [{k: v.to(dev) for k, v in hb.items()}
+                    for hb in make_host_batches(B, kw['n_input_channels'], tile, 1234, N_INPUT_SETS, pin=False)]
+    out = {'torch': torch.__version__, 'cudnn': torch.backends.cudnn.version(),
+           'allow_tf32_conv': bool(torch.backends.cudnn.allow_tf32), 'tiles_per_step': B, 'steps': steps,
+           'warmup': warmup, 'api': 'baseline/torch_unet.py: nn.Conv2d / BatchNorm2d / ReLU / MaxPool2d / '
+                                    'ConvTranspose2d modules, autograd, torch.optim.Adam (stock eager PyTorch)'}
+    for variant in ('fp32', 'bf16_channels_last'):
+        ms, loss = TU.time_train_steps(resident, steps, warmup, variant, mkw)
+        out[f'train_{variant}'] = {'value': B * steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'loss': loss}
+        torch.cuda.empty_cache()
+    if with_inference:
+        x = resident[0]['input'][:32].contiguous()
+        for variant in ('fp32', 'bf16_channels_last'):
+            ms = TU.time_inference(x, steps, warmup, variant, mkw)
+            out[f'inference_{variant}'] = {'value': x.shape[0] * steps / (ms * 1e-3), 'unit': UNIT, 'ms_per_call': ms / steps}
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_cudnn(args):
+    import torch
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py --impl cudnn needs a CUDA device')
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    kw, tile, default_b, _, workload = CONFIGS[args.config]
+    B = args.batch or default_b
+    sampler = ClockSampler(0)
+    sampler.start()
+    nums = cudnn_numbers(args.config, B, args.steps, max(args.warmup, 3), dev)
+    clocks = sampler.stop()
+    best = max(nums['train_fp32']['value'], nums['train_bf16_channels_last']['value'])
+    line = {'impl': 'cudnn', 'metric': METRIC, 'value': best, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': B / best * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'tf32 (fp32 variant) / bf16 autocast (channels_last variant)',
+            'data': 'synthetic', 'config': {'workload': workload, 'tiles_per_gpu': B, 'tile': tile,
+                                            'note': 'value = the faster of the two library variants'},
+            'clocks': clocks, 'cudnn_baseline': nums}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
+def roofline_of(prof, K, pk, math_name, traffic_key_prefix=''):
+    """Roofline block of the dominant kernel category of a per-category profile (rd_profile_*)."""
+    cats = {k: v for k, v in prof.items() if v['calls'] > 0}
+    total_ms = sum(v['ms'] for v in cats.values())
+    dom_name, dom = max(cats.items(), key=lambda kv: kv[1]['ms'])
+    gemm_like = dom['flops'] > 0 and dom['flops'] / max(dom['bytes'], 1.0) > 50.0
+    if gemm_like:
+        achieved = dom['flops'] / (dom['ms'] * 1e-3) / 1e12
+        roof = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
+                'peak_note': f"bf16 cuBLAS sustained ({pk['source']}); this kernel computes in "
+                             f"{math_name.split(' ')[0]}: the tf32 tensor ceiling is half of it"}
+    else:
+        achieved = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
+        roof = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_note': f"copy bandwidth ({pk['source']})"}
+    roof.update(kernel=dom_name, launches_per_step=dom['launches'] / K, avg_launch_ms=dom['ms'] / max(dom['launches'], 1),
+                share_of_step=dom['ms'] / max(total_ms, 1e-9),
+                algorithmic_per_step={'gflop': dom['flops'] / K / 1e9, 'mbytes': dom['bytes'] / K / 1e6})
+    traffic_path = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.isfile(traffic_path):
+        with open(traffic_path) as fh:
+            roof['traffic'] = json.load(fh).get(traffic_key_prefix + dom_name)
+    breakdown = {k: round(v['ms'] / K, 4) for k, v in sorted(cats.items(), key=lambda kv: -kv[1]['ms'])}
+    # every memory-bound category against the HBM roofline, every contraction against the tensor ceiling
+    fracs = {}
+    for k, v in cats.items():
+        if v['ms'] <= 0:
+            continue
+        if v['flops'] > 0 and v['flops'] / max(v['bytes'], 1.0) > 50.0:
+            fracs[k] = {'tflops': round(v['flops'] / (v['ms'] * 1e-3) / 1e12, 1),
+                        'frac_of_bf16_sustained': round(v['flops'] / (v['ms'] * 1e-3) / 1e12 / pk['bf16_tflops_sustained'], 3)}
+        elif v['bytes'] > 0:
+            fracs[k] = {'gbs': round(v['bytes'] / (v['ms'] * 1e-3) / 1e9, 0),
+                        'frac_of_hbm': round(v['bytes'] / (v['ms'] * 1e-3) / 1e9 / pk['hbm_gbs'], 3)}
+    return roof, breakdown, total_ms, fracs
+
+
+class Arm:
+    """One model + Trainer on this rank's GPU with resident and host copies of its synthetic batches."""
+
+    def __init__(self, cfg, B, dev, rank, backward_math='auto', n_sets=N_INPUT_SETS, pin=True):
+        import logging
+        from types import SimpleNamespace
+
+        import torch
+
+        from resdepth_b200.lib.Trainer import Trainer
+        from resdepth_b200.lib.UNet import UNet
+        kw, tile = CONFIGS[cfg][0], CONFIGS[cfg][1]
+        self.cfg, self.B, self.T, self.dev = cfg, B, tile, dev
+        torch.manual_seed(0)
+        self.model = UNet(**kw)
+        self.model.backward_math = backward_math
+        opt = torch.optim.Adam(self.model.parameters(), lr=2e-4, weight_decay=1e-5)       # lib/utils.py:329-331
+        # every rank draws its own tiles (seed 1234 + rank): the loaders below are already per-rank shards, so the
+        # Trainer's batch partition is switched off (it is exercised by tests/dist_gpu_check.py)
+        self.host = make_host_batches(B, kw['n_input_channels'], tile, 1234 + rank, n_sets, pin=pin)
+        args_tr = SimpleNamespace(trainloader=[self.host[0]], valloader=[self.host[0]], model=self.model, optimizer=opt,
+                                  scheduler=None, criterion=torch.nn.L1Loss(reduction='mean'), n_epochs=1,
+                                  evaluate_rate=1, save_model_rate=1, freq_average_train_loss=20, save_dir='',
+                                  log_file=None, checkpoint_dir='', tboard_log_dir=None, pretrained_path=None)
+        logging.getLogger('train_logger').addHandler(logging.NullHandler())
+        logging.getLogger('train_logger').propagate = False
+        self.tr = Trainer.__new__(Trainer)
+        _init_quiet(self.tr, args_tr, dev)
+        self.tr.shard_batches = {'train': False, 'val': False}
+        self.model.train()
+        self.resident = [{k: v.to(dev) for k, v in hb.items()} for hb in self.host]
+        self.handle = self.model.native_handle(dev)
+
+    def device_step(self, i):
+        b = self.resident[i % len(self.resident)]
+        loss = self.tr.device_step(b['input'], b['target'], b['loss_mask'], b['dsm_mean'], b['dsm_std'], True)
+        self.tr.optimizer.step()
+        return loss
+
+    def e2e_step(self, i):
+        stats = self.tr.inference_one_batch(self.host[i % len(self.host)], 'train')
+        self.tr.optimizer.step()
+        return stats['MAE_metric']
+
+    def e2e_epoch(self, K):
+        self.tr.loader['train'] = [self.host[j % len(self.host)] for j in range(K)]
+        return self.tr.inference_one_epoch(0, 'train')['MAE_metric'].avg
+
+    def h2d_bytes(self):
+        hb = self.host[0]
+        return sum(hb[k].numel() * hb[k].element_size() for k in ('input', 'target', 'loss_mask', 'dsm_mean', 'dsm_std'))
+
+    def close(self):
+        import torch
+        self.tr._graphs.clear()
+        self.model._rt['handle'].close()
+        self.model._rt.clear()
+        del self.resident, self.host
+        torch.cuda.empty_cache()
+
+
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from types import SimpleNamespace
 
     from resdepth_b200 import _native
-    from resdepth_b200.lib.Trainer import Trainer
-    from resdepth_b200.lib.UNet import UNet
+    from resdepth_b200.lib.distributed import replicas_identical
 
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank = int(os.environ.get('RANK', 0))
@@ -175,49 +357,15 @@ def run_native(args):
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    B, T, C = args.batch, TILE, MODEL_KW['n_input_channels']
-
-    torch.manual_seed(0)
-    model = UNet(**MODEL_KW)
-    opt = torch.optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)       # lib/utils.py:329-331
-    # synthetic inputs (SURVEY 8d recipe), generated on the host so e2e can start from pinned host memory
-    g = torch.Generator().manual_seed(1234 + rank)
-    host = []
-    for _ in range(N_INPUT_SETS):
-        x = torch.randn(B, C, T, T, generator=g)
-        host.append({'input': x.pin_memory(), 'target': (x[:, :1] + 0.1 * torch.randn(B, 1, T, T, generator=g)).pin_memory(),
-                     'loss_mask': (torch.rand(B, 1, T, T, generator=g) > 0.05).pin_memory(),
-                     'dsm_mean': torch.full((B,), 400.0).pin_memory(), 'dsm_std': torch.full((B,), 3.5).pin_memory()})
-    args_tr = SimpleNamespace(trainloader=[host[0]], valloader=[host[0]], model=model, optimizer=opt, scheduler=None,
-                              criterion=torch.nn.L1Loss(reduction='mean'), n_epochs=1, evaluate_rate=1,
-                              save_model_rate=1, freq_average_train_loss=20, save_dir='', log_file=None,
-                              checkpoint_dir='', tboard_log_dir=None, pretrained_path=None)
-    import logging
-    logging.getLogger('train_logger').addHandler(logging.NullHandler())
-    logging.getLogger('train_logger').propagate = False
-    tr = Trainer.__new__(Trainer)
-    _init_quiet(tr, args_tr, dev)
-    model.train()
-    resident = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
-    handle = model.native_handle(dev)
-
-    def device_step(i):
-        b = resident[i % N_INPUT_SETS]
-        loss = tr.device_step(b['input'], b['target'], b['loss_mask'], b['dsm_mean'], b['dsm_std'], True)
-        tr.optimizer.step()
-        return loss
-
-    def e2e_step(i):
-        stats = tr.inference_one_batch(host[i % N_INPUT_SETS], 'train')
-        tr.optimizer.step()
-        return stats['MAE_metric']
+    kw, T, default_b, gflop_per_tile, workload = CONFIGS[args.config]
+    B, C = args.batch or default_b, kw['n_input_channels']
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, profile=False):
+    def timed(fn, steps, warmup, arm=None, profile=False):
         for i in range(warmup):
             fn(i)
         barrier()
@@ -225,8 +373,10 @@ def run_native(args):
         if rank == 0:
             sampler.start()
         if profile:
-            handle.profile_enable(True)
+            arm.handle.profile_enable(True)
         _native.launch_count(reset=True)
+        if arm is not None:
+            arm.tr.replayed_kernels = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
@@ -235,10 +385,10 @@ def run_native(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = _native.launch_count()
-        prof = handle.profile_read() if profile else None
+        launches = _native.launch_count() + (arm.tr.replayed_kernels if arm is not None else 0)
+        prof = arm.handle.profile_read() if profile else None
         if profile:
-            handle.profile_enable(False)
+            arm.handle.profile_enable(False)
         clocks = sampler.stop() if rank == 0 else None
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -247,85 +397,111 @@ def run_native(args):
         return ms, launches, prof, clocks, last
 
     K, W = args.steps, max(args.warmup, 3)
-    # secondary figure (BASELINE configs[1]): eval-mode forward only, 32 tiles per call, device-resident inputs
-    infer_x = resident[0]['input'][:32].contiguous()
+    main = Arm(args.config, B, dev, rank)
+    model, tr, handle = main.model, main.tr, main.handle
+    math_name, bwd_name = handle.math_mode_name(), handle.bwd_mode_name()
+    extras = {}
 
-    def infer_step(i):
-        model.eval()
-        with torch.no_grad():
-            return model(infer_x)
-    infer_ms, _, _, _, _ = timed(infer_step, K, W)
-    model.train()
-    # tier-next figure: the on-device tile producer that feeds the step (DsmOrthoDataset.__getitem__
-    # for 64 tiles per call: geom-stereo, 4 views on a 4096x4096 raster, random positions / pairs / rot90 / flips)
-    from resdepth_b200.lib.tiles import DeviceTileProducer
-    g = torch.Generator(device=dev).manual_seed(11)
-    R = 4096
-    prod = DeviceTileProducer.from_device(
-        400.0 + 3.0 * torch.randn(R, R, device=dev, generator=g), 400.0 + 3.0 * torch.randn(R, R, device=dev, generator=g),
-        100.0 + 30.0 * torch.randn(4, R, R, device=dev, generator=g), -9999.0, T, 'geom-stereo', [[0, 1], [2, 3], [1, 3]],
-        None, 3.5, None, 40.0, permute_images_within_pair=True)
+    # ---- secondary figure (BASELINE configs[1]): eval-mode forward only, 32 tiles per call, device-resident inputs
+    if args.config == 'cfg3':
+        infer_x = main.resident[0]['input'][:32].contiguous()
 
-    def producer_step(i):
-        return prod.sample_batch(B)['input']
-    prod_ms, _, _, _, _ = timed(producer_step, K, W)
-    del prod
-    # headline pass: no profiling events, weight gradients overlapped on the side stream
-    ms, launches, _, clocks, last_loss = timed(device_step, K, W)
+        def infer_step(i):
+            model.eval()
+            with torch.no_grad():
+                return model(infer_x)
+        infer_ms, _, _, _, _ = timed(infer_step, K, W)
+        _, _, infer_prof, _, _ = timed(infer_step, K, 2, arm=main, profile=True)
+        model.train()
+        if rank == 0:
+            iroof, ibreak, itotal, _ = roofline_of(infer_prof, K, peaks(), math_name, 'inference:')
+            extras['inference'] = {
+                'workload': 'BASELINE configs[1]: eval-mode forward, 3-ch 256x256, depth 5, batch 32/GPU',
+                'value': 32 * world * K / (infer_ms * 1e-3), 'unit': UNIT, 'ms_per_call': infer_ms / K,
+                'gflop_per_tile': 19.797, 'tflops': 32 * K / (infer_ms * 1e-3) * 19.797 / 1e3,
+                'roofline': iroof, 'kernel_ms_per_call': ibreak, 'kernel_ms_total_per_call': itotal / K}
+        # tier-next figure: the on-device tile producer that feeds the step
+        from resdepth_b200.lib.tiles import DeviceTileProducer
+        g = torch.Generator(device=dev).manual_seed(11)
+        R = 4096
+        prod = DeviceTileProducer.from_device(
+            400.0 + 3.0 * torch.randn(R, R, device=dev, generator=g), 400.0 + 3.0 * torch.randn(R, R, device=dev, generator=g),
+            100.0 + 30.0 * torch.randn(4, R, R, device=dev, generator=g), -9999.0, T, 'geom-stereo', [[0, 1], [2, 3], [1, 3]],
+            None, 3.5, None, 40.0, permute_images_within_pair=True)
+        prod_ms, _, _, _, _ = timed(lambda i: prod.sample_batch(B)['input'], K, W)
+        del prod
+        extras['tile_producer'] = {'workload': 'rd_make_tiles: 64 geom-stereo 256x256 training tiles per call from a '
+                                               '4096x4096 raster with 4 views (host-drawn positions / pairs / rot90 / flips)',
+                                   'value': B * world * K / (prod_ms * 1e-3), 'unit': UNIT, 'ms_per_call': prod_ms / K}
+
+    # ---- headline pass: the product path (CUDA-graph replay of forward + loss + backward, weight gradients on the
+    # side stream, all-reduce slices overlapped), no profiling events
+    ms, launches, _, clocks, last_loss = timed(main.device_step, K, W, arm=main)
     loss_value = float(last_loss.item())
-    # per-kernel pass (roofline, breakdown): CUDA events around every kernel category; the side stream is switched off
-    # so that each category is timed alone (concurrent kernels would inflate one another's brackets)
+    identical, checksum = replicas_identical(model._rt['arena'], device=dev)
+    # ---- per-kernel pass (roofline, breakdown): eager launches with CUDA events around every kernel category; the side
+    # stream is switched off so that each category is timed alone
+    tr.use_graphs = False
     handle.set_overlap(False)
-    prof_ms, _, prof, _, _ = timed(device_step, K, 2, profile=True)
+    prof_ms, _, prof, _, _ = timed(main.device_step, K, 2, arm=main, profile=True)
     handle.set_overlap(True)
-    # end to end through the public API the reference's train.py drives: Trainer.inference_one_epoch over a loader of
-    # K pinned HOST batches (per step: H2D copies of that step's inputs -- enqueued one batch ahead so they overlap
-    # the previous step's compute --, forward, loss, backward, optimizer.step, D2H of the loss, consumed by the host
-    # one iteration later so the GPU never waits for the host).  The un-pipelined
-    # per-call figure (inference_one_batch on a host batch: copy, then compute) is kept beside it.
-    def e2e_epoch(i):
-        tr.loader['train'] = [host[j % N_INPUT_SETS] for j in range(K)]
-        return tr.inference_one_epoch(0, 'train')['MAE_metric'].avg
-    e2e_call_ms, _, _, _, _ = timed(e2e_step, K, 2)
-    e2e_ms, _, _, e2e_clocks, _ = timed(e2e_epoch, 1, 1)
+    eager_ms, eager_launches, _, _, _ = timed(main.device_step, K, 2, arm=main)
+    tr.use_graphs = True
+    # ---- end to end through the public API the reference's train.py drives: Trainer.inference_one_epoch over a loader
+    # of K pinned HOST batches (per step: H2D of that step's inputs into a static staging set -- enqueued one batch
+    # ahead so it overlaps the previous step's compute --, graph replay, optimizer.step, 4-byte D2H of the loss, read
+    # by the host one iteration later).  The un-pipelined per-call figure (inference_one_batch) is kept beside it.
+    e2e_call_ms, _, _, _, _ = timed(main.e2e_step, K, 3, arm=main)
+    e2e_ms, _, _, e2e_clocks, _ = timed(lambda i: main.e2e_epoch(K), 1, 1, arm=main)
     tiles = B * world * K
     value = tiles / (ms * 1e-3)
     e2e_value = tiles / (e2e_ms * 1e-3)
-    hb = host[0]
-    h2d = sum(hb[k].numel() * hb[k].element_size() for k in ('input', 'target', 'loss_mask', 'dsm_mean', 'dsm_std'))
+    h2d = main.h2d_bytes()
+
+    # ---- the other backward precision, the other configs, the library baseline (one GPU each, rank-local)
+    if args.config == 'cfg3' and not args.quick:
+        main.close()
+        alt = Arm('cfg3', B, dev, rank, backward_math='tf32')
+        alt_ms, _, _, _, _ = timed(alt.device_step, K, W, arm=alt)
+        extras['value_tf32_bwd'] = {'value': tiles / (alt_ms * 1e-3), 'unit': UNIT, 'ms_per_step': alt_ms / K,
+                                    'note': "model.backward_math = 'tf32': TF32 operands in every backward GEMM "
+                                            "(what cuDNN's autograd would use), same step otherwise"}
+        alt.close()
+        for other in ('cfg5', 'cfg1'):
+            okw, oT, oB, ogf, odesc = CONFIGS[other]
+            arm = Arm(other, oB, dev, rank, n_sets=2)
+            oms, ol, _, _, _ = timed(arm.device_step, K, W, arm=arm)
+            arm.tr.use_graphs = False
+            oms_eager, _, _, _, _ = timed(arm.device_step, K, 2, arm=arm)
+            arm.tr.use_graphs = True
+            oe2e, _, _, _, _ = timed(lambda i: arm.e2e_epoch(K), 1, 1, arm=arm)
+            extras[other] = {'workload': odesc, 'value': oB * world * K / (oms * 1e-3), 'unit': f'{oT}x{oT} tiles/s',
+                             'ms_per_step': oms / K, 'step_tflops': oB * K / (oms * 1e-3) * ogf / 1e3,
+                             'eager_launch_value': oB * world * K / (oms_eager * 1e-3),
+                             'e2e': oB * world * K / (oe2e * 1e-3), 'gpu_launches': ol, 'tiles_per_gpu': oB}
+            arm.close()
+    if rank == 0 and world == 1 and not args.no_cudnn and not args.quick:
+        extras['cudnn_baseline'] = cudnn_numbers(args.config, B, max(5, K // 2), 3, dev)
+        best = max(extras['cudnn_baseline']['train_fp32']['value'], extras['cudnn_baseline']['train_bf16_channels_last']['value'])
+        extras['vs_cudnn'] = {'train_vs_fp32_tf32': value / extras['cudnn_baseline']['train_fp32']['value'],
+                              'train_vs_bf16_channels_last': value / extras['cudnn_baseline']['train_bf16_channels_last']['value'],
+                              'train_vs_best': value / best}
+        if 'inference' in extras:
+            ib = max(extras['cudnn_baseline']['inference_fp32']['value'], extras['cudnn_baseline']['inference_bf16_channels_last']['value'])
+            extras['vs_cudnn']['inference_vs_best'] = extras['inference']['value'] / ib
 
     if rank == 0:
         pk = peaks()
-        adam_ms = None
-        cats = {k: v for k, v in prof.items() if v['calls'] > 0}
-        total_ms = sum(v['ms'] for v in cats.values())
-        dom_name, dom = max(cats.items(), key=lambda kv: kv[1]['ms'])
-        gemm_like = dom['flops'] > 0 and dom['flops'] / max(dom['bytes'], 1.0) > 50.0
-        if gemm_like:
-            achieved = dom['flops'] / (dom['ms'] * 1e-3) / 1e12
-            roof = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                    'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
-                    'peak_note': f"bf16 cuBLAS sustained ({pk['source']}); this kernel computes in "
-                                 f"{handle.math_mode_name().split(' ')[0]}: tf32 tensor ceiling is half of it"}
-        else:
-            achieved = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
-            roof = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': achieved / pk['hbm_gbs'], 'traffic': None, 'peak_note': f"copy bandwidth ({pk['source']})"}
-        roof.update(kernel=dom_name, launches_per_step=dom['launches'] / K, avg_launch_ms=dom['ms'] / max(dom['launches'], 1),
-                    share_of_step=dom['ms'] / max(total_ms, 1e-9),
-                    algorithmic_per_step={'gflop': dom['flops'] / K / 1e9, 'mbytes': dom['bytes'] / K / 1e6})
-        traffic_path = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.isfile(traffic_path):
-            with open(traffic_path) as fh:
-                roof['traffic'] = json.load(fh).get(dom_name)
-        breakdown = {k: round(v['ms'] / K, 4) for k, v in sorted(cats.items(), key=lambda kv: -kv[1]['ms'])}
+        roof, breakdown, total_ms, fracs = roofline_of(prof, K, pk, math_name)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'tf32' if 'tf32' in handle.math_mode_name() else 'f32', 'data': 'synthetic',
-            'config': {'workload': 'ResDepth-stereo training step: 3-ch 256x256, depth 5, batch 64/GPU, Adam+L1 '
-                                   '(BASELINE configs[2]; configs[3] at 8 GPUs)',
-                       'tiles_per_gpu': B, 'global_batch': B * world, 'tile': T, 'parallelism': f'dp{world}',
+            'dtype': ('f32' if 'tf32' not in math_name else
+                      f'tf32 fwd / {bwd_name} bwd (tcgen05 operands; fp32 accumulation, fp32 parameters and activations)'),
+            'data': 'synthetic',
+            'config': {'workload': workload, 'tiles_per_gpu': B, 'global_batch': B * world, 'tile': T,
+                       'parallelism': f'dp{world}',
+                       'sharding': 'rank r draws its own tiles (seed 1234 + r): per-rank loaders, Trainer batch partition off',
                        'l2': f'{N_INPUT_SETS} resident input sets cycled (inputs {N_INPUT_SETS * h2d / 1e6:.0f} MB and '
                              '~11 GB of activations per step exceed the 126 MB L2); no explicit flush'},
             'clocks': clocks,
@@ -338,26 +514,27 @@ def run_native(args):
                                              'api': 'Trainer.inference_one_batch(host batch) + optimizer.step'},
                     'clocks': e2e_clocks},
             'gpu_launches': launches,
+            'host_launches_per_step': 'CUDA-graph replays + Adam (+ all-reduce slices); see eager_launch',
+            'eager_launch': {'value': tiles / (eager_ms * 1e-3), 'unit': UNIT, 'kernel_launches': eager_launches,
+                             'note': 'RESDEPTH_GRAPHS=0: every kernel launched from the host'},
+            'replicas': {'identical_after_steps': identical, 'param_checksum': checksum},
             'roofline': roof,
-            'step_tflops': value * TRAIN_GFLOP_PER_TILE / 1e3,
+            'step_tflops': value * gflop_per_tile / 1e3,
             'kernel_ms_per_step': breakdown,
+            'kernel_roofline_fracs': fracs,
             'kernel_ms_total_per_step': total_ms / K,
-            'kernel_ms_note': f'separate pass of {K} steps with per-category CUDA events and the weight-gradient side '
-                              f'stream off ({prof_ms / K:.3f} ms per step); the headline pass has neither',
+            'kernel_ms_note': f'separate pass of {K} steps with per-category CUDA events, eager launches and the '
+                              f'weight-gradient side stream off ({prof_ms / K:.3f} ms per step); the headline pass has none',
             'loss': loss_value,
-            'inference': {'workload': 'BASELINE configs[1]: eval-mode forward, 3-ch 256x256, depth 5, batch 32/GPU',
-                          'value': 32 * world * K / (infer_ms * 1e-3), 'unit': UNIT, 'ms_per_call': infer_ms / K},
-            'tile_producer': {'workload': 'rd_make_tiles: 64 geom-stereo 256x256 training tiles per call from a 4096x4096 '
-                                          'raster with 4 views (host-drawn positions / pairs / rot90 / flips included)',
-                              'value': B * world * K / (prod_ms * 1e-3), 'unit': UNIT, 'ms_per_call': prod_ms / K},
         }
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            tps, sec = cpu_train_steps(8, 3, 1, threads)
+            tps, sec, done = cpu_train_steps(args.config, B, 3, 1, threads, budget_s=25.0)
             line['cpu_baseline'] = {'value': tps, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                    'sample': '3 train steps of 8 tiles after 1 warm-up (oracle port of lib/UNet.py + '
+                                    'sample': f'{done} train steps of {B} tiles after 1 warm-up (oracle port of lib/UNet.py + '
                                               'lib/Trainer.py step + torch.optim.Adam, all host threads); '
-                                              f'{sec:.2f} s per 8-tile step'}
+                                              f'{sec:.2f} s per {B}-tile step'}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -387,6 +564,7 @@ def _init_quiet(tr, args, dev):
     tr.loader = {'train': args.trainloader, 'val': args.valloader}
     tr.best_loss = math.inf
     tr.freq_average_train_loss = 20
+    tr._init_runtime()
 
 
 def main():
@@ -394,12 +572,17 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', choices=['native', 'reference'], default='native')
-    ap.add_argument('--batch', type=int, default=64, help='tiles per GPU per step')
+    ap.add_argument('--impl', choices=['native', 'reference', 'cudnn'], default='native')
+    ap.add_argument('--config', choices=list(CONFIGS), default='cfg3')
+    ap.add_argument('--batch', type=int, default=0, help='tiles per GPU per step (default: the config\'s)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cudnn', action='store_true')
+    ap.add_argument('--quick', action='store_true', help='headline workload only (no extra configs / baselines)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
+    if args.impl == 'cudnn':
+        return run_cudnn(args)
     return run_native(args)
 
 

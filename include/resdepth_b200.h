@@ -26,13 +26,15 @@
 extern "C" {
 #endif
 
-#define RD_ABI_VERSION 2
+#define RD_ABI_VERSION 3
 
 typedef struct rd_handle rd_handle;
 
 enum { RD_ACT_RELU = 0, RD_ACT_LRELU = 1, RD_ACT_PRELU = 2 };      /* lib/UNet.py:27-33 */
 enum { RD_MATH_FP32 = 0, RD_MATH_TF32 = 1 };  /* CUDA-core fp32 FMA | tcgen05 kind::tf32 */
 enum { RD_UP_TRANSPOSE = 0, RD_UP_BILINEAR = 1 };                  /* lib/UNet.py:17-24 */
+/* operand type of the backward GEMMs in RD_MATH_TF32 mode: AUTO = bf16 unless the environment says RESDEPTH_BWD=tf32 */
+enum { RD_BWD_AUTO = 0, RD_BWD_TF32 = 1, RD_BWD_BF16 = 2 };
 /* rd_forward modes: model.eval() under no_grad | model.train() | model.eval() with autograd recording */
 enum { RD_FWD_EVAL = 0, RD_FWD_TRAIN = 1, RD_FWD_EVAL_SAVE = 2 };
 
@@ -49,6 +51,8 @@ typedef struct rd_config {
   int32_t outer_skip_bn;      /* BatchNorm2d(1) on input channel 0 before the outer residual, lib/UNet.py:192-193 */
   int32_t math_mode;          /* RD_MATH_* for the GEMM-shaped layers */
   int32_t up_mode;            /* RD_UP_* */
+  int32_t bwd_mode;           /* RD_BWD_*: the reference's autograd computes gradients in fp32/TF32 (lib/Trainer.py:179);
+                                 bf16 operands (fp32 accumulation) are this library's faster default */
 } rd_config;
 
 int rd_abi_version(void);
@@ -71,9 +75,15 @@ int64_t rd_buffer_arena_size(const rd_handle* h);
 /* Borrow the caller's arenas (replaces nn.Module parameter/buffer storage and param.grad). */
 int rd_bind(rd_handle* h, float* params, float* grads, float* bn_buffers);
 
-/* Grow the workspace for batches of up to `batch` tiles of `tile` x `tile` pixels. */
+/* Select (building it on first use) the workspace layout for batches of `batch` tiles of `tile` x `tile` pixels.
+ * A handle keeps up to four layouts alive (training batch, validation batch, a partial last batch ...), so that
+ * alternating shapes costs neither a device synchronisation nor a rebuild of the TMA descriptors; the least
+ * recently used one is freed beyond that.  rd_workspace_id: id (> 0) of the current layout; rd_workspace_alive:
+ * whether the layout with that id still exists -- what a caller that replays a CUDA graph captured on it checks. */
 int rd_reserve(rd_handle* h, int batch, int tile, int with_backward);
 int64_t rd_workspace_bytes(const rd_handle* h);
+int64_t rd_workspace_id(const rd_handle* h);
+int rd_workspace_alive(const rd_handle* h, int64_t id);
 
 /* UNet.forward (lib/UNet.py:196-246).  x: [B,C,T,T] fp32 NCHW, y: [B,1,T,T].
  * mode RD_FWD_TRAIN: BatchNorm uses batch statistics, updates running stats in the bound buffer
@@ -92,6 +102,15 @@ int rd_loss(rd_handle* h, const float* y_pred, const float* target, const uint8_
  * parameters, written (not accumulated) into the bound gradient arena.  x is the input of the
  * matching rd_forward call (needed for the first layer's weight gradient). */
 int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream);
+
+/* The same backward pass in three consecutive stages, so that a data-parallel caller can start the gradient
+ * all-reduce of one stage (lib/Trainer.py has none: the reference is single-device) while the next
+ * stage computes.  Stage 0: last_layer + decoder; 1: bottleneck + deepest encoder level; 2: remaining encoder
+ * levels.  Call 0, 1, 2 in order after one saving rd_forward; when a stage returns, `stream` is ordered after
+ * every gradient of that stage.  rd_grad_stage_range: the contiguous slice [offset, offset + numel) of the
+ * gradient arena (floats) that stage `stage` completes. */
+int rd_backward_stage(rd_handle* h, const float* x, const float* dy, int stage, void* stream);
+int rd_grad_stage_range(const rd_handle* h, int stage, int64_t* offset, int64_t* numel);
 
 /* torch.optim.Adam.step / SGD.step as built by lib/utils.py:329-334 (coupled L2 decay), over
  * flat arenas of n floats.  step >= 1 is the Adam time step after the increment. */
@@ -181,6 +200,9 @@ int rd_debug_reduce(int engine, int kind, const float* src, int batch, int h, in
 
 /* Number of kernels launched by this library since the last call with reset != 0. */
 int64_t rd_launch_count(int reset);
+
+/* "bf16", "tf32" or "fp32": operand type of the backward GEMMs of this handle (see rd_config.bwd_mode). */
+const char* rd_bwd_mode_name(const rd_handle* h);
 
 /* Debug/profiling: name of the math path actually compiled for the GEMM-shaped layers. */
 const char* rd_math_mode_name(const rd_handle* h);

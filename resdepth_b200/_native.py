@@ -15,7 +15,8 @@ ACT_IDS = {'relu': 0, 'lrelu': 1, 'prelu': 2}          # RD_ACT_*
 MATH_FP32, MATH_TF32 = 0, 1                             # RD_MATH_*
 FWD_EVAL, FWD_TRAIN, FWD_EVAL_SAVE = 0, 1, 2            # RD_FWD_*
 UP_IDS = {'transpose': 0, 'bilinear': 1}                # RD_UP_*
-ABI_VERSION = 2
+ABI_VERSION = 3
+BWD_IDS = {'auto': 0, 'tf32': 1, 'bf16': 2}                  # RD_BWD_*
 
 # every symbol include/resdepth_b200.h declares
 EXPORTED_SYMBOLS = (
@@ -24,7 +25,8 @@ EXPORTED_SYMBOLS = (
     'rd_workspace_bytes', 'rd_forward', 'rd_loss', 'rd_backward', 'rd_adam_step', 'rd_sgd_step',
     'rd_blend_accumulate', 'rd_launch_count', 'rd_math_mode_name', 'rd_profile_enable', 'rd_profile_collect',
     'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce', 'rd_make_tiles', 'rd_residuals', 'rd_residual_stats',
-    'rd_tile_stds', 'rd_set_overlap',
+    'rd_tile_stds', 'rd_set_overlap', 'rd_backward_stage', 'rd_grad_stage_range', 'rd_bwd_mode_name',
+    'rd_workspace_id', 'rd_workspace_alive',
 )
 PROF_NUM = 18                                           # RD_PROF_NUM
 
@@ -32,7 +34,8 @@ PROF_NUM = 18                                           # RD_PROF_NUM
 class RdConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'n_input_channels', 'start_kernel', 'max_filter_depth', 'depth', 'act_encoder', 'act_decoder',
-        'act_bottleneck', 'do_bn', 'bias_conv_layer', 'outer_skip', 'outer_skip_bn', 'math_mode', 'up_mode')]
+        'act_bottleneck', 'do_bn', 'bias_conv_layer', 'outer_skip', 'outer_skip_bn', 'math_mode', 'up_mode',
+        'bwd_mode')]
 
 
 def library_path() -> str:
@@ -68,12 +71,22 @@ def _declare(lib):
     lib.rd_reserve.argtypes = [vp, i32, i32, i32]
     lib.rd_workspace_bytes.restype = i64
     lib.rd_workspace_bytes.argtypes = [vp]
+    lib.rd_workspace_id.restype = i64
+    lib.rd_workspace_id.argtypes = [vp]
+    lib.rd_workspace_alive.restype = i32
+    lib.rd_workspace_alive.argtypes = [vp, i64]
     lib.rd_forward.restype = i32
     lib.rd_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     lib.rd_loss.restype = i32
     lib.rd_loss.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]
     lib.rd_backward.restype = i32
     lib.rd_backward.argtypes = [vp, vp, vp, vp]
+    lib.rd_backward_stage.restype = i32
+    lib.rd_backward_stage.argtypes = [vp, vp, vp, i32, vp]
+    lib.rd_grad_stage_range.restype = i32
+    lib.rd_grad_stage_range.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64)]
+    lib.rd_bwd_mode_name.restype = C.c_char_p
+    lib.rd_bwd_mode_name.argtypes = [vp]
     lib.rd_adam_step.restype = i32
     lib.rd_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, f32, vp]
     lib.rd_sgd_step.restype = i32
@@ -188,6 +201,12 @@ class Handle:
     def workspace_bytes(self) -> int:
         return int(self._lib.rd_workspace_bytes(self._h))
 
+    def workspace_id(self) -> int:
+        return int(self._lib.rd_workspace_id(self._h))
+
+    def workspace_alive(self, ws_id: int) -> bool:
+        return bool(self._lib.rd_workspace_alive(self._h, int(ws_id)))
+
     def forward(self, x_ptr, y_ptr, batch, tile, mode, stream):
         check(self._lib.rd_forward(self._h, x_ptr, y_ptr, batch, tile, mode, stream), 'rd_forward')
 
@@ -197,6 +216,18 @@ class Handle:
 
     def backward(self, x_ptr, dy_ptr, stream):
         check(self._lib.rd_backward(self._h, x_ptr, dy_ptr, stream), 'rd_backward')
+
+    def backward_stage(self, x_ptr, dy_ptr, stage, stream):
+        check(self._lib.rd_backward_stage(self._h, x_ptr, dy_ptr, stage, stream), 'rd_backward_stage')
+
+    def grad_stage_range(self, stage: int):
+        """(offset, numel) in floats of the gradient-arena slice that backward stage ``stage`` completes."""
+        off, n = C.c_int64(), C.c_int64()
+        check(self._lib.rd_grad_stage_range(self._h, stage, C.byref(off), C.byref(n)), 'rd_grad_stage_range')
+        return int(off.value), int(n.value)
+
+    def bwd_mode_name(self) -> str:
+        return self._lib.rd_bwd_mode_name(self._h).decode()
 
     def set_overlap(self, on: bool):
         """Side-stream weight gradients in rd_backward on (default) / off (everything on the caller's stream)."""

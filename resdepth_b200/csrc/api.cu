@@ -72,23 +72,18 @@ struct UpConv {        // ConvTranspose2d(C, C, 2, 2), or Upsample(bilinear, x2)
 
 using namespace rd;
 
-struct rd_handle {
-  rd_config cfg;
-  int device = 0;
-  int depth = 0;
-  std::vector<int> widths;
+namespace rd {
+// Everything that depends on the (batch, tile, with_backward) layout of the workspace: the slab, the pointers carved
+// out of it (inside the per-layer structs too) and the TMA descriptors / tile plans built on those pointers.  A handle
+// keeps the layouts it has used (rd_reserve switches between them without synchronising or rebuilding anything).
+struct Workspace {
   std::vector<ConvBlock> enc, dec;   // dec has depth-1 entries
   ConvBlock bott;
   std::vector<UpConv> ups;           // depth entries
-  long long last_w = -1, last_b = -1;
-  std::vector<ParamInfo> params, buffers;
-  long long param_floats = 0, buffer_floats = 0;
-  float *P = nullptr, *G = nullptr, *BUF = nullptr;   // bound arenas
-
-  // workspace
   void* slab = nullptr;
   size_t slab_bytes = 0;
   int res_batch = 0, res_tile = 0, res_bwd = 0;
+  long long ws_id = 0, ws_last_use = 0;
   float *partials = nullptr, *scratch = nullptr, *part = nullptr, *coef = nullptr, *consts = nullptr;
   size_t partials_floats = 0, scratch_floats = 0, part_floats = 0;
   std::vector<float*> g_skip;
@@ -97,8 +92,6 @@ struct rd_handle {
   float* xcol = nullptr;       // im2col expansion of the input for the first layer's tensor-core wgrad
   int xcol_k = 0;
   float* gt = nullptr;         // bilinear up-mode: gradient at the low-resolution 1x1-conv output
-  // bf16 backward (RESDEPTH_BWD=bf16, default in TF32 mode): dz and the skip gradients as bf16 GEMM operands
-  bool bwd_bf16 = false;
   void* gy_b = nullptr;
   void* gy_b2 = nullptr;       // second dz buffer: consecutive blocks alternate so a weight gradient on the side
                                // stream can still read block k's dz while block k+1's BatchNorm backward writes its own
@@ -106,17 +99,37 @@ struct rd_handle {
   // weight gradients overlap the rest of the backward pass on a side stream (tensor-bound GEMMs next to the
   // HBM-bound BatchNorm backward kernels); only when every GEMM of the backward runs the bf16 tcgen05 path
   bool overlap = false;
+  void* xcol_b = nullptr;
+  int xcol_b_k = 0;
+  float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
+};
+}  // namespace rd
+
+struct rd_handle : rd::Workspace {
+  rd_config cfg;
+  int device = 0;
+  int depth = 0;
+  std::vector<int> widths;
+  long long last_w = -1, last_b = -1;
+  std::vector<ParamInfo> params, buffers;
+  long long param_floats = 0, buffer_floats = 0;
+  float *P = nullptr, *G = nullptr, *BUF = nullptr;   // bound arenas
+
+  std::vector<rd::Workspace> ws_cache;   // layouts not in use right now (their slabs stay allocated)
+  long long ws_next_id = 1, ws_clock = 0;
+  // bf16 backward (rd_config.bwd_mode; default in TF32 mode): dz and the skip gradients as bf16 GEMM operands
+  bool bwd_bf16 = false;
   bool overlap_allowed = true; // rd_set_overlap
   cudaStream_t side = nullptr;
   cudaEvent_t ev_main = nullptr, ev_join = nullptr, ev_wg[2] = {nullptr, nullptr};
   bool wg_pending[2] = {false, false};
-  void* xcol_b = nullptr;
-  int xcol_b_k = 0;
   // outer_skip_BN: BatchNorm2d(1) on input channel 0
   long long ob_gamma = -1, ob_beta = -1, ob_rm = -1, ob_rv = -1;
-  float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
   // state of the last forward
   int fwd_batch = 0, fwd_tile = 0, fwd_mode = -1;
+  // staged backward (rd_backward_stage): next expected stage, and whether the pooled-tensor gradient is in gp_b
+  int bw_next_stage = 0;
+  bool bw_gp_bf16 = false;
   bool tf32() const { return cfg.math_mode == RD_MATH_TF32; }
 
   // per-category CUDA-event timing (rd_profile_*): off by default
@@ -559,6 +572,7 @@ int rd_create(const rd_config* cfg, int device, rd_handle** out) {
   for (int a : {cfg->act_encoder, cfg->act_decoder, cfg->act_bottleneck})
     if (a < RD_ACT_RELU || a > RD_ACT_PRELU) return fail("unknown activation id %d", a);
   if (cfg->math_mode != RD_MATH_FP32 && cfg->math_mode != RD_MATH_TF32) return fail("unknown math mode %d", cfg->math_mode);
+  if (cfg->bwd_mode < RD_BWD_AUTO || cfg->bwd_mode > RD_BWD_BF16) return fail("unknown bwd_mode %d", cfg->bwd_mode);
 
   rd_handle* h = new rd_handle();
   h->cfg = *cfg;
@@ -588,8 +602,12 @@ int rd_create(const rd_config* cfg, int device, rd_handle** out) {
       plan_block(h, h->dec[j], "decoder." + std::to_string(j) + ".1", C, h->widths[D - 2 - j], cfg->act_decoder, false);
   }
   {
+    // operand type of the backward GEMMs: explicit in the config, or (RD_BWD_AUTO) bf16 unless RESDEPTH_BWD=tf32
     const char* env = getenv("RESDEPTH_BWD");
-    h->bwd_bf16 = cfg->math_mode == RD_MATH_TF32 && !(env && std::string(env) == "tf32");
+    bool bf = !(env && std::string(env) == "tf32");
+    if (cfg->bwd_mode == RD_BWD_TF32) bf = false;
+    if (cfg->bwd_mode == RD_BWD_BF16) bf = true;
+    h->bwd_bf16 = cfg->math_mode == RD_MATH_TF32 && bf;
   }
   add_param(h, "last_layer.weight", (long long)cfg->start_kernel * 9, &h->last_w);
   if (cfg->bias_conv_layer) add_param(h, "last_layer.bias", 1, &h->last_b);
@@ -613,10 +631,10 @@ static void destroy_side(rd_handle* h) {
 
 int rd_destroy(rd_handle* h) {
   if (!h) return 0;
-  if (h->slab) {
-    cudaSetDevice(h->device);
-    cudaFree(h->slab);
-  }
+  cudaSetDevice(h->device);
+  if (h->slab) cudaFree(h->slab);
+  for (auto& w : h->ws_cache)
+    if (w.slab) cudaFree(w.slab);
   for (auto& r : h->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
   for (auto& e : h->event_pool) cudaEventDestroy(e);
   destroy_side(h);
@@ -654,33 +672,63 @@ int rd_bind(rd_handle* h, float* params, float* grads, float* bn_buffers) {
   return 0;
 }
 
+static const int kMaxLayouts = 4;     // the current one + three cached (train batch, validation batch, partial last batch)
+
+static bool layout_serves(const rd::Workspace& w, int batch, int tile, int with_backward) {
+  return w.slab && batch == w.res_batch && tile == w.res_tile && (w.res_bwd || !with_backward);
+}
+
+static int evict_oldest_layout(rd_handle* h) {
+  size_t k = 0;
+  for (size_t i = 1; i < h->ws_cache.size(); ++i)
+    if (h->ws_cache[i].ws_last_use < h->ws_cache[k].ws_last_use) k = i;
+  RD_CUDA(cudaDeviceSynchronize());              // work on the evicted slab may still be in flight
+  RD_CUDA(cudaFree(h->ws_cache[k].slab));
+  h->ws_cache.erase(h->ws_cache.begin() + k);
+  return 0;
+}
+
 int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
   if (!h) return fail("rd_reserve: null handle");
   RD_TRY(check_shape(h, batch, tile));
   RD_CUDA(cudaSetDevice(h->device));
-  if (h->slab && batch == h->res_batch && tile == h->res_tile && (h->res_bwd || !with_backward)) return 0;
-  const size_t need = carve(h, nullptr, batch, tile, with_backward);
-  if (need > h->slab_bytes) {
-    if (h->slab) {
-      RD_CUDA(cudaDeviceSynchronize());
-      RD_CUDA(cudaFree(h->slab));
-      h->slab = nullptr; h->slab_bytes = 0;
-    }
-    void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, need);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return fail("workspace allocation of %.1f MB failed: %s", need / 1048576.0, cudaGetErrorString(e));
-    }
-    h->slab = p; h->slab_bytes = need;
-  } else {
-    RD_CUDA(cudaDeviceSynchronize());   // re-carving a live slab: wait for in-flight work
+  rd::Workspace& cur = *h;
+  if (layout_serves(cur, batch, tile, with_backward)) return 0;
+  // another shape: park the current layout (slab, carved pointers, TMA descriptors stay valid) and look for one that
+  // was built for this shape before -- switching costs neither a synchronisation nor a plan rebuild
+  if (cur.slab) {
+    cur.ws_last_use = ++h->ws_clock;
+    h->ws_cache.push_back(cur);
+    cur.slab = nullptr; cur.slab_bytes = 0; cur.ws_id = 0;
+    cur.res_batch = cur.res_tile = cur.res_bwd = 0;
   }
-  carve(h, h->slab, batch, tile, with_backward);
+  h->fwd_mode = -1;
+  for (size_t i = 0; i < h->ws_cache.size(); ++i) {
+    if (layout_serves(h->ws_cache[i], batch, tile, with_backward)) {
+      cur = h->ws_cache[i];
+      h->ws_cache.erase(h->ws_cache.begin() + i);
+      return 0;
+    }
+  }
+  while ((int)h->ws_cache.size() >= kMaxLayouts - 1) RD_TRY(evict_oldest_layout(h));
+  const size_t need = carve(h, nullptr, batch, tile, with_backward);
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, need);
+  while (e != cudaSuccess && !h->ws_cache.empty()) {       // out of memory: give the parked layouts back first
+    cudaGetLastError();
+    RD_TRY(evict_oldest_layout(h));
+    e = cudaMalloc(&p, need);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("workspace allocation of %.1f MB failed: %s", need / 1048576.0, cudaGetErrorString(e));
+  }
+  cur.slab = p; cur.slab_bytes = need;
+  carve(h, cur.slab, batch, tile, with_backward);
   if (with_backward && !h->side) {                          // side stream + events of the overlapped weight gradients
     RD_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&h->ev_main, &h->ev_join, &h->ev_wg[0], &h->ev_wg[1]})
-      RD_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* ev : {&h->ev_main, &h->ev_join, &h->ev_wg[0], &h->ev_wg[1]})
+      RD_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
   RD_TRY(build_tc_plans(h, batch, tile, with_backward));
   const float consts[4] = {0.f, 0.01f, 1.f, 0.f};          // relu slope, LeakyReLU default slope (lib/UNet.py:30)
@@ -689,8 +737,18 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
     RD_TRY(launch_im2col_first_bf16_clear(h->xcol_b, (size_t)batch * tile * tile * h->xcol_b_k * 2, nullptr));
     RD_CUDA(cudaDeviceSynchronize());
   }
-  h->res_batch = batch; h->res_tile = tile; h->res_bwd = with_backward;
-  h->fwd_mode = -1;
+  cur.res_batch = batch; cur.res_tile = tile; cur.res_bwd = with_backward;
+  cur.ws_id = h->ws_next_id++;
+  return 0;
+}
+
+int64_t rd_workspace_id(const rd_handle* h) { return h ? h->ws_id : 0; }
+
+int rd_workspace_alive(const rd_handle* h, int64_t id) {
+  if (!h || id <= 0) return 0;
+  if (h->slab && h->ws_id == id) return 1;
+  for (auto& w : h->ws_cache)
+    if (w.ws_id == id) return 1;
   return 0;
 }
 
@@ -812,7 +870,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
                                 h->cfg.outer_skip ? x : nullptr, h->cfg.n_input_channels * T * T, x_affine, y, B, T, T,
                                 C0, s));
   }
-  if (save) { h->fwd_batch = B; h->fwd_tile = T; h->fwd_mode = mode; }
+  if (save) { h->fwd_batch = B; h->fwd_tile = T; h->fwd_mode = mode; h->bw_next_stage = 0; }
   return 0;
 }
 
@@ -940,7 +998,9 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
 
 }  // namespace
 
-int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
+// stage 0: last_layer + decoder (down to the first up-conv); 1: bottleneck + deepest encoder level; 2: the other
+// encoder levels; -1: everything.  Stages must run in order 0, 1, 2 after one saving forward pass.
+static int backward_stages(rd_handle* h, const float* x, const float* dy, int stage, void* stream) {
   if (!h || !dy || !x) return fail("rd_backward: null argument");
   if (!h->G) return fail("rd_backward: gradient arena not bound (rd_bind)");
   if (h->fwd_mode != RD_FWD_TRAIN && h->fwd_mode != RD_FWD_EVAL_SAVE)
@@ -949,8 +1009,21 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int B = h->fwd_batch, T = h->fwd_tile, D = h->depth;
   const int C0 = h->cfg.start_kernel;
-  bool gp_bf16 = false;                                  // is the gradient at the current pooled tensor held in gp_b?
+  const bool all = stage < 0;
+  if (!all && stage != h->bw_next_stage)
+    return fail("rd_backward_stage: stage %d out of order (expected %d)", stage, h->bw_next_stage);
+  bool& gp_bf16 = h->bw_gp_bf16;                         // is the gradient at the current pooled tensor held in gp_b?
+  auto join = [&]() -> int {                             // the caller's stream continues only after every weight gradient
+    if (h->overlap && h->overlap_allowed) {
+      RD_CUDA(cudaEventRecord(h->ev_join, h->side));
+      RD_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
+      h->wg_pending[0] = h->wg_pending[1] = false;
+    }
+    return 0;
+  };
 
+  if (all || stage == 0) {
+  gp_bf16 = false;
   // last_layer (lib/UNet.py:184,227): du -> gradient at u_{D-1}, which is also the skip gradient of level 0
   {
     const double px = (double)B * T * T;
@@ -1029,9 +1102,7 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
     }
     }
     if (j == 0) {
-      gp_bf16 = h->gp_b && h->bott.tc;
-      RD_TRY(block_backward(h, h->bott, h->gh, GradRef(), B, Hin, h->enc[D - 1].p, false, gp_bf16 ? nullptr : h->gp, 0,
-                            nullptr, gp_bf16 ? h->gp_b : nullptr, s));
+      break;                                               // the bottleneck block belongs to stage 1
     } else {
       // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded (fp32
       // backward) or only as bf16 (bf16 backward)
@@ -1041,7 +1112,15 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
                             h->G + h->ups[j - 1].bias, only_b ? h->gs_b[D - j] : nullptr, s));
     }
   }
+  if (!all) { RD_TRY(join()); h->bw_next_stage = 1; return 0; }
+  }
+  if (all || stage == 1) {
+    gp_bf16 = h->gp_b && h->bott.tc;
+    RD_TRY(block_backward(h, h->bott, h->gh, GradRef(), B, T >> D, h->enc[D - 1].p, false, gp_bf16 ? nullptr : h->gp, 0,
+                          nullptr, gp_bf16 ? h->gp_b : nullptr, s));
+  }
   for (int i = D - 1; i >= 0; --i) {
+    if (!all && (stage == 1) != (i == D - 1)) continue;
     const int H = T >> i;
     const GradRef gs = skip_grad_bf16(h, i) ? GradRef(h->gs_b[i], 1) : GradRef(h->g_skip[i]);
     const GradRef gp = gp_bf16 ? GradRef(h->gp_b, 1) : GradRef(h->gp);
@@ -1050,11 +1129,28 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
                           (i == 0 || out_b) ? nullptr : h->gp, 0, nullptr, out_b ? h->gp_b : nullptr, s));
     gp_bf16 = out_b;
   }
-  if (h->overlap && h->overlap_allowed) {                 // the caller's stream continues only after every weight gradient
-    RD_CUDA(cudaEventRecord(h->ev_join, h->side));
-    RD_CUDA(cudaStreamWaitEvent(s, h->ev_join, 0));
-    h->wg_pending[0] = h->wg_pending[1] = false;
-  }
+  RD_TRY(join());
+  h->bw_next_stage = all ? 0 : (stage == 1 ? 2 : 0);
+  return 0;
+}
+
+int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream) {
+  if (h) h->bw_next_stage = 0;
+  return backward_stages(h, x, dy, -1, stream);
+}
+
+int rd_backward_stage(rd_handle* h, const float* x, const float* dy, int stage, void* stream) {
+  if (stage < 0 || stage > 2) return fail("rd_backward_stage: stage must be 0, 1 or 2 (got %d)", stage);
+  return backward_stages(h, x, dy, stage, stream);
+}
+
+int rd_grad_stage_range(const rd_handle* h, int stage, int64_t* offset, int64_t* numel) {
+  if (!h || stage < 0 || stage > 2 || !offset || !numel) return fail("rd_grad_stage_range: bad argument");
+  const long long e_deep = h->enc[h->depth - 1].w, d_first = h->ups[0].w;
+  const long long lo = stage == 2 ? 0 : (stage == 1 ? e_deep : d_first);
+  const long long hi = stage == 2 ? e_deep : (stage == 1 ? d_first : h->param_floats);
+  *offset = lo;
+  *numel = hi - lo;
   return 0;
 }
 
@@ -1211,6 +1307,12 @@ int64_t rd_launch_count(int reset) {
   const long long v = g_launch_count;
   if (reset) g_launch_count = 0;
   return v;
+}
+
+const char* rd_bwd_mode_name(const rd_handle* h) {
+  if (!h) return "none";
+  if (!h->tf32()) return "fp32";
+  return h->bwd_bf16 ? "bf16" : "tf32";
 }
 
 const char* rd_math_mode_name(const rd_handle* h) {

@@ -10,9 +10,18 @@ What changes is the step itself: forward, masked de-normalised L1 loss, backward
 as hand-written CUDA kernels through the C ABI (``rd_forward``, ``rd_loss``, ``rd_backward``,
 ``rd_adam_step``); the per-sample Python loop of ``denormalize_torch`` (lib/data_normalization.py:29-38) and
 the ~2B+8 small kernels of ``_compute_denormalized_loss`` (lib/Trainer.py:87-100) collapse into one launch
-sequence, and host-to-device copies use pinned, non-blocking transfers.  With ``torch.distributed``
-initialised (one process per GPU) the gradient arena is summed with a single NCCL all-reduce before the
-optimizer step.
+sequence, and host-to-device copies use pinned, non-blocking transfers.
+
+Data parallel (``torch.distributed`` initialised, one process per GPU): the parameter / BatchNorm arenas are
+broadcast from rank 0 at construction, every loader batch is partitioned over the ranks (rank r takes tiles
+[r*B/N, (r+1)*B/N)) unless the loader's sampler already shards, the gradient arena is all-reduced
+in three slices that overlap the backward pass, and the validation metric is averaged over ranks before it
+drives the scheduler / best-model decisions.
+
+Steady-state steps replay CUDA graphs (one launch for forward + loss + backward; three with the all-reduce
+slices in between) captured per batch shape once the same device buffers have been seen twice; host batches are
+copied into two alternating static staging sets so that the pointers repeat.  ``RESDEPTH_GRAPHS=0`` switches
+the capture off.
 """
 from __future__ import annotations
 
@@ -25,7 +34,8 @@ import torch
 
 from .. import _native
 from .AverageMeter import AverageMeter
-from .distributed import allreduce_gradients
+from .distributed import (BucketedAllReduce, allreduce_mean_of_meter, broadcast_state, loader_is_sharded,
+                          shard_batch)
 from .optim import fuse_optimizer
 from .UNet import UNet
 
@@ -68,6 +78,21 @@ class _NullWriter:
 class _StagedBatch(dict):
     """A batch whose tensors already live on the device; ``ready`` = CUDA event recorded after its H2D copies."""
     ready = None
+
+
+_STEP_KEYS = ('input', 'target', 'loss_mask', 'dsm_mean', 'dsm_std')
+_MAX_GRAPHS = 16
+
+
+class _GraphedStep:
+    """CUDA graphs of one step on fixed device buffers: ``segments`` are replayed in order, ``between[i]`` (a flat
+    gradient slice or None) is handed to the all-reduce after segment i."""
+
+    def __init__(self):
+        self.segments = []
+        self.between = []
+        self.loss = None
+        self.keep = None            # tensors captured by address (inputs, y, dy): kept alive with the graphs
 
 
 class Trainer(object):
@@ -132,6 +157,7 @@ class Trainer(object):
             self.model = self.model.to(self.device)
 
         self.loader = {'train': args.trainloader, 'val': args.valloader}
+        self._init_runtime()
 
         batch = next(iter(self.loader['train']))
         x, _, _ = self._extract_inputs_outputs_loss_masks(batch)
@@ -151,7 +177,27 @@ class Trainer(object):
         else:
             self.hparams.update(scheduler='None', patience=-1, step_size=-1)
 
-        self._loss_buf = None
+    def _init_runtime(self):
+        """Device-side state behind the step API: replica synchronisation, the batch-partition policy, staging
+        buffers and the CUDA-graph cache (also used by bench.py, which skips the logging part of ``__init__``)."""
+        self._copy_stream = None
+        self._static = {}            # (set index, shapes) -> static staging tensors of host batches
+        self._static_done = {}       # set index -> event: the step that last read this staging set has finished
+        self._stage_count = 0
+        self.replayed_kernels = 0    # library kernels launched through graph replays (bench: gpu_launches)
+        self._graphs = {}            # pointer key -> _GraphedStep
+        self._graph_seen = {}
+        self.use_graphs = os.environ.get('RESDEPTH_GRAPHS', '1') != '0'
+        self._reducer = BucketedAllReduce() if self.distributed else None
+        # every rank partitions the loader's batches unless the sampler already hands it its own tiles
+        self.shard_batches = {ph: self.distributed and ld is not None and not loader_is_sharded(ld)
+                              for ph, ld in self.loader.items()}
+        rt = self.model._runtime(self.device)
+        if self.distributed:
+            broadcast_state([rt['arena'], rt['bufs'], rt['nbt']])
+        h = rt['handle']
+        self.logger.info(f'resdepth_b200: forward {h.math_mode_name()}; backward GEMM operands {h.bwd_mode_name()}'
+                         + (f'; data parallel over {self.world_size} ranks' if self.distributed else ''))
 
     # ---------------------------------------------------------------------------------------------
     @staticmethod
@@ -166,38 +212,78 @@ class Trainer(object):
             t = t.pin_memory()
         return t.to(self.device, dtype=dtype, non_blocking=True)
 
-    def _stage_batch(self, batch):
+    def _my_shard(self, batch, phase):
+        """The tiles of a loader batch this rank owns; the whole batch on one rank or when the
+        loader's sampler already partitions the data."""
+        if self.shard_batches.get(phase) and not isinstance(batch, _StagedBatch):
+            return shard_batch(batch, self.rank, self.world_size)
+        return batch
+
+    def _static_set(self, batch):
+        """Two alternating sets of device staging tensors per batch shape: host batches always land at the same
+        addresses, which is what lets the step replay a CUDA graph."""
+        k = self._stage_count & 1
+        self._stage_count += 1
+        sig = (k,) + tuple((tuple(batch[n].shape), batch[n].dtype) for n in _STEP_KEYS)
+        st = self._static.get(sig)
+        if st is None:
+            if len(self._static) >= 8:
+                self._static.clear()
+            want = {'input': torch.float32, 'target': torch.float32, 'loss_mask': batch['loss_mask'].dtype,
+                    'dsm_mean': torch.float32, 'dsm_std': torch.float32}
+            st = {n: torch.empty(torch.flatten(batch[n]).shape if n.startswith('dsm_') else batch[n].shape,
+                                 dtype=want[n], device=self.device) for n in _STEP_KEYS}
+            self._static[sig] = st
+        return k, st
+
+    def _stage_batch(self, batch, phase='train'):
         """Enqueue the H2D copies of one host batch on the copy stream and return the device-resident batch
         (``_StagedBatch``) with the event that marks the copies complete."""
+        batch = self._my_shard(batch, phase)
         main = torch.cuda.current_stream(self.device)
-        if getattr(self, '_copy_stream', None) is None:
+        if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         staged = _StagedBatch(batch)
+        on_device = any(batch[n].is_cuda for n in _STEP_KEYS)
+        if on_device:
+            # device-resident batches (e.g. DeviceTileProducer) may still be being written on the compute stream
+            self._copy_stream.wait_stream(main)
+        use_static = self.use_graphs and not on_device
+        if use_static:
+            k, st = self._static_set(batch)
+            if k in self._static_done:                       # the step that read this set two batches ago
+                self._copy_stream.wait_event(self._static_done[k])
+            staged.static_set = k
         with torch.cuda.stream(self._copy_stream):
-            staged['input'] = self._to_device(batch['input'], torch.float32)
-            staged['target'] = self._to_device(batch['target'], torch.float32)
-            staged['loss_mask'] = self._to_device(batch['loss_mask'])
-            staged['dsm_mean'] = self._to_device(torch.flatten(batch['dsm_mean']), torch.float32)
-            staged['dsm_std'] = self._to_device(torch.flatten(batch['dsm_std']), torch.float32)
+            for n in _STEP_KEYS:
+                src = torch.flatten(batch[n]) if n.startswith('dsm_') else batch[n]
+                if use_static:
+                    if not src.is_pinned():
+                        src = src.pin_memory()
+                    st[n].copy_(src, non_blocking=True)
+                    staged[n] = st[n]
+                else:
+                    staged[n] = self._to_device(src, None if n == 'loss_mask' else torch.float32)
             staged.ready = torch.cuda.Event()
             staged.ready.record(self._copy_stream)
-        for k in ('input', 'target', 'loss_mask', 'dsm_mean', 'dsm_std'):
-            staged[k].record_stream(main)
+        if not use_static:
+            for n in _STEP_KEYS:
+                staged[n].record_stream(main)
         return staged
 
-    def _prefetched(self, loader):
+    def _prefetched(self, loader, phase='train'):
         """Iterate ``loader`` one batch ahead: the H2D copies of batch i+1 are enqueued (copy stream) before the
         step of batch i is launched, so they overlap its compute.  Same batches, same order as the plain loop of
         the reference (lib/Trainer.py:212-213)."""
         it = iter(loader)
         try:
-            nxt = self._stage_batch(next(it))
+            nxt = self._stage_batch(next(it), phase)
         except StopIteration:
             return
         while nxt is not None:
             cur = nxt
             try:
-                nxt = self._stage_batch(next(it))
+                nxt = self._stage_batch(next(it), phase)
             except StopIteration:
                 nxt = None
             yield cur
@@ -208,12 +294,9 @@ class Trainer(object):
         handle = self.model.native_handle(self.device)
         loss = torch.empty(1, device=self.device, dtype=torch.float32)
         dy = torch.empty_like(y_pred) if want_grad else None
-        if loss_mask.dtype == torch.bool:
-            mask_u8 = loss_mask.contiguous().view(torch.uint8)        # zero-copy reinterpretation
-        else:
-            mask_u8 = (loss_mask != 0).view(torch.uint8) if loss_mask.dtype != torch.uint8 else loss_mask
+        mask_u8 = self._mask_u8(loss_mask)
         with torch.cuda.device(self.device):
-            handle.loss(y_pred.data_ptr(), y.contiguous().data_ptr(), mask_u8.contiguous().data_ptr(),
+            handle.loss(y_pred.data_ptr(), y.contiguous().data_ptr(), mask_u8.data_ptr(),
                         mean.data_ptr(), std.data_ptr(), loss.data_ptr(), dy.data_ptr() if want_grad else None,
                         B, T, torch.cuda.current_stream().cuda_stream)
         return loss, dy
@@ -221,7 +304,10 @@ class Trainer(object):
     def _load_pretrain(self, resume):
         if not os.path.isfile(resume):
             raise ValueError(f"No checkpoint found at '{resume}.\n'")
-        checkpoint = torch.load(resume, map_location='cpu', weights_only=False)
+        # tensors + plain scalars only (what both implementations write); full unpickling of an untrusted file is
+        # opt-in: RESDEPTH_TRUSTED_CHECKPOINT=1
+        trusted = os.environ.get('RESDEPTH_TRUSTED_CHECKPOINT', '0') == '1'
+        checkpoint = torch.load(resume, map_location='cpu', weights_only=not trusted)
         self.model.load_state_dict(checkpoint['model_state_dict'])
         self.model = self.model.to(self.device)            # before the optimizer state, as the reference does
         self.optimizer.load_state_dict(checkpoint['optimizer_state_dict'])
@@ -238,19 +324,19 @@ class Trainer(object):
     def _save_checkpoint(self, epoch, loss_train, loss_val, filepath):
         if self.rank != 0:
             return
-        # clone(): parameters are views of one arena; saving clones keeps each tensor's file footprint its own
+        # clone(): parameters / optimizer moments are views of flat arenas; saving clones keeps each tensor's file
+        # footprint its own.  The optimizer's live state dictionaries are copied, never rebound.
+        opt_sd = self.optimizer.state_dict()
+        opt_sd = {'state': {pid: {k: (v.detach().clone() if isinstance(v, torch.Tensor) else v)
+                                  for k, v in st.items()} for pid, st in opt_sd.get('state', {}).items()},
+                  'param_groups': opt_sd['param_groups']}
         state = {
             'epoch': epoch,
             'model_state_dict': {k: v.detach().clone() for k, v in self.model.state_dict().items()},
-            'optimizer_state_dict': self.optimizer.state_dict(),
+            'optimizer_state_dict': opt_sd,
             'loss_train': loss_train,
             'loss_val': loss_val,
         }
-        opt_state = state['optimizer_state_dict'].get('state', {})
-        for st in opt_state.values():
-            for k, v in list(st.items()):
-                if isinstance(v, torch.Tensor):
-                    st[k] = v.detach().clone()
         if self.scheduler is not None:
             state['scheduler_state_dict'] = self.scheduler.state_dict()
         torch.save(state, filepath)
@@ -267,16 +353,33 @@ class Trainer(object):
         self.model.train() if train else self.model.eval()
 
         if isinstance(batch, _StagedBatch):                 # copies already in flight (``_prefetched``)
-            torch.cuda.current_stream(self.device).wait_event(batch.ready)
-            return self.device_step(batch['input'], batch['target'], batch['loss_mask'], batch['dsm_mean'],
+            main = torch.cuda.current_stream(self.device)
+            main.wait_event(batch.ready)
+            loss = self.device_step(batch['input'], batch['target'], batch['loss_mask'], batch['dsm_mean'],
                                     batch['dsm_std'], train)
+            k = getattr(batch, 'static_set', None)
+            if k is not None:                               # the staging set may be overwritten after this point
+                ev = self._static_done.get(k)
+                if ev is None:
+                    ev = self._static_done[k] = torch.cuda.Event()
+                ev.record(main)
+            return loss
 
+        batch = self._my_shard(batch, phase)
+        if all(batch[n].is_cuda for n in _STEP_KEYS):
+            # device-resident batch (DeviceTileProducer, a pre-staged loader): nothing to copy
+            return self.device_step(batch['input'].float(), batch['target'].float(), batch['loss_mask'],
+                                    torch.flatten(batch['dsm_mean']).float(), torch.flatten(batch['dsm_std']).float(),
+                                    train)
+        if self.use_graphs and not any(batch[n].is_cuda for n in _STEP_KEYS):
+            # one code path for host batches: stage (static buffers), then the graphed step
+            return self._launch_batch(self._stage_batch(batch, phase), phase)
         x, y, loss_mask = self._extract_inputs_outputs_loss_masks(batch)
         # the input tiles are needed first: copy them on the compute stream; target / mask / normalisation constants
         # are only needed by the loss, so their copies ride a side stream and overlap the forward pass
         x = self._to_device(x, torch.float32)
         main = torch.cuda.current_stream(self.device)
-        if getattr(self, '_copy_stream', None) is None:
+        if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         self._copy_stream.wait_stream(main)
         with torch.cuda.stream(self._copy_stream):
@@ -291,22 +394,135 @@ class Trainer(object):
 
         return self.device_step(x, y, loss_mask, mean, std, train, wait_before_loss=copied)
 
+    # -- the step on device-resident tensors ---------------------------------------------------------------
+    def _mask_u8(self, loss_mask):
+        if loss_mask.dtype == torch.bool:
+            return loss_mask.contiguous().view(torch.uint8)            # zero-copy reinterpretation
+        if loss_mask.dtype == torch.uint8:
+            return loss_mask.contiguous()
+        return (loss_mask != 0).view(torch.uint8)
+
+    def _enqueue_forward_loss(self, x, y, loss_mask, mean, std, train):
+        y_pred = self.model._forward_native(x, _native.FWD_TRAIN if train else _native.FWD_EVAL)
+        return y_pred, self._compute_denormalized_loss(y_pred, y, loss_mask, mean, std, want_grad=train)
+
+    def _set_grads(self):
+        rt = self.model._rt
+        named = dict(self.model.named_parameters())
+        flat = rt['grads']
+        for name, numel, off in rt['pinfos']:
+            named[name].grad = flat[off:off + numel].view(named[name].shape)
+
     def device_step(self, x, y, loss_mask, mean, std, train, wait_before_loss=None):
         """The step on device-resident tensors: forward, fused loss (+ gradient seed), backward, gradient
         all-reduce; leaves ``param.grad`` set (views of the flat gradient arena) and returns the loss as a
         device tensor [1] without synchronising.  ``inference_one_batch`` = H2D copies + this + ``loss.item()``."""
         with torch.no_grad():
+            if self.use_graphs and wait_before_loss is None:
+                loss = self._graphed_step(x, y, loss_mask, mean, std, train)
+                if loss is not None:
+                    return loss
             y_pred = self.model._forward_native(x, _native.FWD_TRAIN if train else _native.FWD_EVAL)
             if wait_before_loss is not None:
                 torch.cuda.current_stream(self.device).wait_event(wait_before_loss)
             loss, dy = self._compute_denormalized_loss(y_pred, y, loss_mask, mean, std, want_grad=train)
             if train:
-                grads = self.model._backward_native(x, dy, detach_copy=False)
-                # the ONE collective of the path: sum the flat gradient arena over ranks (NCCL / NVLink)
-                self.optimizer.grad_scale = allreduce_gradients(self.model._rt['grads'])
-                for p, g in zip(self.model.parameters(), grads):
-                    p.grad = g
+                # the ONE collective of the path: the flat gradient arena summed over ranks (NCCL / NVLink), issued
+                # slice by slice as the backward stages complete so that it overlaps the rest of the backward pass
+                red = self._reducer
+                self.model._backward_native(x, dy, detach_copy=False,
+                                            on_stage_done=red.launch if red is not None else None)
+                self.optimizer.grad_scale = red.finish() if red is not None else 1.0
+                self._set_grads()
         return loss
+
+    def _graphed_step(self, x, y, loss_mask, mean, std, train):
+        """Replays (or, the second time the same device buffers are seen, captures) the CUDA graphs of a step on
+        these buffers; returns None when the step should run eagerly instead."""
+        tensors = (x, y, loss_mask, mean, std)
+        if not all(t.is_cuda and t.is_contiguous() for t in tensors) or x.dtype != torch.float32 \
+                or y.dtype != torch.float32 or mean.dtype != torch.float32 or std.dtype != torch.float32:
+            return None
+        key = tuple(t.data_ptr() for t in tensors) + (tuple(x.shape), bool(train), self.model._rt.get('math'))
+        g = self._graphs.get(key)
+        if g is None:
+            seen = self._graph_seen.get(key, 0) + 1
+            if len(self._graph_seen) > 4096:
+                self._graph_seen.clear()
+            self._graph_seen[key] = seen
+            if seen < 2:
+                return None                      # first sight: eager (also reserves the workspace for this shape)
+            g = self._capture_step(x, y, loss_mask, mean, std, train)
+            if len(self._graphs) >= _MAX_GRAPHS:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._graphs[key] = g
+        if not self.model._rt['handle'].workspace_alive(g.ws_id):
+            # the workspace layout this graph was captured on has been freed: its addresses are stale
+            self._graphs.pop(key, None)
+            self._graph_seen.pop(key, None)
+            return None
+        red = self._reducer
+        self.replayed_kernels += g.n_kernels
+        for seg, grad_slice in zip(g.segments, g.between):
+            seg.replay()
+            if grad_slice is not None and red is not None:
+                red.launch(grad_slice)
+        self.model._rt['token'] += 1                 # a replay overwrites the saved activations like a forward call
+        if train:
+            self.optimizer.grad_scale = red.finish() if red is not None else 1.0
+            self._set_grads()
+        return g.loss
+
+    def _capture_step(self, x, y, loss_mask, mean, std, train):
+        rt = self.model._rt
+        handle = rt['handle']
+        B, _, T, _ = x.shape
+        handle.reserve(B, T, train)
+        g = _GraphedStep()
+        g.keep = (x, y, loss_mask, mean, std)
+        kernels_before = _native.launch_count()
+        stream = torch.cuda.Stream(self.device)
+        stream.wait_stream(torch.cuda.current_stream(self.device))
+        pool = None
+        staged = self.distributed and train
+
+        def segment(fn):
+            nonlocal pool
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, pool=pool, stream=stream):
+                fn()
+            if pool is None:
+                pool = cg.pool()
+            g.segments.append(cg)
+
+        state = {}
+
+        def first():
+            state['y_pred'], (state['loss'], state['dy']) = self._enqueue_forward_loss(x, y, loss_mask, mean, std, train)
+            if train:
+                s = torch.cuda.current_stream(self.device).cuda_stream
+                if staged:
+                    handle.backward_stage(x.data_ptr(), state['dy'].data_ptr(), 0, s)
+                else:
+                    handle.backward(x.data_ptr(), state['dy'].data_ptr(), s)
+
+        segment(first)
+        if staged:
+            off, n = handle.grad_stage_range(0)
+            g.between.append(rt['grads'][off:off + n] if n > 0 else None)
+            for stage in (1, 2):
+                segment(lambda st=stage: handle.backward_stage(x.data_ptr(), state['dy'].data_ptr(), st,
+                                                               torch.cuda.current_stream(self.device).cuda_stream))
+                off, n = handle.grad_stage_range(stage)
+                g.between.append(rt['grads'][off:off + n] if n > 0 else None)
+        else:
+            g.between.append(None)
+        torch.cuda.current_stream(self.device).wait_stream(stream)
+        g.loss = state['loss']
+        g.keep = g.keep + (state['y_pred'], state['dy'])
+        g.ws_id = handle.workspace_id()
+        g.n_kernels = _native.launch_count() - kernels_before
+        return g
 
     def inference_one_epoch(self, epoch, phase):
         assert phase in ['train', 'val']
@@ -335,7 +551,7 @@ class Trainer(object):
                 self.writer.add_scalar("train/learning_rate", self._get_lr(), curr_iter)
 
         pending = None
-        for c_iter, batch in enumerate(self._prefetched(self.loader[phase])):
+        for c_iter, batch in enumerate(self._prefetched(self.loader[phase], phase)):
             loss = self._launch_batch(batch, phase)
 
             if phase == 'train':
@@ -362,53 +578,55 @@ class Trainer(object):
     def stats_meter(self):
         return {key: AverageMeter() for key in self.stats_dict()}
 
+    # -- the epoch loop of lib/Trainer.py:255-318, split into its decisions ----------------------------------
+    def _validate(self, epoch, train_avg):
+        """One validation pass plus everything the reference hangs on its result (lib/Trainer.py:271-300): scalar
+        logging, best-model checkpoint + hparams, scheduler step.  Under data parallelism the metric is the mean
+        over all ranks' tiles, so every replica takes the same decisions."""
+        meters = self.inference_one_epoch(epoch, 'val')
+        if self.distributed:
+            for meter in meters.values():
+                total, count = allreduce_mean_of_meter(meter.sum, meter.count, self.device)
+                if count > 0:
+                    meter.sum, meter.count, meter.avg = total, count, total / count
+        line = f"\nval:\tEpoch: {epoch}\t\t"
+        for key, meter in meters.items():
+            self.writer.add_scalar(f"val/{key}", meter.avg, epoch)
+            line += f'{key}: {meter.avg:.6f}\t'
+        self.logger.info(line + '\n')
+        self.writer.add_scalar("val/learning_rate", self._get_lr(), epoch)
+
+        val_avg = meters['MAE_metric'].avg
+        if val_avg < self.best_loss:
+            self.best_loss, self.index_best_loss = val_avg, epoch
+            self._save_checkpoint(epoch, train_avg, val_avg, self.path_model_best)
+            self.writer.add_hparams(hparam_dict=self.hparams, metric_dict={'hparam/MAE_metric': val_avg},
+                                    run_name=self.tboard_log_dir)
+        if self.scheduler is not None:
+            plateau = self.scheduler.__class__.__name__ == 'ReduceLROnPlateau'
+            self.scheduler.step(val_avg) if plateau else self.scheduler.step()
+        return meters
+
     def train(self):
         self.logger.info('Start training...\n')
-        start_time = time.time()
+        t_start = time.time()
         epoch = self.start_epoch
-        train_stats_meter = val_stats_meter = self.stats_meter()
+        train_meters = val_meters = self.stats_meter()
 
         for epoch in range(self.start_epoch, self.n_epochs):
-            print_msg = f'Epoch {epoch}/{self.n_epochs - 1}'
-            self.logger.info('\n{}\n{}\n'.format(print_msg, '-' * len(print_msg)))
+            title = f'Epoch {epoch}/{self.n_epochs - 1}'
+            self.logger.info('\n{}\n{}\n'.format(title, '-' * len(title)))
 
-            train_stats_meter = self.inference_one_epoch(epoch, 'train')
-
+            train_meters = self.inference_one_epoch(epoch, 'train')
             if (epoch + 1) % self.evaluate_rate == 0:
-                val_stats_meter = self.inference_one_epoch(epoch, 'val')
-
-                message = f"\nval:\tEpoch: {epoch}\t\t"
-                for key, value in val_stats_meter.items():
-                    self.writer.add_scalar(f"val/{key}", value.avg, epoch)
-                    message += f'{key}: {value.avg:.6f}\t'
-                self.logger.info(message + '\n')
-                self.writer.add_scalar("val/learning_rate", self._get_lr(), epoch)
-
-                if val_stats_meter['MAE_metric'].avg < self.best_loss:
-                    self.best_loss = val_stats_meter['MAE_metric'].avg
-                    self.index_best_loss = epoch
-                    self._save_checkpoint(epoch, train_stats_meter['MAE_metric'].avg,
-                                          val_stats_meter['MAE_metric'].avg, self.path_model_best)
-                    self.writer.add_hparams(hparam_dict=self.hparams,
-                                            metric_dict={'hparam/MAE_metric': val_stats_meter['MAE_metric'].avg},
-                                            run_name=self.tboard_log_dir)
-
-                if self.scheduler is not None:
-                    if self.scheduler.__class__.__name__ == 'ReduceLROnPlateau':
-                        self.scheduler.step(val_stats_meter['MAE_metric'].avg)
-                    else:
-                        self.scheduler.step()
-
+                val_meters = self._validate(epoch, train_meters['MAE_metric'].avg)
             if (epoch + 1) % self.save_model_rate == 0 and epoch > self.evaluate_rate:
-                name = 'Model_after_' + str(epoch + 1) + '_epochs.pth'
-                self._save_checkpoint(epoch, train_stats_meter['MAE_metric'].avg, val_stats_meter['MAE_metric'].avg,
-                                      os.path.join(self.checkpoint_dir, name))
+                self._save_checkpoint(epoch, train_meters['MAE_metric'].avg, val_meters['MAE_metric'].avg,
+                                      os.path.join(self.checkpoint_dir, f'Model_after_{epoch + 1}_epochs.pth'))
 
-        time_text = time.strftime('%H:%M:%S', time.gmtime(time.time() - start_time))
-        self.logger.info(f'\n\nTraining finished!\nTraining time: {time_text}')
+        elapsed = time.strftime('%H:%M:%S', time.gmtime(time.time() - t_start))
+        self.logger.info(f'\n\nTraining finished!\nTraining time: {elapsed}')
         self.logger.info(f'\nBest model at epoch: {self.index_best_loss}')
         self.logger.info('Validation loss of the best model: {:.6f}'.format(self.best_loss))
         self.writer.close()
-
-        self._save_checkpoint(epoch, train_stats_meter['MAE_metric'].avg, val_stats_meter['MAE_metric'].avg,
-                              self.path_model_last)
+        self._save_checkpoint(epoch, train_meters['MAE_metric'].avg, val_meters['MAE_metric'].avg, self.path_model_last)

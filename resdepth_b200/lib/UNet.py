@@ -150,6 +150,20 @@ class UNet(nn.Module):
             raise ValueError(f"RESDEPTH_MATH must be 'tf32' or 'fp32', got '{m}'")
         return _native.MATH_TF32 if m == 'tf32' else _native.MATH_FP32
 
+    # Operand type of the backward GEMMs on the tcgen05 path.  The reference's autograd runs them in fp32 (TF32 under
+    # cuDNN); this implementation defaults to bf16 operands with fp32 accumulation ('auto' = bf16 unless the
+    # environment says RESDEPTH_BWD=tf32).  Set ``model.backward_math = 'tf32'`` before the first forward call for
+    # TF32 operands; gradient error of either mode against the fp32 oracle: DESIGN.md section 5.
+    backward_math = 'auto'
+
+    def _bwd_mode(self) -> int:
+        if self.backward_math not in _native.BWD_IDS:
+            raise ValueError(f"backward_math must be one of {list(_native.BWD_IDS)}, got '{self.backward_math}'")
+        mode = _native.BWD_IDS[self.backward_math]
+        if mode == 0 and os.environ.get('RESDEPTH_BWD', '').lower() == 'tf32':
+            mode = _native.BWD_IDS['tf32']
+        return mode
+
     def _config(self) -> _native.RdConfig:
         return _native.RdConfig(
             n_input_channels=self.n_input_channels, start_kernel=self.start_kernel,
@@ -158,12 +172,13 @@ class UNet(nn.Module):
             act_bottleneck=_native.ACT_IDS[self.act_fn_bottleneck], do_bn=int(bool(self.do_BN)),
             bias_conv_layer=int(bool(self.bias_conv_layer)), outer_skip=int(bool(self.do_outer_skip)),
             outer_skip_bn=int(bool(self.do_outer_skip_BN)), math_mode=self._math_mode(),
-            up_mode=_native.UP_IDS[self.up_mode])
+            up_mode=_native.UP_IDS[self.up_mode], bwd_mode=self._bwd_mode())
 
     def _runtime(self, device: torch.device) -> dict:
         """Creates (once per device) the native handle and moves parameters/buffers into flat arenas."""
         rt = self._rt
-        if rt.get('device') != device or rt.get('math') != self._math_mode():
+        math_key = (self._math_mode(), self._bwd_mode())
+        if rt.get('device') != device or rt.get('math') != math_key:
             if 'handle' in rt:
                 rt['handle'].close()
             rt.clear()
@@ -177,7 +192,7 @@ class UNet(nn.Module):
                 if named[name].numel() != numel:
                     raise RuntimeError(f'resdepth_b200: parameter {name} has {named[name].numel()} elements, '
                                        f'native plan expects {numel}')
-            rt.update(device=device, math=self._math_mode(), handle=handle, pinfos=infos,
+            rt.update(device=device, math=math_key, handle=handle, pinfos=infos,
                       binfos=handle.buffer_infos(), token=0,
                       arena=torch.zeros(max(handle.param_arena_size(), 4), device=device),
                       grads=torch.zeros(max(handle.param_arena_size(), 4), device=device),
@@ -253,15 +268,25 @@ class UNet(nn.Module):
         rt['token'] += 1
         return y
 
-    def _backward_native(self, x: torch.Tensor, dy: torch.Tensor, detach_copy: bool) -> List[torch.Tensor]:
+    def _backward_native(self, x: torch.Tensor, dy: torch.Tensor, detach_copy: bool,
+                         on_stage_done=None) -> List[torch.Tensor]:
         """Runs rd_backward; returns per-parameter gradient views (into the persistent gradient arena, or into a
-        fresh copy of it when ``detach_copy``)."""
+        fresh copy of it when ``detach_copy``).  With ``on_stage_done`` the pass runs in its three stages
+        (rd_backward_stage) and ``on_stage_done(flat_gradient_slice)`` is called after each one has been enqueued:
+        the hook of the data-parallel trainer, which starts that slice's all-reduce while the next stage computes."""
         rt = self._rt
         dy = dy.contiguous()
         x = x.contiguous()
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            rt['handle'].backward(x.data_ptr(), dy.data_ptr(), stream)
+            if on_stage_done is None:
+                rt['handle'].backward(x.data_ptr(), dy.data_ptr(), stream)
+            else:
+                for stage in range(3):
+                    rt['handle'].backward_stage(x.data_ptr(), dy.data_ptr(), stage, stream)
+                    off, n = rt['handle'].grad_stage_range(stage)
+                    if n > 0:
+                        on_stage_done(rt['grads'][off:off + n])
         flat = rt['grads'].clone() if detach_copy else rt['grads']
         named = dict(self.named_parameters())
         return [flat[off:off + numel].view(named[name].shape) for name, numel, off in rt['pinfos']]

@@ -8,8 +8,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from resdepth_b200.lib.distributed import (allreduce_gradients, owns_batch, shard_batch, shard_bounds,
-                                            sum_partial_rasters, world)
+from resdepth_b200.lib.distributed import (BucketedAllReduce, allreduce_gradients, allreduce_mean_of_meter,
+                                            broadcast_state, loader_is_sharded, owns_batch, replicas_identical,
+                                            shard_batch, shard_bounds, state_checksum, sum_partial_rasters, world)
 
 
 def _free_port():
@@ -43,7 +44,25 @@ def _worker(rank, world_size, port, out_dir):
             if owns_batch(bi, rank, world_size):
                 raster[bi % 4, bi % 6] += weights[bi]
         raster = sum_partial_rasters(raster)
-        torch.save({'grads': grads, 'scale': scale, 'raster': raster}, os.path.join(out_dir, f'rank{rank}.pt'))
+        # replica synchronisation at start-up: different per-rank values -> rank 0's everywhere
+        arena = torch.full((10,), float(rank + 1))
+        counters = torch.tensor([rank], dtype=torch.int64)
+        same_before, _ = replicas_identical(arena)
+        broadcast_state([arena, None, counters])
+        same_after, cs = replicas_identical(arena)
+        assert not same_before and same_after and torch.equal(arena, torch.ones(10)) and int(counters) == 0
+        # the step's collective issued slice by slice (CPU tensors: the same sequence, synchronously)
+        flat = torch.arange(12.) * (rank + 1)
+        red = BucketedAllReduce()
+        for lo, hi in ((8, 12), (3, 8), (0, 3)):              # backward order: decoder slice first
+            red.launch(flat[lo:hi])
+        bscale = red.finish()
+        assert bscale == 0.5 and torch.equal(flat, torch.arange(12.) * 3)
+        # validation metric: every rank ends with the global mean
+        tot, cnt = allreduce_mean_of_meter(2.0 * (rank + 1), rank + 1)
+        assert cnt == 3 and abs(tot - 6.0) < 1e-12
+        torch.save({'grads': grads, 'scale': scale, 'raster': raster, 'checksum': cs},
+                   os.path.join(out_dir, f'rank{rank}.pt'))
     finally:
         dist.destroy_process_group()
 
@@ -83,3 +102,22 @@ def test_shard_bounds_cover_the_batch():
 def test_single_process_is_a_no_op():
     g = torch.ones(8)
     assert allreduce_gradients(g) == 1.0 and torch.equal(g, torch.ones(8))
+
+
+def test_loader_shard_detection_and_checksum():
+    from torch.utils.data import DataLoader, TensorDataset
+    from torch.utils.data.distributed import DistributedSampler
+    ds = TensorDataset(torch.arange(8.))
+    assert not loader_is_sharded(DataLoader(ds, batch_size=2))
+    assert not loader_is_sharded([1, 2, 3])
+    assert loader_is_sharded(DataLoader(ds, batch_size=2, sampler=DistributedSampler(ds, num_replicas=2, rank=0)))
+    a = torch.arange(20.)
+    b = a.clone()
+    assert state_checksum(a) == state_checksum(b)
+    b[3], b[4] = a[4], a[3]                                  # a permutation changes it (position-weighted)
+    assert state_checksum(a) != state_checksum(b)
+    assert replicas_identical(a) == (True, state_checksum(a))
+    assert allreduce_mean_of_meter(3.0, 2) == (3.0, 2)
+    red = BucketedAllReduce()
+    red.launch(a)
+    assert red.finish() == 1.0

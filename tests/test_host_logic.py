@@ -123,7 +123,7 @@ def test_epoch_prefetcher_keeps_order_and_stages_one_batch_ahead():
     tr = Trainer.__new__(Trainer)
     events = []
 
-    def fake_stage(batch):
+    def fake_stage(batch, phase="train"):
         events.append(('stage', batch))
         return {'staged': batch}
     tr._stage_batch = fake_stage
