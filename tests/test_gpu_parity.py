@@ -533,7 +533,9 @@ def _trainer_for(model, batches, tmp_path, opt=None, sched=None, pretrained=None
 def test_loss_trajectory_200_steps_bf16_backward_follows_fp32(tmp_path, monkeypatch):
     """Training behaviour, not one step: 200 Adam steps from the same seed on the same batches with (a) the exact
     CUDA-core fp32 path, (b) the default tcgen05 path (TF32 forward, bf16-operand backward) and (c) TF32 forward +
-    TF32 backward.  The loss must fall, and the mean loss of the last 20 steps must agree within 1 %."""
+    TF32 backward, at the reference's learning rate (lib/config.py:100).  The loss must fall to less than half, and the
+    mean loss of the last 50 steps must agree within 1 % (a CPU study with the oracle: perturbing every initial weight
+    by 0.1 % / 0.3 % moves that mean by 0.1 % / 0.5 %, so 1 % is the resolution of this test)."""
     kwargs = dict(n_input_channels=3, start_kernel=64, depth=3, bias_conv_layer=True)
     batches = [O.synthetic_batch(8, 3, 64, seed=700 + i) for i in range(10)]
     curves = {}
@@ -541,7 +543,7 @@ def test_loss_trajectory_200_steps_bf16_backward_follows_fp32(tmp_path, monkeypa
         monkeypatch.setenv('RESDEPTH_MATH', math)
         model = _model(kwargs)
         model.backward_math = bwd
-        tr = _trainer_for(model, batches, tmp_path / label, opt=torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-5))
+        tr = _trainer_for(model, batches, tmp_path / label)
         assert tr.model.native_handle().bwd_mode_name() == {'fp32': 'fp32', 'default': 'bf16', 'tf32bwd': 'tf32'}[label]
         losses = []
         for step in range(200):
@@ -550,11 +552,11 @@ def test_loss_trajectory_200_steps_bf16_backward_follows_fp32(tmp_path, monkeypa
             losses.append(loss.clone())
         curves[label] = torch.cat(losses).cpu().double()
     ref = curves['fp32']
-    assert float(ref[-20:].mean()) < 0.8 * float(ref[:20].mean()), 'the reference trajectory does not train'
+    assert float(ref[-50:].mean()) < 0.5 * float(ref[:20].mean()), 'the reference trajectory does not train'
     for label in ('default', 'tf32bwd'):
         c = curves[label]
-        assert abs(float(c[-20:].mean()) - float(ref[-20:].mean())) <= 1e-2 * float(ref[-20:].mean()), \
-            (label, float(c[-20:].mean()), float(ref[-20:].mean()))
+        assert abs(float(c[-50:].mean()) - float(ref[-50:].mean())) <= 1e-2 * float(ref[-50:].mean()), \
+            (label, float(c[-50:].mean()), float(ref[-50:].mean()))
         assert abs(float(c[:20].mean()) - float(ref[:20].mean())) <= 5e-3 * float(ref[:20].mean())
 
 
