@@ -473,23 +473,23 @@ Act act_view(const rd_handle* h, const ConvBlock& b) {
 int pack_weights(rd_handle* h, bool for_backward, cudaStream_t s) {
   const int rnd = h->tf32() ? 1 : 0;
   ProfScope ps(h, RD_PROF_PACK, 0.0, 4.0 * 3.0 * (double)h->param_floats, s);
+  PackJobs J;
   auto block = [&](ConvBlock& b) -> int {
     if (!b.w_kn) return 0;
     // tcgen05 layers read the [N][K] copies, CUDA-core layers the [K][N] copies: pack only what is used
-    return launch_pack_conv3x3(h->P + b.w, b.tc ? nullptr : b.w_kn, b.tc ? b.w_nk : nullptr,
-                               for_backward && !b.tc ? b.wd_kn : nullptr,
-                               for_backward && b.tc && !b.bb ? b.wd_nk : nullptr, for_backward && b.bb ? b.wd_nk_b : nullptr,
-                               b.Cout, b.Cin, rnd && b.tc, s);
+    return pack_jobs_add(J, PACK_CONV3X3, h->P + b.w, b.tc ? nullptr : b.w_kn, b.tc ? b.w_nk : nullptr,
+                         for_backward && !b.tc ? b.wd_kn : nullptr, for_backward && b.tc && !b.bb ? b.wd_nk : nullptr,
+                         for_backward && b.bb ? b.wd_nk_b : nullptr, b.Cout, b.Cin, rnd && b.tc);
   };
   for (auto& b : h->enc) RD_TRY(block(b));
   RD_TRY(block(h->bott));
   for (auto& b : h->dec) RD_TRY(block(b));
   for (auto& u : h->ups) {
-    if (u.bilinear) RD_TRY(launch_pack_conv1x1(h->P + u.w, u.w_nk, u.w_kn, u.C, u.C, rnd && u.tc, s));
-    else RD_TRY(launch_pack_convt(h->P + u.w, u.w_kn, u.w_nk, for_backward && u.bb ? u.w_kn_b : nullptr, u.C, u.C,
-                                  rnd && u.tc, s));
+    if (u.bilinear) RD_TRY(pack_jobs_add(J, PACK_CONV1X1, h->P + u.w, u.w_nk, u.w_kn, nullptr, nullptr, nullptr, u.C, u.C, rnd && u.tc));
+    else RD_TRY(pack_jobs_add(J, PACK_CONVT, h->P + u.w, u.w_kn, u.w_nk, nullptr, nullptr, for_backward && u.bb ? u.w_kn_b : nullptr,
+                              u.C, u.C, rnd && u.tc));
   }
-  return 0;
+  return launch_pack_batched(J, s);      // one launch for all layers
 }
 
 // conv3x3 of one block: src NHWC [B,H,W,Cin] -> z (+ statistics partials)

@@ -120,6 +120,23 @@ int launch_sum_partials(const float* part, int nparts, int n, int row_stride, in
 int launch_pack_conv3x3(const float* w, float* kn, float* nk, float* dkn, float* dnk, void* dnk_b, int Co, int Ci,
                         int round_tf32, cudaStream_t s);
 int launch_pack_convt(const float* w, float* kn, float* nk, void* kn_b, int Ci, int Co, int round_tf32, cudaStream_t s);
+// all layers in one launch: collect jobs with pack_jobs_add (same output meanings as the per-layer launchers above;
+// conv1x1: o0 = copy, o1 = transpose), then launch_pack_batched
+enum { PACK_CONV3X3 = 0, PACK_CONV3X3_TILED = 1, PACK_CONVT = 2, PACK_CONV1X1 = 3 };
+static constexpr int PACK_MAX_JOBS = 40;
+struct PackJob {
+  const float* w;
+  float *o0, *o1, *o2, *o3;
+  void* ob;
+  int kind, Co, Ci, rnd, block0;
+};
+struct PackJobs {
+  int n = 0, total_blocks = 0;
+  PackJob job[PACK_MAX_JOBS];
+};
+int pack_jobs_add(PackJobs& J, int kind, const float* w, float* o0, float* o1, float* o2, float* o3, void* ob, int Co,
+                  int Ci, int rnd);
+int launch_pack_batched(const PackJobs& J, cudaStream_t s);
 // reduce split partials and un-pack to the PyTorch layouts
 //   conv: part [S][(t,ci)][co] -> dW OIHW ;  convT: part [S][(a,b,co)][ci] -> dW [ci][co][2][2]
 int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s);

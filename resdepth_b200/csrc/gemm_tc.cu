@@ -173,19 +173,22 @@ __device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg
     tmem_ld32(t_row + ch * 32, v);
     int co;
     const unsigned S = chunk_off(ch, co);
-    const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 bv = __ldg(bp + j);
-      sts128(stg_s + (lane * 32 + ((j ^ (lane & 7)) << 2)) * 4,
-             make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w));
+    // bias / BatchNorm constants of this lane's four channels in the transposed domain: requested before the staging
+    // stores, consumed after them (they used to be eight row-domain loads in front of the stores)
+    const float4 bi = __ldg(reinterpret_cast<const float4*>(P.bias + co) + c4);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sl = 0.f;
+    if (has_skip && P.skip_scale) {
+      sc = __ldg(reinterpret_cast<const float4*>(P.skip_scale + co) + c4);
+      sh = __ldg(reinterpret_cast<const float4*>(P.skip_shift + co) + c4);
+      sl = __ldg(P.skip_slope);
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(stg_s + (lane * 32 + ((j ^ (lane & 7)) << 2)) * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
     __syncwarp();
     if (has_skip && ch + 2 < NCH) prefetch(ch + 2, a_nxt);     // v[] is dead here: a_nxt takes its registers
     if (has_skip && P.skip_scale) {    // the skip tensor is a raw conv output: BatchNorm + activation of its layer
-      const float4 sc = __ldg(reinterpret_cast<const float4*>(P.skip_scale + co) + c4);
-      const float4 sh = __ldg(reinterpret_cast<const float4*>(P.skip_shift + co) + c4);
-      const float sl = __ldg(P.skip_slope);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float y0 = fmaf(a_cur[i].x, sc.x, sh.x), y1 = fmaf(a_cur[i].y, sc.y, sh.y);
@@ -198,7 +201,8 @@ __device__ __forceinline__ void convt_epilogue(const TcRowsParams& P, float* stg
     for (int i = 0; i < 8; ++i) {
       const int r = i * 4 + (lane >> 3);
       float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
-      val.x += a_cur[i].x; val.y += a_cur[i].y; val.z += a_cur[i].z; val.w += a_cur[i].w;
+      val.x = (val.x + bi.x) + a_cur[i].x; val.y = (val.y + bi.y) + a_cur[i].y;     // (acc + bias) + skip
+      val.z = (val.z + bi.z) + a_cur[i].z; val.w = (val.w + bi.w) + a_cur[i].w;
       if (P.round_tf32) {
         val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w);
       }
@@ -284,6 +288,24 @@ __device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8
   for (int m = 0; m < RING_SLOTS - 1; ++m) issue(m);
   __nv_bfloat16* outb = reinterpret_cast<__nv_bfloat16*>(P.out_b);
   const float sl = P.skip_scale ? __ldg(P.skip_slope) : 0.f;
+  // per-channel constants of a chunk (bias, BatchNorm scale / shift of the skip's layer) for THIS lane's four channels of
+  // the transposed domain, fetched one chunk ahead: ncu (round 2) had a third of the epilogue's warp samples on the first
+  // use of these L1-resident loads when they were issued inside the chunk that consumes them
+  auto chunk_consts = [&](int m, float4& bi, float4& sc, float4& sh) {
+    bi = make_float4(0.f, 0.f, 0.f, 0.f); sc = make_float4(1.f, 1.f, 1.f, 1.f); sh = bi;
+    if (m < total) {
+      const int tile = blockIdx.x + (m / NCH2) * gridDim.x;
+      int co;
+      (void)chunk_off(tile % n_tiles, 2 * (m % NCH2) + half, co);
+      bi = __ldg(reinterpret_cast<const float4*>(P.bias + co) + c4);
+      if (P.skip_scale) {
+        sc = __ldg(reinterpret_cast<const float4*>(P.skip_scale + co) + c4);
+        sh = __ldg(reinterpret_cast<const float4*>(P.skip_shift + co) + c4);
+      }
+    }
+  };
+  float4 bi, sc, sh, bi_n, sc_n, sh_n;
+  chunk_consts(0, bi, sc, sh);
   unsigned R[8];
   unsigned okm = 0;
   int nt = 0, acc = 0;
@@ -307,21 +329,13 @@ __device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8
     const int ch = 2 * ci + half;
     int co;
     const unsigned S = chunk_off(nt, ch, co);
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (P.skip_scale) {
-      sc = __ldg(reinterpret_cast<const float4*>(P.skip_scale + co) + c4);
-      sh = __ldg(reinterpret_cast<const float4*>(P.skip_shift + co) + c4);
-    }
+    chunk_consts(m + 1, bi_n, sc_n, sh_n);
     {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
-      const float4* bp = reinterpret_cast<const float4*>(P.bias + co);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bv = __ldg(bp + j);
-        sts128(stg_s + (lane * 32 + ((j ^ (lane & 7)) << 2)) * 4,
-             make_float4(v[4 * j] + bv.x, v[4 * j + 1] + bv.y, v[4 * j + 2] + bv.z, v[4 * j + 3] + bv.w));
-      }
+      for (int j = 0; j < 8; ++j)
+        sts128(stg_s + (lane * 32 + ((j ^ (lane & 7)) << 2)) * 4, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
     }
     __syncwarp();
     cp_async_wait<RING_SLOTS - 1>();                    // this chunk's skip rows have landed
@@ -337,7 +351,8 @@ __device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8
         a.z = y2 > 0.f ? y2 : y2 * sl; a.w = y3 > 0.f ? y3 : y3 * sl;
       }
       float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
-      val.x += a.x; val.y += a.y; val.z += a.z; val.w += a.w;
+      val.x = (val.x + bi.x) + a.x; val.y = (val.y + bi.y) + a.y;           // (acc + bias) + skip
+      val.z = (val.z + bi.z) + a.z; val.w = (val.w + bi.w) + a.w;
       if (P.round_tf32) {
         val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w);
       }
@@ -359,6 +374,7 @@ __device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    bi = bi_n; sc = sc_n; sh = sh_n;
   }
   cp_async_wait<0>();
 }

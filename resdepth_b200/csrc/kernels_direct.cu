@@ -389,6 +389,120 @@ conv_last_fwd64_kernel(const float* __restrict__ u, const float* __restrict__ w,
   conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
 }
 
+// Persistent form of the kernel above with the u rows of a half-warp fetched by cp.async into a per-half-warp ring,
+// LF_NST - 1 iterations (4 halo pixels = 1 KB) ahead and across tile boundaries: the one-tile-per-CTA kernel prefetched a
+// single iteration into registers and restarted its pipeline every 10 iterations (ncu, round 2: 23 % of the warp samples
+// on the first use of a loaded row, DRAM 37 %).  Each lane reads back exactly the 16 bytes it copied.
+static constexpr int LF_NST = 4;
+__device__ __forceinline__ void lf_cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const uint32_t n = pred ? 16u : 0u;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__global__ void __launch_bounds__(256, 2)
+conv_last_fwd64_ring_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
+                            const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
+                            float* __restrict__ y, int B, int H, int W, int C, int tiles_x, int tiles_y, int ntiles) {
+  __shared__ float ts[LH_H * LH_W][9];
+  __shared__ float wsm[64 * 9];
+  extern __shared__ __align__(16) float4 lf_ring[];       // [16 half-warps][LF_NST][4 pixels][16 lanes]
+  const int tid = threadIdx.x;
+  const int l16 = tid & 15, hw = tid >> 4;
+  const int c0 = l16 * 4;
+  for (int i = tid; i < C * 9; i += 256) wsm[i] = w[i];
+  __syncthreads();
+  const int tsel = l16 & 3;                 // tap order of this lane
+  const int pperm = (l16 >> 2) & 3;         // pixel order of this lane (slot i holds pixel i ^ pperm)
+  int tap[9];
+  float4 wr[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    tap[k] = kTapPerm[tsel][k];
+    wr[k] = c0 < C ? make_float4(wsm[(c0 + 0) * 9 + tap[k]], wsm[(c0 + 1) * 9 + tap[k]], wsm[(c0 + 2) * 9 + tap[k]],
+                                 wsm[(c0 + 3) * 9 + tap[k]])
+                   : make_float4(0, 0, 0, 0);
+  }
+  const int tap0 = tap[0], tap1 = tap[1];
+  constexpr int NPIX = LH_H * LH_W, NGROUPS = (NPIX + 3) / 4, NIT = (NGROUPS + 15) / 16;
+  float4* ring = lf_ring + (size_t)hw * LF_NST * 64;
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_it = my_tiles * NIT;
+  auto tile_origin = [&](int it, int& b, int& h0, int& w0) {
+    int t = blockIdx.x + (it / NIT) * gridDim.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    b = t / tiles_y;
+    h0 = ty * LT_H; w0 = tx * LT_W;
+  };
+  auto issue = [&](int it) {
+    if (it < total_it) {
+      int b, h0, w0;
+      tile_origin(it, b, h0, w0);
+      const int g = (it % NIT) * 16 + hw;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = g * 4 + (i ^ pperm);
+        const int hh = p / LH_W, ww = p - hh * LH_W;
+        const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+        const bool ok = p < NPIX && (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W && c0 < C;
+        lf_cp_async16(&ring[((it % LF_NST) * 4 + i) * 16 + l16], ok ? u + (((size_t)b * H + gh) * W + gw) * C + c0 : u, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int k = 0; k < LF_NST - 1; ++k) issue(k);
+#pragma unroll 1
+  for (int it = 0; it < total_it; ++it) {
+    issue(it + LF_NST - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LF_NST - 1) : "memory");
+    const int g = (it % NIT) * 16 + hw;
+    float4 uv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) uv[i] = ring[((it % LF_NST) * 4 + i) * 16 + l16];
+    float v[36];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 ux = make_float2(uv[i].x, uv[i].x), uy = make_float2(uv[i].y, uv[i].y);
+      const float2 uz = make_float2(uv[i].z, uv[i].z);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {                   // two tap slots per FFMA2, same summation order as the scalar form
+        float2 acc = make_float2(uv[i].w * wr[k].w, uv[i].w * wr[k + 1].w);
+        acc = ffma2(uz, make_float2(wr[k].z, wr[k + 1].z), acc);
+        acc = ffma2(uy, make_float2(wr[k].y, wr[k + 1].y), acc);
+        acc = ffma2(ux, make_float2(wr[k].x, wr[k + 1].x), acc);
+        v[i * 9 + k] = acc.x;
+        v[i * 9 + k + 1] = acc.y;
+      }
+      v[i * 9 + 8] = fmaf(uv[i].x, wr[8].x, fmaf(uv[i].y, wr[8].y, fmaf(uv[i].z, wr[8].z, uv[i].w * wr[8].w)));
+    }
+#pragma unroll
+    for (int j = 0; j < 18; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 18], 8);     // pixel pairs
+#pragma unroll
+    for (int j = 0; j < 9; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 9], 4);       // pixels
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 5], 2);       // tap groups {0-3|5-8}, 4
+    v[4] += __shfl_xor_sync(0xffffffffu, v[4], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[2], 1);                                       // tap pairs
+    v[1] += __shfl_xor_sync(0xffffffffu, v[3], 1);
+    v[4] += __shfl_xor_sync(0xffffffffu, v[4], 1);
+    const int p = g * 4 + pperm;
+    if (p < NPIX) {
+      ts[p][tap0] = v[0];
+      ts[p][tap1] = v[1];
+      if (tsel == 0) ts[p][4] = v[4];
+    }
+    if (it % NIT == NIT - 1) {                           // tile complete (block-uniform): gather its outputs
+      int b, h0, w0;
+      tile_origin(it, b, h0, w0);
+      __syncthreads();
+      conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
+      __syncthreads();
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(256)
 conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
                      const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
@@ -436,7 +550,13 @@ int launch_conv_last_fwd(const float* u, const float* w, const float* bias, cons
   if (C % 4 || C > 128) return fail("conv_last: unsupported C=%d (needs C%%4==0, C<=128)", C);
   const int tiles_x = cdiv(W, LT_W), tiles_y = cdiv(H, LT_H);
   const int grid = tiles_x * tiles_y * B;
-  if (C <= 64)
+  static const bool no_ring = getenv("RESDEPTH_LAST_FWD_NORING") != nullptr;
+  if (C <= 64 && !no_ring) {
+    const int smem = 16 * LF_NST * 64 * (int)sizeof(float4);
+    RD_CUDA(cudaFuncSetAttribute(conv_last_fwd64_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    conv_last_fwd64_ring_kernel<<<grid < 148 * 2 ? grid : 148 * 2, 256, smem, s>>>(u, w, bias, x, x_bstride, x_affine, y, B,
+                                                                                   H, W, C, tiles_x, tiles_y, grid);
+  } else if (C <= 64)
     conv_last_fwd64_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
   else
     conv_last_fwd_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
@@ -589,6 +709,151 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
   }
 }
 
+// Same pass for C <= 64 with the u rows fetched by cp.async into a per-16-lane-group ring, LB_NST - 1 iterations
+// (4 pixels = 1 KB per group each) ahead of their use -- across tile boundaries.  ncu on the kernel above (round 2):
+// 37 % of all warp samples sat on the first FFMA2 that consumes a freshly loaded u row (long scoreboard), DRAM 40 %;
+// the loads were issued in the iteration that uses them.  Every lane copies exactly the 16 bytes it reads back, so the
+// ring needs no cross-lane synchronisation; its shared memory is reused by the block reduction at the end.
+static constexpr int LB_NST = 4;
+__device__ __forceinline__ void lb_cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const uint32_t n = pred ? 16u : 0u;                  // src-size 0: zero fill, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__global__ void __launch_bounds__(256, 2)
+conv_last_bwd_ring_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ w,
+                          float* __restrict__ du, __nv_bfloat16* __restrict__ du_b, float* __restrict__ part, int B, int H,
+                          int W, int C, int tiles_x, int tiles_y, int ntiles) {
+  __shared__ float dys[LB_HH * LB_HW];
+  extern __shared__ __align__(16) float red_dyn[];    // ring [16 groups][LB_NST][4 pixels][16 lanes] float4, then [16][RS]
+  constexpr int NDW = 9 * 4 * 16;
+  constexpr int RS = NDW + 4 * 16 + 1;
+  constexpr int ITERS = LB_TH * LB_TW / 64;           // iterations of one group per tile
+  const int tid = threadIdx.x;
+  const int lane16 = tid & 15, grp = tid >> 4;
+  const int c = lane16 * 4;
+  const bool cok = c < C;
+  float4 wr[9], dwacc[9], dusum = make_float4(0, 0, 0, 0);
+  float dbacc = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    wr[k] = cok ? make_float4(w[(c + 0) * 9 + k], w[(c + 1) * 9 + k], w[(c + 2) * 9 + k], w[(c + 3) * 9 + k])
+                : make_float4(0, 0, 0, 0);
+    dwacc[k] = make_float4(0, 0, 0, 0);
+  }
+  float4* ring = reinterpret_cast<float4*>(red_dyn) + (size_t)grp * LB_NST * 64;
+  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int total_it = my_tiles * ITERS;
+  auto tile_origin = [&](int it, int& b, int& h0, int& w0) {
+    int t = blockIdx.x + (it / ITERS) * gridDim.x;
+    const int tx = t % tiles_x; t /= tiles_x;
+    const int ty = t % tiles_y;
+    b = t / tiles_y;
+    h0 = ty * LB_TH; w0 = tx * LB_TW;
+  };
+  auto issue = [&](int it) {
+    if (it < total_it) {
+      int b, h0, w0;
+      tile_origin(it, b, h0, w0);
+      const int p0 = grp + 64 * (it % ITERS);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int p = p0 + 16 * i;
+        const int gh = h0 + p / LB_TW, gw = w0 + p % LB_TW;
+        const bool ok = cok && gh < H && gw < W;
+        lb_cp_async16(&ring[((it % LB_NST) * 4 + i) * 16 + lane16],
+                      ok ? u + (((size_t)b * H + gh) * W + gw) * C + c : u, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // empty groups keep the group count uniform
+  };
+#pragma unroll
+  for (int k = 0; k < LB_NST - 1; ++k) issue(k);
+  int b = 0, h0 = 0, w0 = 0;
+#pragma unroll 1
+  for (int it = 0; it < total_it; ++it) {
+    if (it % ITERS == 0) {                              // next tile: its dy halo (block-uniform branch)
+      tile_origin(it, b, h0, w0);
+      __syncthreads();
+      for (int i = tid; i < LB_HH * LB_HW; i += 256) {
+        const int hh = i / LB_HW, ww = i % LB_HW;
+        const int gh = h0 + hh - 1, gw = w0 + ww - 1;
+        dys[i] = (gh >= 0 && gh < H && gw >= 0 && gw < W) ? dy[((size_t)b * H + gh) * W + gw] : 0.f;
+      }
+      __syncthreads();
+    }
+    issue(it + LB_NST - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(LB_NST - 1) : "memory");
+    const int p0 = grp + 64 * (it % ITERS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int p = p0 + 16 * i;
+      const int lh = p / LB_TW, lw = p % LB_TW;
+      const int gh = h0 + lh, gw = w0 + lw;
+      if (gh >= H || gw >= W) continue;
+      float n[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * LB_HW + (lw + 1 - (s2 - 1))];
+      if (lane16 == 0) dbacc += n[4];
+      if (!cok) continue;
+      const float4 uv = ring[((it % LB_NST) * 4 + i) * 16 + lane16];
+      float4 d = make_float4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float2 nk = make_float2(n[k], n[k]);
+        const float2 lo = ffma2(nk, make_float2(wr[k].x, wr[k].y), make_float2(d.x, d.y));
+        const float2 hi = ffma2(nk, make_float2(wr[k].z, wr[k].w), make_float2(d.z, d.w));
+        d = make_float4(lo.x, lo.y, hi.x, hi.y);
+        const float2 lo2 = ffma2(make_float2(uv.x, uv.y), nk, make_float2(dwacc[k].x, dwacc[k].y));
+        const float2 hi2 = ffma2(make_float2(uv.z, uv.w), nk, make_float2(dwacc[k].z, dwacc[k].w));
+        dwacc[k] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+      }
+      const size_t o = (((size_t)b * H + gh) * W + gw) * C + c;
+      if (du) *reinterpret_cast<float4*>(du + o) = d;
+      if (du_b) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(du_b + o) = pk;
+      }
+      dusum.x += d.x; dusum.y += d.y; dusum.z += d.z; dusum.w += d.w;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();                                      // the ring is dead: its memory becomes the reduction buffer
+  // block reduction over the 16 pixel groups -> part[blk][C*9 dW][1 db][C channel sums of du]
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float* rr = red_dyn + grp * RS + (lane16 * 9 + k) * 4;
+    rr[0] = dwacc[k].x; rr[1] = dwacc[k].y; rr[2] = dwacc[k].z; rr[3] = dwacc[k].w;
+  }
+  {
+    float* rr = red_dyn + grp * RS + NDW + lane16 * 4;
+    rr[0] = dusum.x; rr[1] = dusum.y; rr[2] = dusum.z; rr[3] = dusum.w;
+  }
+  if (lane16 == 0) red_dyn[grp * RS + RS - 1] = dbacc;
+  __syncthreads();
+  const size_t prow = (size_t)blockIdx.x * (C * 10 + 1);
+  for (int i = tid; i < RS; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) a += red_dyn[g * RS + i];
+    if (i == RS - 1) {
+      part[prow + C * 9] = a;
+    } else if (i >= NDW) {
+      const int cc = i - NDW;
+      if (cc < C) part[prow + C * 9 + 1 + cc] = a;
+    } else {
+      const int cc = i & 3, k = (i >> 2) % 9, ql = (i >> 2) / 9;
+      const int ch = ql * 4 + cc;
+      if (ch < C) part[prow + ch * 9 + k] = a;
+    }
+  }
+}
+
 int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float* du, void* du_b, float* dw,
                          float* dbias, float* du_channel_sum, float* scratch, size_t scratch_floats, int B, int H, int W,
                          int C, cudaStream_t s) {
@@ -608,9 +873,18 @@ int launch_conv_last_bwd(const float* u, const float* dy, const float* w, float*
     conv_last_bwd_kernel<1, 2><<<grid, 256, smem, s>>>(u, dy, w, nullptr, nullptr, scratch, B, H, W, C, tiles_x, tiles_y,
                                                        ntiles);
   } else if (C <= 64) {
-    const int smem = 16 * (10 * 4 * 16 * 1 + 1) * (int)sizeof(float);
-    conv_last_bwd_kernel<1, 0><<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B,
-                                                       H, W, C, tiles_x, tiles_y, ntiles);
+    static const bool no_ring = getenv("RESDEPTH_LAST_BWD_NORING") != nullptr;
+    const int red = 16 * (10 * 4 * 16 * 1 + 1) * (int)sizeof(float);
+    if (no_ring) {
+      conv_last_bwd_kernel<1, 0><<<grid, 256, red, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B,
+                                                        H, W, C, tiles_x, tiles_y, ntiles);
+    } else {
+      const int ring = 16 * LB_NST * 64 * (int)sizeof(float4);
+      const int smem = ring > red ? ring : red;
+      RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv_last_bwd_ring_kernel<<<grid, 256, smem, s>>>(u, dy, w, du, reinterpret_cast<__nv_bfloat16*>(du_b), scratch, B,
+                                                        H, W, C, tiles_x, tiles_y, ntiles);
+    }
   } else {
     const int smem = 16 * (10 * 4 * 16 * 2 + 1) * (int)sizeof(float);
     RD_CUDA(cudaFuncSetAttribute(conv_last_bwd_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -136,3 +136,26 @@ def test_epoch_prefetcher_keeps_order_and_stages_one_batch_ahead():
                       ('step', 12), ('step', 13)]
     assert list(tr._prefetched(iter([]))) == []
     assert [b['staged'] for b in tr._prefetched([7])] == [7]
+
+
+def test_rd_config_layout_matches_header_and_integration_snippet():
+    """The ctypes struct, the C header and the binding snippet in INTEGRATION.md list the same int32 fields in the
+    same order (a short struct handed to rd_create reads garbage: VERDICT r1 'docs bug with teeth')."""
+    import ctypes
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, 'include', 'resdepth_b200.h')).read()
+    body = header[header.index('typedef struct rd_config {'):header.index('} rd_config;')]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for decl in re.findall(r'int32_t\s+([^;]+);', body):
+        fields += [n.strip() for n in decl.split(',')]
+    from resdepth_b200 import _native
+    assert [n for n, _ in _native.RdConfig._fields_] == fields
+    assert ctypes.sizeof(_native.RdConfig) == 4 * len(fields) == 56
+    doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+    snippet = doc[doc.index('class RdConfig(C.Structure)'):doc.index('lib.rd_create.argtypes')]
+    assert re.findall(r"'(\w+)'", snippet) == fields
+    # every symbol the header declares is bound, and vice versa
+    declared = set(re.findall(r'\b(rd_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
