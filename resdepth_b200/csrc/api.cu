@@ -102,6 +102,7 @@ struct Workspace {
   void* xcol_b = nullptr;
   int xcol_b_k = 0;
   float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
+  float* taps = nullptr;       // last-conv forward: 9 tap partial sums per pixel
 };
 }  // namespace rd
 
@@ -283,6 +284,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   h->coef = c.take(4 * 2048);
   h->consts = c.take(64);
   h->ob_mean = c.take(4); h->ob_invstd = c.take(4); h->ob_affine = c.take(4);
+  h->taps = c.take((size_t)9 * B * T * T);               // tap partials of the last conv's forward (planar, 36 B / pixel)
   if (bwd) {
     h->part_floats = (size_t)8 << 20;
     h->part = c.take(h->part_floats);
@@ -868,7 +870,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
     }
     RD_TRY(launch_conv_last_fwd(h->ups[D - 1].u, h->P + h->last_w, h->last_b >= 0 ? h->P + h->last_b : nullptr,
                                 h->cfg.outer_skip ? x : nullptr, h->cfg.n_input_channels * T * T, x_affine, y, B, T, T,
-                                C0, s));
+                                C0, h->taps, s));
   }
   if (save) { h->fwd_batch = B; h->fwd_tile = T; h->fwd_mode = mode; h->bw_next_stage = 0; }
   return 0;

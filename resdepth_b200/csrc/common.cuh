@@ -52,8 +52,9 @@ int launch_conv_first_wgrad(const float* x, const float* dz, float* dw_oihw, flo
                             int B, int Cin, int H, int W, int Cout, cudaStream_t s);
 // last conv C->1 (+bias +residual x[:,0]):  u NHWC [B,H,W,C] -> y [B,H,W]
 //   x_affine (optional, 2 floats: scale, shift): the residual is x0*scale+shift (outer_skip_BN)
+//   tap_scratch (optional, 9*B*H*W floats): enables the thread-per-pixel two-pass form for C = 32 / 64
 int launch_conv_last_fwd(const float* u, const float* w_oihw, const float* bias, const float* x_nchw, int x_cstride_b,
-                         const float* x_affine, float* y, int B, int H, int W, int C, cudaStream_t s);
+                         const float* x_affine, float* y, int B, int H, int W, int C, float* tap_scratch, cudaStream_t s);
 // backward of the last conv: du NHWC (written), dW (OIHW [1,C,3,3], written), dbias (written if non-null)
 //   du_channel_sum (optional, [C]): per-channel sums of du = bias gradient of the transposed conv that produced u
 //   du_b (optional): bf16 copy of du

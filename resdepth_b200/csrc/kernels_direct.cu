@@ -389,118 +389,10 @@ conv_last_fwd64_kernel(const float* __restrict__ u, const float* __restrict__ w,
   conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
 }
 
-// Persistent form of the kernel above with the u rows of a half-warp fetched by cp.async into a per-half-warp ring,
-// LF_NST - 1 iterations (4 halo pixels = 1 KB) ahead and across tile boundaries: the one-tile-per-CTA kernel prefetched a
-// single iteration into registers and restarted its pipeline every 10 iterations (ncu, round 2: 23 % of the warp samples
-// on the first use of a loaded row, DRAM 37 %).  Each lane reads back exactly the 16 bytes it copied.
-static constexpr int LF_NST = 4;
 __device__ __forceinline__ void lf_cp_async16(void* smem_dst, const void* gsrc, bool pred) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const uint32_t n = pred ? 16u : 0u;
+  const uint32_t n = pred ? 16u : 0u;                  // src-size 0: zero fill, nothing is read
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__global__ void __launch_bounds__(256, 2)
-conv_last_fwd64_ring_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
-                            const float* __restrict__ x0, long long x_bstride, const float* __restrict__ x_affine,
-                            float* __restrict__ y, int B, int H, int W, int C, int tiles_x, int tiles_y, int ntiles) {
-  __shared__ float ts[LH_H * LH_W][9];
-  __shared__ float wsm[64 * 9];
-  extern __shared__ __align__(16) float4 lf_ring[];       // [16 half-warps][LF_NST][4 pixels][16 lanes]
-  const int tid = threadIdx.x;
-  const int l16 = tid & 15, hw = tid >> 4;
-  const int c0 = l16 * 4;
-  for (int i = tid; i < C * 9; i += 256) wsm[i] = w[i];
-  __syncthreads();
-  const int tsel = l16 & 3;                 // tap order of this lane
-  const int pperm = (l16 >> 2) & 3;         // pixel order of this lane (slot i holds pixel i ^ pperm)
-  int tap[9];
-  float4 wr[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    tap[k] = kTapPerm[tsel][k];
-    wr[k] = c0 < C ? make_float4(wsm[(c0 + 0) * 9 + tap[k]], wsm[(c0 + 1) * 9 + tap[k]], wsm[(c0 + 2) * 9 + tap[k]],
-                                 wsm[(c0 + 3) * 9 + tap[k]])
-                   : make_float4(0, 0, 0, 0);
-  }
-  const int tap0 = tap[0], tap1 = tap[1];
-  constexpr int NPIX = LH_H * LH_W, NGROUPS = (NPIX + 3) / 4, NIT = (NGROUPS + 15) / 16;
-  float4* ring = lf_ring + (size_t)hw * LF_NST * 64;
-  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total_it = my_tiles * NIT;
-  auto tile_origin = [&](int it, int& b, int& h0, int& w0) {
-    int t = blockIdx.x + (it / NIT) * gridDim.x;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    b = t / tiles_y;
-    h0 = ty * LT_H; w0 = tx * LT_W;
-  };
-  auto issue = [&](int it) {
-    if (it < total_it) {
-      int b, h0, w0;
-      tile_origin(it, b, h0, w0);
-      const int g = (it % NIT) * 16 + hw;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int p = g * 4 + (i ^ pperm);
-        const int hh = p / LH_W, ww = p - hh * LH_W;
-        const int gh = h0 + hh - 1, gw = w0 + ww - 1;
-        const bool ok = p < NPIX && (unsigned)gh < (unsigned)H && (unsigned)gw < (unsigned)W && c0 < C;
-        lf_cp_async16(&ring[((it % LF_NST) * 4 + i) * 16 + l16], ok ? u + (((size_t)b * H + gh) * W + gw) * C + c0 : u, ok);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-#pragma unroll
-  for (int k = 0; k < LF_NST - 1; ++k) issue(k);
-#pragma unroll 1
-  for (int it = 0; it < total_it; ++it) {
-    issue(it + LF_NST - 1);
-    asm volatile("cp.async.wait_group %0;" ::"n"(LF_NST - 1) : "memory");
-    const int g = (it % NIT) * 16 + hw;
-    float4 uv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) uv[i] = ring[((it % LF_NST) * 4 + i) * 16 + l16];
-    float v[36];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 ux = make_float2(uv[i].x, uv[i].x), uy = make_float2(uv[i].y, uv[i].y);
-      const float2 uz = make_float2(uv[i].z, uv[i].z);
-#pragma unroll
-      for (int k = 0; k < 8; k += 2) {                   // two tap slots per FFMA2, same summation order as the scalar form
-        float2 acc = make_float2(uv[i].w * wr[k].w, uv[i].w * wr[k + 1].w);
-        acc = ffma2(uz, make_float2(wr[k].z, wr[k + 1].z), acc);
-        acc = ffma2(uy, make_float2(wr[k].y, wr[k + 1].y), acc);
-        acc = ffma2(ux, make_float2(wr[k].x, wr[k + 1].x), acc);
-        v[i * 9 + k] = acc.x;
-        v[i * 9 + k + 1] = acc.y;
-      }
-      v[i * 9 + 8] = fmaf(uv[i].x, wr[8].x, fmaf(uv[i].y, wr[8].y, fmaf(uv[i].z, wr[8].z, uv[i].w * wr[8].w)));
-    }
-#pragma unroll
-    for (int j = 0; j < 18; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 18], 8);     // pixel pairs
-#pragma unroll
-    for (int j = 0; j < 9; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 9], 4);       // pixels
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j + 5], 2);       // tap groups {0-3|5-8}, 4
-    v[4] += __shfl_xor_sync(0xffffffffu, v[4], 2);
-    v[0] += __shfl_xor_sync(0xffffffffu, v[2], 1);                                       // tap pairs
-    v[1] += __shfl_xor_sync(0xffffffffu, v[3], 1);
-    v[4] += __shfl_xor_sync(0xffffffffu, v[4], 1);
-    const int p = g * 4 + pperm;
-    if (p < NPIX) {
-      ts[p][tap0] = v[0];
-      ts[p][tap1] = v[1];
-      if (tsel == 0) ts[p][4] = v[4];
-    }
-    if (it % NIT == NIT - 1) {                           // tile complete (block-uniform): gather its outputs
-      int b, h0, w0;
-      tile_origin(it, b, h0, w0);
-      __syncthreads();
-      conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
-      __syncthreads();
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(256)
@@ -545,18 +437,138 @@ conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, c
   conv_last_gather(ts, bias, x0, x_bstride, x_affine, y, b, h0, w0, H, W);
 }
 
+// ----------------------------------------------------------------------------------------------
+// last conv forward, thread-per-pixel form (C = 32 / 64).  The half-warp-per-pixel kernels above spend most of their
+// issue slots on the cross-lane reduction and on index arithmetic (ncu, round 2: 58 % SM throughput at 37 % DRAM).
+// Here a pixel's 9 tap partials t[p][k] = sum_c u[p][c] W[c][k] are formed by ONE thread, so there is nothing to
+// reduce, and a warp instruction serves 32 pixels with one broadcast weight load:
+//   pass 1 (conv_last_taps_kernel): persistent CTAs stream contiguous chunks of 256 pixels (256 x C floats, one
+//     contiguous block of the NHWC tensor) through a 3-stage cp.async ring into shared memory rows padded to C*4 + 16
+//     bytes (conflict-free LDS.128 per thread); per channel quad 1 + 9 LDS.128 and 18 FFMA2; the 9 partials go to
+//     planar scratch t[k][pixel] (coalesced 128-byte stores).  No halo: every u element is read exactly once.
+//   pass 2 (conv_last_gather_kernel): y[q] = bias + x0[q] + sum_k t[k][q + off(k)]   (36 B per pixel, L2-resident)
+// ----------------------------------------------------------------------------------------------
+static constexpr int LTP_PIX = 256, LTP_NST = 3;
+template <int C>
+__global__ void __launch_bounds__(256, 1)
+conv_last_taps_kernel(const float* __restrict__ u, const float* __restrict__ w, float* __restrict__ taps, long long NP) {
+  constexpr int Q = C / 4, ROWB = C * 4 + 16, STAGE = LTP_PIX * ROWB;
+  extern __shared__ __align__(16) uint8_t ltp_smem[];
+  float* wq = reinterpret_cast<float*>(ltp_smem + LTP_NST * STAGE);       // [Q][36]: 4 x (k 0..7), then k = 8 of the 4 channels
+  const int tid = threadIdx.x;
+  for (int i = tid; i < C * 9; i += 256) {
+    const int c = i / 9, k = i - c * 9;
+    wq[(c >> 2) * 36 + (k < 8 ? (c & 3) * 8 + k : 32 + (c & 3))] = w[i];
+  }
+  const long long nchunks = (NP + LTP_PIX - 1) / LTP_PIX;
+  auto issue = [&](long long n) {                      // n-th chunk of this CTA
+    const long long chunk = (long long)blockIdx.x + n * gridDim.x;
+    if (chunk < nchunks) {
+      uint8_t* dst = ltp_smem + (int)(n % LTP_NST) * STAGE;
+      const long long p0 = chunk * LTP_PIX;
+#pragma unroll
+      for (int j = 0; j < Q; ++j) {
+        const int idx = j * 256 + tid;
+        const int px = idx / Q, ch = idx % Q;
+        const bool ok = p0 + px < NP;
+        lf_cp_async16(dst + px * ROWB + ch * 16, ok ? u + (size_t)(p0 + px) * C + ch * 4 : u, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int n = 0; n < LTP_NST - 1; ++n) issue(n);
+  for (long long n = 0;; ++n) {
+    const long long chunk = (long long)blockIdx.x + n * gridDim.x;
+    if (chunk >= nchunks) break;
+    asm volatile("cp.async.wait_group %0;" ::"n"(LTP_NST - 2) : "memory");
+    __syncthreads();                                   // chunk n has landed for every thread; chunk n-1's stage is free
+    issue(n + LTP_NST - 1);
+    const uint8_t* row = ltp_smem + (int)(n % LTP_NST) * STAGE + tid * ROWB;
+    float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01, a8 = a01;
+#pragma unroll
+    for (int cq = 0; cq < Q; ++cq) {
+      const float4 uv = *reinterpret_cast<const float4*>(row + cq * 16);
+      const float4* wp = reinterpret_cast<const float4*>(wq + cq * 36);
+      const float uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 wa = wp[2 * j], wb = wp[2 * j + 1];
+        const float2 ub = make_float2(uu[j], uu[j]);
+        a01 = ffma2(ub, make_float2(wa.x, wa.y), a01);
+        a23 = ffma2(ub, make_float2(wa.z, wa.w), a23);
+        a45 = ffma2(ub, make_float2(wb.x, wb.y), a45);
+        a67 = ffma2(ub, make_float2(wb.z, wb.w), a67);
+      }
+      const float4 w8 = wp[8];
+      a8 = ffma2(make_float2(uv.x, uv.y), make_float2(w8.x, w8.y), a8);
+      a8 = ffma2(make_float2(uv.z, uv.w), make_float2(w8.z, w8.w), a8);
+    }
+    const long long p = chunk * LTP_PIX + tid;
+    if (p < NP) {
+      taps[0 * NP + p] = a01.x; taps[1 * NP + p] = a01.y; taps[2 * NP + p] = a23.x; taps[3 * NP + p] = a23.y;
+      taps[4 * NP + p] = a45.x; taps[5 * NP + p] = a45.y; taps[6 * NP + p] = a67.x; taps[7 * NP + p] = a67.y;
+      taps[8 * NP + p] = a8.x + a8.y;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256)
+conv_last_gather_kernel(const float* __restrict__ taps, const float* __restrict__ bias, const float* __restrict__ x0,
+                        long long x_bstride, const float* __restrict__ x_affine, float* __restrict__ y, int B, int H, int W) {
+  const long long NP = (long long)B * H * W;
+  const float bv = bias ? bias[0] : 0.f;
+  const float xs = x_affine ? x_affine[0] : 1.f, xo = x_affine ? x_affine[1] : 0.f;
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < NP; p += gridDim.x * 256LL) {
+    const int gw = (int)(p % W);
+    const long long r_ = p / W;
+    const int gh = (int)(r_ % H);
+    const long long b = r_ / H;
+    float a = bv;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hh = gh + r - 1;
+      if ((unsigned)hh >= (unsigned)H) continue;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int ww = gw + q - 1;
+        if ((unsigned)ww < (unsigned)W) a += __ldg(taps + (size_t)(r * 3 + q) * NP + p + (long long)(r - 1) * W + (q - 1));
+      }
+    }
+    if (x0) a += fmaf(__ldg(x0 + (size_t)b * x_bstride + (size_t)gh * W + gw), xs, xo);
+    y[p] = a;
+  }
+}
+
 int launch_conv_last_fwd(const float* u, const float* w, const float* bias, const float* x, int x_bstride,
-                         const float* x_affine, float* y, int B, int H, int W, int C, cudaStream_t s) {
+                         const float* x_affine, float* y, int B, int H, int W, int C, float* tap_scratch, cudaStream_t s) {
   if (C % 4 || C > 128) return fail("conv_last: unsupported C=%d (needs C%%4==0, C<=128)", C);
+  static const bool no_tp = getenv("RESDEPTH_LAST_FWD_OLD") != nullptr;
+  if (tap_scratch && !no_tp && (C == 64 || C == 32)) {
+    // thread-per-pixel tap partials (planar scratch, 9 floats per pixel), then the 3x3 gather
+    const long long NP = (long long)B * H * W;
+    const long long nchunks = (NP + LTP_PIX - 1) / LTP_PIX;
+    const int grid = (int)(nchunks < 148 ? nchunks : 148);
+    if (C == 64) {
+      const int smem = LTP_NST * LTP_PIX * (64 * 4 + 16) + 64 * 9 * 4;
+      RD_CUDA(cudaFuncSetAttribute(conv_last_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv_last_taps_kernel<64><<<grid, 256, smem, s>>>(u, w, tap_scratch, NP);
+    } else {
+      const int smem = LTP_NST * LTP_PIX * (32 * 4 + 16) + 32 * 9 * 4;
+      RD_CUDA(cudaFuncSetAttribute(conv_last_taps_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      conv_last_taps_kernel<32><<<grid, 256, smem, s>>>(u, w, tap_scratch, NP);
+    }
+    RD_LAUNCHED();
+    const long long blocks = (NP + 255) / 256;
+    conv_last_gather_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, s>>>(tap_scratch, bias, x, x_bstride, x_affine,
+                                                                                    y, B, H, W);
+    RD_LAUNCHED();
+    return 0;
+  }
   const int tiles_x = cdiv(W, LT_W), tiles_y = cdiv(H, LT_H);
   const int grid = tiles_x * tiles_y * B;
-  static const bool no_ring = getenv("RESDEPTH_LAST_FWD_NORING") != nullptr;
-  if (C <= 64 && !no_ring) {
-    const int smem = 16 * LF_NST * 64 * (int)sizeof(float4);
-    RD_CUDA(cudaFuncSetAttribute(conv_last_fwd64_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    conv_last_fwd64_ring_kernel<<<grid < 148 * 2 ? grid : 148 * 2, 256, smem, s>>>(u, w, bias, x, x_bstride, x_affine, y, B,
-                                                                                   H, W, C, tiles_x, tiles_y, grid);
-  } else if (C <= 64)
+  if (C <= 64)
     conv_last_fwd64_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
   else
     conv_last_fwd_kernel<<<grid, 256, 0, s>>>(u, w, bias, x, x_bstride, x_affine, y, B, H, W, C, tiles_x, tiles_y);
@@ -709,28 +721,37 @@ conv_last_bwd_kernel(const float* __restrict__ u, const float* __restrict__ dy, 
   }
 }
 
-// Same pass for C <= 64 with the u rows fetched by cp.async into a per-16-lane-group ring, LB_NST - 1 iterations
-// (4 pixels = 1 KB per group each) ahead of their use -- across tile boundaries.  ncu on the kernel above (round 2):
-// 37 % of all warp samples sat on the first FFMA2 that consumes a freshly loaded u row (long scoreboard), DRAM 40 %;
-// the loads were issued in the iteration that uses them.  Every lane copies exactly the 16 bytes it reads back, so the
-// ring needs no cross-lane synchronisation; its shared memory is reused by the block reduction at the end.
+// Same pass for C <= 64, restructured after two ncu captures (round 2).  (1) The kernel above issued its u loads in the
+// iteration that consumes them: 37 % of the warp samples sat on the first FFMA2 of a fresh row.  Here the rows are
+// fetched by cp.async into a per-16-lane-group ring, LB_NST - 1 iterations (4 pixels = 1 KB per group) ahead and across
+// tile boundaries; every lane reads back exactly the 16 bytes it copied, so the ring needs no cross-lane
+// synchronisation, and its shared memory is reused by the block reduction at the end.  (2) With the latency hidden the
+// kernel was issue-bound on index arithmetic (~1000 instructions per 4-pixel iteration for 144 FFMA2): an iteration now
+// covers four CONSECUTIVE pixels of one row, so the nine dy taps of each pixel come from one 3 x 6 register window
+// (six vector loads), output addresses are one base plus i*C, and tile coordinates are decoded once per tile.
 static constexpr int LB_NST = 4;
+static constexpr int LB_DW = 36;                        // padded row length of the dy halo tile (vector loads)
 __device__ __forceinline__ void lb_cp_async16(void* smem_dst, const void* gsrc, bool pred) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   const uint32_t n = pred ? 16u : 0u;                  // src-size 0: zero fill, nothing is read
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
 }
+struct LbCursor {                                       // position of a group in its CTA's tile sequence
+  int t, j, b, h0, w0;
+};
 __global__ void __launch_bounds__(256, 2)
 conv_last_bwd_ring_kernel(const float* __restrict__ u, const float* __restrict__ dy, const float* __restrict__ w,
                           float* __restrict__ du, __nv_bfloat16* __restrict__ du_b, float* __restrict__ part, int B, int H,
                           int W, int C, int tiles_x, int tiles_y, int ntiles) {
-  __shared__ float dys[LB_HH * LB_HW];
+  __shared__ __align__(16) float dys[LB_HH * LB_DW];
   extern __shared__ __align__(16) float red_dyn[];    // ring [16 groups][LB_NST][4 pixels][16 lanes] float4, then [16][RS]
   constexpr int NDW = 9 * 4 * 16;
   constexpr int RS = NDW + 4 * 16 + 1;
-  constexpr int ITERS = LB_TH * LB_TW / 64;           // iterations of one group per tile
+  constexpr int ITERS = LB_TH * LB_TW / 64;           // iterations of one group per tile (16)
+  static_assert(LB_TW == 32 && LB_TH == 32 && ITERS == 16, "unit decomposition below assumes 32 x 32 tiles");
   const int tid = threadIdx.x;
   const int lane16 = tid & 15, grp = tid >> 4;
+  const int rpar = grp >> 3, cb4 = (grp & 7) * 4;     // this group's row parity and first column inside a tile
   const int c = lane16 * 4;
   const bool cok = c < C;
   float4 wr[9], dwacc[9], dusum = make_float4(0, 0, 0, 0);
@@ -742,84 +763,97 @@ conv_last_bwd_ring_kernel(const float* __restrict__ u, const float* __restrict__
     dwacc[k] = make_float4(0, 0, 0, 0);
   }
   float4* ring = reinterpret_cast<float4*>(red_dyn) + (size_t)grp * LB_NST * 64;
-  const int my_tiles = (int)blockIdx.x < ntiles ? (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int total_it = my_tiles * ITERS;
-  auto tile_origin = [&](int it, int& b, int& h0, int& w0) {
-    int t = blockIdx.x + (it / ITERS) * gridDim.x;
+  auto decode = [&](LbCursor& cu) {
+    int t = cu.t;
     const int tx = t % tiles_x; t /= tiles_x;
     const int ty = t % tiles_y;
-    b = t / tiles_y;
-    h0 = ty * LB_TH; w0 = tx * LB_TW;
+    cu.b = t / tiles_y;
+    cu.h0 = ty * LB_TH; cu.w0 = tx * LB_TW;
   };
-  auto issue = [&](int it) {
-    if (it < total_it) {
-      int b, h0, w0;
-      tile_origin(it, b, h0, w0);
-      const int p0 = grp + 64 * (it % ITERS);
+  LbCursor pf{(int)blockIdx.x, 0, 0, 0, 0}, cs = pf;
+  if (pf.t < ntiles) { decode(pf); cs = pf; }
+  int pf_slot = 0, cs_slot = 0;
+  auto issue = [&]() {
+    if (pf.t < ntiles) {
+      const int gh = pf.h0 + 2 * pf.j + rpar, gw0 = pf.w0 + cb4;
+      const bool rowok = cok && gh < H;
+      const float* src = u + (((size_t)pf.b * H + gh) * W + gw0) * C + c;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int p = p0 + 16 * i;
-        const int gh = h0 + p / LB_TW, gw = w0 + p % LB_TW;
-        const bool ok = cok && gh < H && gw < W;
-        lb_cp_async16(&ring[((it % LB_NST) * 4 + i) * 16 + lane16],
-                      ok ? u + (((size_t)b * H + gh) * W + gw) * C + c : u, ok);
+        const bool ok = rowok && gw0 + i < W;
+        lb_cp_async16(&ring[(pf_slot * 4 + i) * 16 + lane16], ok ? src + (size_t)i * C : u, ok);
+      }
+      if (++pf.j == ITERS) {
+        pf.j = 0;
+        pf.t += gridDim.x;
+        if (pf.t < ntiles) decode(pf);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // empty groups keep the group count uniform
+    pf_slot = (pf_slot + 1) & (LB_NST - 1);
   };
 #pragma unroll
-  for (int k = 0; k < LB_NST - 1; ++k) issue(k);
-  int b = 0, h0 = 0, w0 = 0;
+  for (int k = 0; k < LB_NST - 1; ++k) issue();
 #pragma unroll 1
-  for (int it = 0; it < total_it; ++it) {
-    if (it % ITERS == 0) {                              // next tile: its dy halo (block-uniform branch)
-      tile_origin(it, b, h0, w0);
+  while (cs.t < ntiles) {
+    if (cs.j == 0) {                                    // next tile: its dy halo (block-uniform branch)
       __syncthreads();
-      for (int i = tid; i < LB_HH * LB_HW; i += 256) {
-        const int hh = i / LB_HW, ww = i % LB_HW;
-        const int gh = h0 + hh - 1, gw = w0 + ww - 1;
-        dys[i] = (gh >= 0 && gh < H && gw >= 0 && gw < W) ? dy[((size_t)b * H + gh) * W + gw] : 0.f;
+      for (int i = tid; i < LB_HH * LB_DW; i += 256) {
+        const int hh = i / LB_DW, ww = i - hh * LB_DW;
+        const int gh = cs.h0 + hh - 1, gw = cs.w0 + ww - 1;
+        dys[i] = (ww < LB_HW && gh >= 0 && gh < H && gw >= 0 && gw < W) ? dy[((size_t)cs.b * H + gh) * W + gw] : 0.f;
       }
       __syncthreads();
     }
-    issue(it + LB_NST - 1);
+    issue();
     asm volatile("cp.async.wait_group %0;" ::"n"(LB_NST - 1) : "memory");
-    const int p0 = grp + 64 * (it % ITERS);
+    const int lh = 2 * cs.j + rpar;
+    const int gh = cs.h0 + lh, gw0 = cs.w0 + cb4;
+    if (gh < H && gw0 < W) {
+      // dy window: halo rows lh..lh+2, halo columns cb4..cb4+5; tap (r, s) of pixel i reads win[2 - r][i + 2 - s]
+      float win[3][6];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int p = p0 + 16 * i;
-      const int lh = p / LB_TW, lw = p % LB_TW;
-      const int gh = h0 + lh, gw = w0 + lw;
-      if (gh >= H || gw >= W) continue;
-      float n[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s2 = 0; s2 < 3; ++s2) n[r * 3 + s2] = dys[(lh + 1 - (r - 1)) * LB_HW + (lw + 1 - (s2 - 1))];
-      if (lane16 == 0) dbacc += n[4];
-      if (!cok) continue;
-      const float4 uv = ring[((it % LB_NST) * 4 + i) * 16 + lane16];
-      float4 d = make_float4(0, 0, 0, 0);
-#pragma unroll
-      for (int k = 0; k < 9; ++k) {
-        const float2 nk = make_float2(n[k], n[k]);
-        const float2 lo = ffma2(nk, make_float2(wr[k].x, wr[k].y), make_float2(d.x, d.y));
-        const float2 hi = ffma2(nk, make_float2(wr[k].z, wr[k].w), make_float2(d.z, d.w));
-        d = make_float4(lo.x, lo.y, hi.x, hi.y);
-        const float2 lo2 = ffma2(make_float2(uv.x, uv.y), nk, make_float2(dwacc[k].x, dwacc[k].y));
-        const float2 hi2 = ffma2(make_float2(uv.z, uv.w), nk, make_float2(dwacc[k].z, dwacc[k].w));
-        dwacc[k] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+      for (int a = 0; a < 3; ++a) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&dys[(lh + a) * LB_DW + cb4]);
+        const float2 q2 = *reinterpret_cast<const float2*>(&dys[(lh + a) * LB_DW + cb4 + 4]);
+        win[a][0] = q4.x; win[a][1] = q4.y; win[a][2] = q4.z; win[a][3] = q4.w; win[a][4] = q2.x; win[a][5] = q2.y;
       }
-      const size_t o = (((size_t)b * H + gh) * W + gw) * C + c;
-      if (du) *reinterpret_cast<float4*>(du + o) = d;
-      if (du_b) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(du_b + o) = pk;
+      const size_t o0 = (((size_t)cs.b * H + gh) * W + gw0) * C + c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (gw0 + i >= W) break;
+        if (lane16 == 0) dbacc += win[1][i + 1];
+        if (!cok) continue;
+        const float4 uv = ring[(cs_slot * 4 + i) * 16 + lane16];
+        float4 d = make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float nv = win[2 - k / 3][i + 2 - k % 3];
+          const float2 nk = make_float2(nv, nv);
+          const float2 lo = ffma2(nk, make_float2(wr[k].x, wr[k].y), make_float2(d.x, d.y));
+          const float2 hi = ffma2(nk, make_float2(wr[k].z, wr[k].w), make_float2(d.z, d.w));
+          d = make_float4(lo.x, lo.y, hi.x, hi.y);
+          const float2 lo2 = ffma2(make_float2(uv.x, uv.y), nk, make_float2(dwacc[k].x, dwacc[k].y));
+          const float2 hi2 = ffma2(make_float2(uv.z, uv.w), nk, make_float2(dwacc[k].z, dwacc[k].w));
+          dwacc[k] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+        }
+        const size_t o = o0 + (size_t)i * C;
+        if (du) *reinterpret_cast<float4*>(du + o) = d;
+        if (du_b) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(d.x, d.y), hi = __floats2bfloat162_rn(d.z, d.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(du_b + o) = pk;
+        }
+        dusum.x += d.x; dusum.y += d.y; dusum.z += d.z; dusum.w += d.w;
       }
-      dusum.x += d.x; dusum.y += d.y; dusum.z += d.z; dusum.w += d.w;
+    }
+    cs_slot = (cs_slot + 1) & (LB_NST - 1);
+    if (++cs.j == ITERS) {
+      cs.j = 0;
+      cs.t += gridDim.x;
+      if (cs.t < ntiles) decode(cs);
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
