@@ -583,6 +583,12 @@ class Trainer(object):
         """One validation pass plus everything the reference hangs on its result (lib/Trainer.py:271-300): scalar
         logging, best-model checkpoint + hparams, scheduler step.  Under data parallelism the metric is the mean
         over all ranks' tiles, so every replica takes the same decisions."""
+        if self.distributed:
+            # BatchNorm running statistics are per-rank during training (every rank sees its own tiles, as in plain
+            # DDP); before they are USED -- validation, checkpoints -- they become the mean over ranks on every replica
+            bufs = self.model._rt['bufs']
+            torch.distributed.all_reduce(bufs, op=torch.distributed.ReduceOp.SUM)
+            bufs.mul_(1.0 / self.world_size)
         meters = self.inference_one_epoch(epoch, 'val')
         if self.distributed:
             for meter in meters.values():

@@ -11,7 +11,8 @@ Every rank builds the model from a DIFFERENT seed and hands the SAME global batc
   * after K steps through inference_one_epoch (graph replays, all-reduce slices overlapping the backward pass) the
     parameter arenas are bit-identical on all ranks AND bit-identical to a single-process emulation on rank 0 that
     runs the N shards one after the other, sums their gradient arenas and applies Adam with grad_scale 1/N;
-  * the validation metric is the same number on every rank.
+  * the validation metric is the same number on every rank, and validation leaves the BatchNorm running statistics
+    (per rank during training, as in DDP) averaged and identical on all replicas.
 Prints one JSON line on rank 0.
 """
 import json
@@ -28,17 +29,23 @@ import torch.distributed as dist  # noqa: E402
 from oracle.unet_oracle import synthetic_batch  # noqa: E402
 
 
-def make_trainer(model, batches, lr=2e-4):
+def make_trainer(model, batches, out_dir, single_process=False):
+    """The real constructor (replica broadcast, shard policy, logging on rank 0 only).  single_process=True builds the
+    rank-0-only emulation trainer: torch.distributed is hidden from it so that it issues no collectives."""
     from resdepth_b200.lib.Trainer import Trainer
-    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=1e-5)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, weight_decay=1e-5)
     args = SimpleNamespace(trainloader=batches, valloader=batches[:2], model=model, optimizer=opt, scheduler=None,
                            criterion=torch.nn.L1Loss(reduction='mean'), n_epochs=1, evaluate_rate=1, save_model_rate=1,
-                           freq_average_train_loss=1000, save_dir='', log_file=None, checkpoint_dir='',
-                           tboard_log_dir=None, pretrained_path=None)
-    tr = Trainer.__new__(Trainer)
-    import bench
-    bench._init_quiet(tr, args, torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0))))
-    return tr
+                           freq_average_train_loss=1000, save_dir=out_dir, log_file=None,
+                           checkpoint_dir=os.path.join(out_dir, 'ckpt'), tboard_log_dir=None, pretrained_path=None)
+    if not single_process:
+        return Trainer(args)
+    real = torch.distributed.is_initialized
+    torch.distributed.is_initialized = lambda: False
+    try:
+        return Trainer(args)
+    finally:
+        torch.distributed.is_initialized = real
 
 
 def main():
@@ -54,29 +61,31 @@ def main():
 
     torch.manual_seed(1000 + rank)                      # replicas start DIFFERENT on purpose
     model = UNet(**kwargs)
-    tr = make_trainer(model, batches)
+    import tempfile
+    out_dir = tempfile.mkdtemp(prefix=f'rd_dist_r{rank}_')
+    tr = make_trainer(model, batches, out_dir)
     assert tr.distributed and tr.shard_batches == {'train': True, 'val': True}
     same0, _ = replicas_identical(model._rt['arena'], model._rt['bufs'], device=dev)
     start = model._rt['arena'].clone()
     meters = tr.inference_one_epoch(0, 'train')
-    same1, cs = replicas_identical(model._rt['arena'], model._rt['bufs'], device=dev)
+    same1, cs = replicas_identical(model._rt['arena'], device=dev)        # parameters; BN statistics are per rank
     n_graphs = len(tr._graphs)
     val = tr._validate(0, meters['MAE_metric'].avg)['MAE_metric'].avg
+    same2, _ = replicas_identical(model._rt['arena'], model._rt['bufs'], device=dev)   # statistics averaged by _validate
     v = torch.tensor([val], dtype=torch.float64, device=dev)
     vmin, vmax = v.clone(), v.clone()
     dist.all_reduce(vmin, op=dist.ReduceOp.MIN)
     dist.all_reduce(vmax, op=dist.ReduceOp.MAX)
 
     result = {'world': world, 'identical_after_broadcast': same0, 'identical_after_steps': same1, 'checksum': cs,
-              'graphs_captured': n_graphs, 'val_same_on_all_ranks': bool(vmin.item() == vmax.item()), 'val': val}
+              'graphs_captured': n_graphs, 'buffers_identical_after_validation': same2, 'val_same_on_all_ranks': bool(vmin.item() == vmax.item()), 'val': val}
     if rank == 0:
         # single-process emulation of the same K data-parallel steps, eager launches
         os.environ['RESDEPTH_GRAPHS'] = '0'
         torch.manual_seed(1000)
         emu = UNet(**kwargs)
-        etr = make_trainer(emu, batches)
-        etr.distributed, etr._reducer = False, None
-        etr.shard_batches = {'train': False, 'val': False}
+        etr = make_trainer(emu, batches, out_dir + '_emu', single_process=True)
+        assert not etr.distributed and etr._reducer is None and etr.shard_batches == {'train': False, 'val': False}
         assert torch.equal(emu._rt['arena'], start)
         bufs_r0 = None
         for b in batches:
@@ -94,7 +103,7 @@ def main():
             etr.optimizer.step()
         result['bitwise_equal_to_emulation'] = bool(torch.equal(emu._rt['arena'], model._rt['arena']))
         result['max_abs_diff_to_emulation'] = float((emu._rt['arena'] - model._rt['arena']).abs().max())
-        ok = same0 and same1 and result['val_same_on_all_ranks'] and result['max_abs_diff_to_emulation'] <= 1e-6
+        ok = same0 and same1 and same2 and result['val_same_on_all_ranks'] and result['max_abs_diff_to_emulation'] <= 1e-6
         result['ok'] = bool(ok)
         print(json.dumps(result), flush=True)
     dist.barrier()
