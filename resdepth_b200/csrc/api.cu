@@ -729,7 +729,13 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
   cur.slab = p; cur.slab_bytes = need;
   carve(h, cur.slab, batch, tile, with_backward);
   if (with_backward && !h->side) {                          // side stream + events of the overlapped weight gradients
-    RD_CUDA(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    // High priority: a weight-gradient CTA (one per SM, tensor-bound, ~200 KB of shared memory) should take the first
+    // SM slot an HBM-bound BatchNorm CTA of the main stream frees, so that the two kinds of work really run side by
+    // side; at default priority the block scheduler drains the older kernel's grid first and the GEMM starts in its tail.
+    static const bool flat_prio = getenv("RESDEPTH_SIDE_PRIO0") != nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    RD_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    RD_CUDA(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, flat_prio ? prio_lo : prio_hi));
     for (cudaEvent_t* ev : {&h->ev_main, &h->ev_join, &h->ev_wg[0], &h->ev_wg[1]})
       RD_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
   }
@@ -938,6 +944,13 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
     RD_TRY(launch_bn_bwd_apply(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? b.gyb : nullptr, B,
                                H, H, h->tf32() && (b.tc || b.tc_wgrad.valid), s));
   }
+  // Order of the two GEMMs that read dz.  Both need a whole SM (shared memory), so they never run side by side; what can
+  // share an SM with the weight gradient is the HBM-bound BatchNorm backward of the NEXT block.  With the side stream on,
+  // the data gradient (critical path) is therefore enqueued first and the weight gradient is released when it completes:
+  // it then overlaps the main stream's next elementwise kernels instead of delaying the data gradient.
+  static const bool wg_first = getenv("RESDEPTH_WG_FIRST") != nullptr;
+  const bool dgrad_first = ov && !wg_first && !first && (dgrad_out || dgrad_out_b);
+  auto do_wgrad = [&]() -> int {
   if (ov) {
     RD_CUDA(cudaEventRecord(h->ev_main, s));
     RD_CUDA(cudaStreamWaitEvent(ws, h->ev_main, 0));
@@ -976,6 +989,9 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
     RD_CUDA(cudaEventRecord(h->ev_wg[b.par], ws));
     h->wg_pending[b.par] = true;
   }
+  return 0;
+  };
+  auto do_dgrad = [&]() -> int {
   if (dgrad_out || dgrad_out_b) {
     Gather g = gather_conv3x3(H, H, b.Cout);
     Epilogue e{};
@@ -996,6 +1012,15 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
       ProfScope ps(h, RD_PROF_BIAS_GRAD, 0.0, 0.0, s);
       RD_TRY(launch_sum_partials(h->partials, npart, b.Cin, 2 * b.Cin, 2, dgrad_colsum, s));
     }
+  }
+  return 0;
+  };
+  if (dgrad_first) {
+    RD_TRY(do_dgrad());
+    RD_TRY(do_wgrad());
+  } else {
+    RD_TRY(do_wgrad());
+    RD_TRY(do_dgrad());
   }
   return 0;
 }
@@ -1092,30 +1117,42 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
     int S = 0;
     const bool ov = h->overlap && h->overlap_allowed;
     cudaStream_t ws = ov ? h->side : s;                 // the gradient at u_j (bf16) is complete on the main stream here
-    if (ov) {
-      RD_CUDA(cudaEventRecord(h->ev_main, s));
-      RD_CUDA(cudaStreamWaitEvent(ws, h->ev_main, 0));
-    }
-    {
-      ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, ws);
-      if (u.tc_wgrad.valid) {
-        RD_TRY(launch_gemm_reduce_tc(u.tc_wgrad, ws));
-        S = u.tc_wgrad.splits;
-      } else {
-        RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, ws));
+    static const bool wg_first = getenv("RESDEPTH_WG_FIRST") != nullptr;
+    auto up_wgrad = [&]() -> int {
+      if (ov) {
+        RD_CUDA(cudaEventRecord(h->ev_main, s));
+        RD_CUDA(cudaStreamWaitEvent(ws, h->ev_main, 0));
       }
-    }
-    {
-      ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 4.0 * cc * (S + 1.0), ws);
-      RD_TRY(launch_unpack_convt_grad(h->part, S, h->G + u.w, u.C, u.C, ws));
-    }
-    Epilogue e{};
-    e.mode = EPI_PLAIN;
-    e.out = h->gh;
-    {
+      {
+        ProfScope ps(h, RD_PROF_CONVT_WGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, ws);
+        if (u.tc_wgrad.valid) {
+          RD_TRY(launch_gemm_reduce_tc(u.tc_wgrad, ws));
+          S = u.tc_wgrad.splits;
+        } else {
+          RD_TRY(launch_gemm_reduce_simt(Gu, g4, X, B, u.C, h->part, h->part_floats, &S, ws));
+        }
+      }
+      {
+        ProfScope ps(h, RD_PROF_UNPACK, 0.0, 4.0 * 4.0 * cc * (S + 1.0), ws);
+        RD_TRY(launch_unpack_convt_grad(h->part, S, h->G + u.w, u.C, u.C, ws));
+      }
+      return 0;
+    };
+    auto up_dgrad = [&]() -> int {
+      Epilogue e{};
+      e.mode = EPI_PLAIN;
+      e.out = h->gh;
       ProfScope ps(h, RD_PROF_CONVT_DGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
       if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_dgrad, e, nullptr, s));
       else RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
+      return 0;
+    };
+    if (ov && !wg_first) {                              // data gradient first (see block_backward)
+      RD_TRY(up_dgrad());
+      RD_TRY(up_wgrad());
+    } else {
+      RD_TRY(up_wgrad());
+      RD_TRY(up_dgrad());
     }
     }
     if (j == 0) {
