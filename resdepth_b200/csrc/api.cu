@@ -103,6 +103,8 @@ struct Workspace {
   int xcol_b_k = 0;
   float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
   float* taps = nullptr;       // last-conv forward: 9 tap partial sums per pixel
+  float* gram = nullptr;       // first encoder block: Gram matrix of the bf16 im2col expansion [Kc][Kc]
+  TcReducePlan tc_gram;        // reduce GEMM (xcol, xcol) that produces it
 };
 }  // namespace rd
 
@@ -286,6 +288,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   h->consts = c.take(64);
   h->ob_mean = c.take(4); h->ob_invstd = c.take(4); h->ob_affine = c.take(4);
   h->taps = c.take((size_t)9 * B * T * T);               // tap partials of the last conv's forward (planar, 36 B / pixel)
+  h->gram = c.take(128 * 128);
   if (bwd) {
     h->part_floats = (size_t)8 << 20;
     h->part = c.take(h->part_floats);
@@ -371,9 +374,15 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
   if (bwd && h->enc[0].Cout % 32 == 0) {
     ConvBlock& b0 = h->enc[0];
     Gather gb = gather_plain(T, T, h->xcol_b_k);
+    h->tc_gram.valid = false;
     if (bf && h->xcol_b && tc_reduce_eligible(gb, b0.Cout, 1)) {
       RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, b0.gyb, b0.Cout, h->part, h->part_floats, 1));
       b0.bb = true;
+      // Gram matrix of the expansion (same GEMM with the expansion as both operands): lets the first block's weight
+      // gradient be formed from gY, without the apply pass of its BatchNorm backward (block_backward)
+      static const bool no_gram = getenv("RESDEPTH_NO_GRAM") != nullptr;
+      if (!no_gram && h->cfg.do_bn && b0.Cin * 9 < h->xcol_b_k && tc_reduce_eligible(gb, h->xcol_b_k, 1))
+        RD_TRY(tc_make_reduce_plan(&h->tc_gram, h->xcol_b, gb, B, h->xcol_b, h->xcol_b_k, h->part, h->part_floats, 1));
     } else if (h->xcol) {
       Gather g0 = gather_plain(T, T, h->xcol_k);
       if (tc_reduce_eligible(g0, b0.Cout))
@@ -915,6 +924,13 @@ struct GradRef {          // a gradient tensor stored as fp32 or as bf16 (the bf
   GradRef(const void* q, int is_bf16) : p(q), bf16(is_bf16) {}
 };
 
+// Gram matrix of the first layer's im2col expansion: reduce GEMM (xcol, xcol) -> split partials -> h->gram
+int first_layer_gram(rd_handle* h, cudaStream_t s) {
+  RD_TRY(launch_gemm_reduce_tc(h->tc_gram, s));
+  const int kc = h->xcol_b_k;
+  return launch_sum_partials(h->part, h->tc_gram.splits, kc * kc, kc * kc, 1, h->gram, s);
+}
+
 int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, int B, int H,
                    const float* src_in, bool first, float* dgrad_out, int round_dgrad, float* dgrad_colsum,
                    void* dgrad_out_b, cudaStream_t s) {
@@ -924,9 +940,19 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
   int np = 0;
   const double px = (double)B * H * H, n = px * b.Cout;
   const double gin = (g_full.p ? (g_full.bf16 ? 0.5 : 1.0) : 0.0) + (g_pool.p ? (g_pool.bf16 ? 0.125 : 0.25) : 0.0);
+  // First encoder block on the bf16 tcgen05 path: its dz feeds only the weight gradient, which is rebuilt from gY, the
+  // Gram matrix of the input expansion and the BatchNorm coefficients (launch_first_grad_correct) -- the reduce pass
+  // stores gY and the apply pass (a second sweep over z, the largest tensor of the network) is skipped.
+  const bool gy_path = first && b.bb && b.tc_wgrad.valid && h->tc_gram.valid && g_pool.p && do_bn;
+  const bool ov0 = h->overlap && h->overlap_allowed;
+  if (gy_path && ov0 && h->wg_pending[b.par]) {           // gY goes into this block's dz buffer: wait for its last reader
+    RD_CUDA(cudaStreamWaitEvent(s, h->ev_wg[b.par], 0));
+    h->wg_pending[b.par] = false;
+  }
   {
-    ProfScope ps(h, RD_PROF_BN_BWD_REDUCE, 0.0, 4.0 * n * (1.0 + gin), s);
-    RD_TRY(launch_bn_bwd_reduce(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->partials, &np, B, H, H, s));
+    ProfScope ps(h, RD_PROF_BN_BWD_REDUCE, 0.0, 4.0 * n * (1.0 + gin + (gy_path ? 0.5 : 0.0)), s);
+    RD_TRY(launch_bn_bwd_reduce(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->partials, &np, B, H, H, s,
+                                gy_path ? b.gyb : nullptr));
     RD_TRY(launch_bn_bwd_finalize(L, h->partials, np, (long long)B * H * H, do_bn, h->fwd_mode == RD_FWD_TRAIN,
                                   do_bn ? h->G + b.gamma : nullptr, h->G + (do_bn ? b.beta : b.bias),
                                   b.slope >= 0 ? h->G + b.slope : nullptr, h->scratch, h->coef, s));
@@ -939,7 +965,7 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
     RD_CUDA(cudaStreamWaitEvent(s, h->ev_wg[b.par], 0));
     h->wg_pending[b.par] = false;
   }
-  {
+  if (!gy_path) {
     ProfScope ps(h, RD_PROF_BN_BWD_APPLY, 0.0, 4.0 * n * (1.0 + (b.bb ? 0.5 : 1.0) + gin), s);
     RD_TRY(launch_bn_bwd_apply(g_full.p, g_pool.p, g_full.bf16, g_pool.bf16, b.z, L, act, h->coef, b.bb ? nullptr : h->gy, b.bb ? b.gyb : nullptr, B,
                                H, H, h->tf32() && (b.tc || b.tc_wgrad.valid), s));
@@ -960,10 +986,13 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
     if (b.tc_wgrad.valid) {
       const int kc = b.bb ? h->xcol_b_k : h->xcol_k;
       if (h->xcol_early) h->xcol_early = false;           // expansion already enqueued at the start of the backward pass
-      else if (b.bb) RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, kc, ws));
-      else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, ws));
+      else if (b.bb) {
+        RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, kc, ws));
+        if (gy_path) RD_TRY(first_layer_gram(h, ws));
+      } else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, ws));
       RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, ws));
       RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, kc, ws));
+      if (gy_path) RD_TRY(launch_first_grad_correct(h->G + b.w, h->P + b.w, h->gram, h->coef, b.Cout, b.Cin * 9, kc, ws));
     } else {
       RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
     }
@@ -1064,6 +1093,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
     const double px = (double)B * T * T;
     ProfScope ps(h, RD_PROF_FIRST_WGRAD, 0.0, px * (4.0 * b0.Cin + 2.0 * b0.Cin * 9), h->side);
     RD_TRY(launch_im2col_first_bf16(x, h->xcol_b, B, b0.Cin, T, T, h->xcol_b_k, h->side));
+    if (h->tc_gram.valid) RD_TRY(first_layer_gram(h, h->side));
     h->xcol_early = true;
   }
   // last_layer (lib/UNet.py:184,227): du -> gradient at u_{D-1}, which is also the skip gradient of level 0
@@ -1317,6 +1347,18 @@ int rd_profile_enable(rd_handle* h, int on) {
 int rd_profile_collect(rd_handle* h) {
   if (!h) return fail("rd_profile_collect: null handle");
   RD_CUDA(cudaSetDevice(h->device));
+  // RESDEPTH_TIMELINE=1: print every bracket as (category, start, end) in ms relative to the first one -- brackets of the
+  // main and the side stream share the clock, so this is the step's two-stream timeline (profiles/timeline.py)
+  static const bool timeline = getenv("RESDEPTH_TIMELINE") != nullptr;
+  if (timeline && !h->prof.empty()) {
+    for (auto& r : h->prof) RD_CUDA(cudaEventSynchronize(r.e1));
+    for (auto& r : h->prof) {
+      float t0 = 0.f, t1 = 0.f;
+      RD_CUDA(cudaEventElapsedTime(&t0, h->prof[0].e0, r.e0));
+      RD_CUDA(cudaEventElapsedTime(&t1, h->prof[0].e0, r.e1));
+      fprintf(stderr, "TL %s %.4f %.4f\n", kProfNames[r.cat], t0, t1);
+    }
+  }
   for (auto& r : h->prof) {
     RD_CUDA(cudaEventSynchronize(r.e1));
     float ms = 0.f;

@@ -85,9 +85,15 @@ int launch_bn_act_pool(const float* z, const float* scale, const float* shift, A
 // backward pass 1:  gA = unpool(g_pool, a) + g_full ; gY = gA*act'(y) ; per-block partial sums
 //   partials [nblk][C][3] = (sum gY, sum gY*(z-mean), sum gA*min(y,0))
 // g_full / g_pool: fp32 tensors, or bf16 tensors when the matching *_bf16 flag is set
+//   gy_b (optional, pooled blocks): also store gY as bf16 (first encoder block: its apply pass is replaced by
+//   launch_first_grad_correct)
 int launch_bn_bwd_reduce(const void* g_full, const void* g_pool, int gf_bf16, int gp_bf16, const float* z,
                          const BnLayer& L, Act act, float* partials, int* n_partials, int B, int H, int W,
-                         cudaStream_t s);
+                         cudaStream_t s, void* gy_b = nullptr);
+// dW of the first encoder conv from X^T gY (already in dw), the Gram matrix of the im2col expansion and the BatchNorm
+// backward coefficients (see first_grad_correct_kernel)
+int launch_first_grad_correct(float* dw, const float* w, const float* gram, const void* coef, int Co, int K, int Kc,
+                              cudaStream_t s);
 // finalize: dgamma, dbeta (or conv dbias) -> grads, PReLU slope gradient, coefficients for pass 2 (coef: 4*C floats)
 int launch_bn_bwd_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int do_bn,
                            int batch_stats, float* dgamma, float* dbeta, float* dslope, float* dslope_scratch, void* coef,

@@ -754,6 +754,12 @@ int tc_make_rows_plan(TcRowsPlan* plan, const void* src, const Gather& g, int B,
   P.cchunks = g.C / P.kchunk;
   plan->BN = tc_pick_bn(N);
   {
+    // small layers (bottleneck, deepest levels at small batch): with 256-column tiles fewer than half of the SMs get a
+    // tile (ncu round 1: 64 CTAs, 33 % tensor pipe on the bottleneck dgrad); 128-column tiles double the tile count
+    const long long m_tiles = ((long long)B * g.Ho * g.Wo + 127) / 128;
+    if (plan->BN == 256 && N % 128 == 0 && m_tiles * (N / 256) <= 74) plan->BN = 128;
+  }
+  {
     // HBM-bound up-conv forward (1 tap, N = 4C, K = C <= 128): 128-column tiles leave room for deeper skip rings
     static const bool ring128 = getenv("RESDEPTH_RING_BN128") != nullptr;
     if (ring128 && !bf16 && g.ntaps == 1 && N == 4 * g.C && g.C <= 128 && N % 128 == 0) plan->BN = 128;

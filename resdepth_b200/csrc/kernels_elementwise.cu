@@ -204,7 +204,10 @@ struct BwdCoef {            // per channel, built by bn_bwd_finalize
 };
 
 // RELU: the activation is a plain ReLU (slope 0, no slope gradient) -- the common case, with a shorter inner loop
-template <bool POOL, bool APPLY, bool RELU>
+// STORE_GY (reduce pass only): also store gY (bf16).  Used for the FIRST encoder block, whose dz feeds nothing but the
+// weight gradient: there dW = X^T dz is rebuilt from X^T gY and small correction terms (first_grad_correct_kernel), and
+// the second full pass over z (the apply pass) is not run at all.
+template <bool POOL, bool APPLY, bool RELU, bool STORE_GY = false>
 __global__ void __launch_bounds__(EW_THREADS, APPLY ? 4 : 3)
 bn_bwd_kernel(const void* __restrict__ g_full, const void* __restrict__ g_pool, int gf_bf16, int gp_bf16,
               const float* __restrict__ z,
@@ -277,13 +280,14 @@ bn_bwd_kernel(const void* __restrict__ g_full, const void* __restrict__ g_pool, 
             if (APPLY) {
               out[k][c] = cs[c] * (gY - c1[c] - zc * c2[c]);
             } else {
+              if (STORE_GY) out[k][c] = gY;
               s1[c] += gY;
               s2[c] = fmaf(gY, zc, s2[c]);
               if (!RELU) s3[c] += y > 0.f ? 0.f : gA * y;
             }
           }
         }
-        if (APPLY) {
+        if (APPLY || STORE_GY) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const size_t o = base + ((size_t)(k >> 1) * W + (k & 1)) * C;
@@ -305,12 +309,13 @@ bn_bwd_kernel(const void* __restrict__ g_full, const void* __restrict__ g_pool, 
           if (APPLY) {
             out[c] = cs[c] * (gY - c1[c] - zc * c2[c]);
           } else {
+            if (STORE_GY) out[c] = gY;
             s1[c] += gY;
             s2[c] = fmaf(gY, zc, s2[c]);
             if (!RELU) s3[c] += y > 0.f ? 0.f : gA[c] * y;
           }
         }
-        if (APPLY) {
+        if (APPLY || STORE_GY) {
           float4 r = make_float4(out[0], out[1], out[2], out[3]);
           if (dz) st4(dz + o, round_out ? tf32_rn4(r) : r);
           if (dz_b) st4_bf16(dz_b, o, r);
@@ -344,7 +349,7 @@ static int bwd_grid(long long nwin, int PL, int per_sm = 4) {
 
 int launch_bn_bwd_reduce(const void* g_full, const void* g_pool, int gf_bf16, int gp_bf16, const float* z,
                          const BnLayer& L, Act act, float* partials, int* n_partials, int B, int H, int W,
-                         cudaStream_t s) {
+                         cudaStream_t s, void* gy_b) {
   const int C = L.C, Q = C / 4;
   if (C % 4 || Q > EW_THREADS) return fail("bn_bwd: unsupported C=%d", C);
   if ((long long)B * H * W >= (1LL << 32)) return fail("bn_bwd: more than 2^32 pixels");
@@ -354,18 +359,20 @@ int launch_bn_bwd_reduce(const void* g_full, const void* g_pool, int gf_bf16, in
   const bool relu = act.kind == RD_ACT_RELU;
   if (g_pool) {
     grid = bwd_grid((long long)B * (H / 2) * (W / 2), PL, 3);     // 3 resident CTAs per SM: one wave
-#define RD_BWD_R(RL)                                                                                              \
+#define RD_BWD_R(RL, ST)                                                                                          \
   {                                                                                                               \
-    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<true, false, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+    RD_CUDA(cudaFuncSetAttribute(bn_bwd_kernel<true, false, RL, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                  64 * 1024));                                                                     \
-    bn_bwd_kernel<true, false, RL><<<grid, EW_THREADS, smem, s>>>(g_full, g_pool, gf_bf16, gp_bf16, z, L.scale,   \
+    bn_bwd_kernel<true, false, RL, ST><<<grid, EW_THREADS, smem, s>>>(g_full, g_pool, gf_bf16, gp_bf16, z, L.scale, \
                                                                   L.shift, act.slope, L.mean, nullptr, nullptr,   \
-                                                                  partials, B, H, W, C, 0, nullptr);              \
+                                                                  partials, B, H, W, C, 0, gy_b);                 \
   }
-    if (relu) RD_BWD_R(true) else RD_BWD_R(false)
+    if (gy_b) { if (relu) RD_BWD_R(true, true) else RD_BWD_R(false, true) }
+    else { if (relu) RD_BWD_R(true, false) else RD_BWD_R(false, false) }
 #undef RD_BWD_R
   } else {
     if (!g_full) return fail("bn_bwd: no incoming gradient");
+    if (gy_b) return fail("bn_bwd: the gY-storing reduce pass exists for pooled blocks only");
     grid = bwd_grid((long long)B * H * W, PL, 3);
 #define RD_BWD_R(RL)                                                                                              \
   {                                                                                                               \
@@ -1034,7 +1041,9 @@ im2col_first_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict_
           const int r = rs / 3, q = rs - r * 3;
           const int hh = h + r - 1, ww = w + q - 1;
           const bool ok = k < K && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
-          v[e] = ok ? __ldg(xb + (ci * H + hh) * W + ww) : 0.f;
+          // column K is the constant 1: the Gram GEMM xcol^T xcol then also yields the column sums of xcol (row K) and
+          // the pixel count; the weight-gradient GEMM ignores that row
+          v[e] = ok ? __ldg(xb + (ci * H + hh) * W + ww) : (k == K ? 1.f : 0.f);
         }
         __nv_bfloat162 bb = __floats2bfloat162_rn(v[0], v[1]);
         pk[jj] = *reinterpret_cast<uint32_t*>(&bb);
@@ -1081,6 +1090,32 @@ unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restric
 }
 int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s) {
   unpack_first_grad_kernel<<<cdiv(Co * K, 32), 256, 0, s>>>(part, S, dw, Co, K, Kc);
+  RD_LAUNCHED();
+  return 0;
+}
+
+// First encoder block, weight gradient without the apply pass.  With X = im2col(x) [pixels][K], A = X^T gY (what the
+// reduce GEMM + unpack_first_grad have just written into dw as dw[co][k]) and dz = cs (gY - c1 - (z - mean) c2):
+//   dW[co][k] = sum_p X[p][k] dz[p][co] = cs[co] ( A[k][co] - c1[co] cx[k] - c2[co] ( (G W[co])[k] - cx[k] mean[co] ) )
+// because z = X W^T (bias-free conv under BatchNorm): sum_p X[p][k] z[p][co] = sum_k' G[k][k'] W[co][k'] with the Gram
+// matrix G = X^T X.  gram [Kc][Kc] comes from the same reduce GEMM run on (xcol, xcol); its column K holds cx (the
+// im2col kernel writes a constant-one column there).  One thread per (co, k); K <= 27.
+__global__ void __launch_bounds__(256)
+first_grad_correct_kernel(float* __restrict__ dw, const float* __restrict__ w, const float* __restrict__ gram,
+                          const BwdCoef* __restrict__ coef, int Co, int K, int Kc) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= Co * K) return;
+  const int co = i / K, k = i - co * K;
+  const BwdCoef cf = coef[co];
+  const float cx = gram[(size_t)k * Kc + K];
+  double gw = 0.0;
+  for (int k2 = 0; k2 < K; ++k2) gw += (double)gram[(size_t)k * Kc + k2] * (double)w[(size_t)co * K + k2];
+  const double corr = (double)cf.c1 * cx + (double)cf.c2 * (gw - (double)cx * (double)cf.mean);
+  dw[i] = (float)((double)cf.cs * ((double)dw[i] - corr));
+}
+int launch_first_grad_correct(float* dw, const float* w, const float* gram, const void* coef, int Co, int K, int Kc,
+                              cudaStream_t s) {
+  first_grad_correct_kernel<<<cdiv(Co * K, 256), 256, 0, s>>>(dw, w, gram, reinterpret_cast<const BwdCoef*>(coef), Co, K, Kc);
   RD_LAUNCHED();
   return 0;
 }
