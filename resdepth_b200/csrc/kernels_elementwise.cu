@@ -66,8 +66,19 @@ bn_finalize_kernel(const float* __restrict__ partials, int nparts, int C, double
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0;
   if (do_bn && training && c < C) {
-    for (int p = pl; p < nparts; p += 32) {
-      const float2 v = *reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2);
+    // four independent loads in flight per thread: with one, the ~20 iterations of a 592-row partial table were 20
+    // serialised L2 round trips (10 us for a kernel that moves 300 KB; timeline of round 2)
+    int p = pl;
+    for (; p + 96 < nparts; p += 128) {
+      const float2 v0 = __ldg(reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2));
+      const float2 v1 = __ldg(reinterpret_cast<const float2*>(partials + ((size_t)(p + 32) * C + c) * 2));
+      const float2 v2 = __ldg(reinterpret_cast<const float2*>(partials + ((size_t)(p + 64) * C + c) * 2));
+      const float2 v3 = __ldg(reinterpret_cast<const float2*>(partials + ((size_t)(p + 96) * C + c) * 2));
+      s1 += ((double)v0.x + (double)v1.x) + ((double)v2.x + (double)v3.x);
+      s2 += ((double)v0.y + (double)v1.y) + ((double)v2.y + (double)v3.y);
+    }
+    for (; p < nparts; p += 32) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(partials + ((size_t)p * C + c) * 2));
       s1 += (double)v.x;
       s2 += (double)v.y;
     }
@@ -401,9 +412,21 @@ bn_bwd_finalize_kernel(const float* __restrict__ partials, int nparts, int C, do
   const int c = blockIdx.x * 32 + cl;
   double s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (c < C) {
-    for (int p = pl; p < nparts; p += 32) {
+    int p = pl;
+    for (; p + 96 < nparts; p += 128) {                 // four partial rows in flight per thread (see bn_finalize_kernel)
+      const float* v0 = partials + ((size_t)p * C + c) * 3;
+      const float* v1 = partials + ((size_t)(p + 32) * C + c) * 3;
+      const float* v2 = partials + ((size_t)(p + 64) * C + c) * 3;
+      const float* v3 = partials + ((size_t)(p + 96) * C + c) * 3;
+      const float a0 = __ldg(v0), a1 = __ldg(v0 + 1), a2 = __ldg(v0 + 2), b0 = __ldg(v1), b1 = __ldg(v1 + 1), b2 = __ldg(v1 + 2);
+      const float c0 = __ldg(v2), c1 = __ldg(v2 + 1), c2 = __ldg(v2 + 2), d0 = __ldg(v3), d1 = __ldg(v3 + 1), d2 = __ldg(v3 + 2);
+      s1 += ((double)a0 + (double)b0) + ((double)c0 + (double)d0);
+      s2 += ((double)a1 + (double)b1) + ((double)c1 + (double)d1);
+      s3 += ((double)a2 + (double)b2) + ((double)c2 + (double)d2);
+    }
+    for (; p < nparts; p += 32) {
       const float* v = partials + ((size_t)p * C + c) * 3;
-      s1 += (double)v[0]; s2 += (double)v[1]; s3 += (double)v[2];
+      s1 += (double)__ldg(v); s2 += (double)__ldg(v + 1); s3 += (double)__ldg(v + 2);
     }
   }
   red[pl][cl][0] = s1; red[pl][cl][1] = s2; red[pl][cl][2] = s3;
@@ -1149,8 +1172,16 @@ sum_partials_kernel(const float* __restrict__ part, int nparts, int n, int row_s
   const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + cl;
   double a = 0.0;
-  if (i < n)
-    for (int p = pl; p < nparts; p += 32) a += (double)part[(size_t)p * row_stride + (size_t)i * col_stride];
+  if (i < n) {
+    const float* col = part + (size_t)i * col_stride;
+    int p = pl;
+    for (; p + 96 < nparts; p += 128) {                  // four rows in flight per thread
+      const float v0 = __ldg(col + (size_t)p * row_stride), v1 = __ldg(col + (size_t)(p + 32) * row_stride);
+      const float v2 = __ldg(col + (size_t)(p + 64) * row_stride), v3 = __ldg(col + (size_t)(p + 96) * row_stride);
+      a += ((double)v0 + (double)v1) + ((double)v2 + (double)v3);
+    }
+    for (; p < nparts; p += 32) a += (double)__ldg(col + (size_t)p * row_stride);
+  }
   red[pl][cl] = a;
   __syncthreads();
   if (pl == 0 && i < n) {

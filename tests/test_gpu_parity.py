@@ -269,7 +269,8 @@ def test_eval_tiles_are_independent_at_full_size(math_mode):
         xd = x.to(DEV)
         y_all = model(xd)
         y_parts = torch.cat([model(xd[i:i + 8]) for i in range(0, 32, 8)])
-        assert _rel(y_parts, y_all) <= 1e-6
+        # the tile plan of the deep layers depends on the batch (128- vs 256-column tiles): summation order only
+        assert _rel(y_parts, y_all) <= (1e-6 if math_mode == 'fp32' else 1e-5)
         y_ref = O.unet_forward(sd, x[:2], spec_of(kwargs), training=False)
     rel, same, mae = O.residual_metrics(y_all[:2].cpu(), y_ref, x[:2, :1])
     assert rel <= (1e-5 if math_mode == 'fp32' else 1e-3) and same and mae <= 1e-3, (rel, same, mae)
