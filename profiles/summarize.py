@@ -76,9 +76,9 @@ def step(md_path):
     print('Command (on the B200 box): `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,'
           'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,'
           'sm__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,launch__registers_per_thread,'
-          'sm__warps_active.avg.pct_of_peak_sustained_active,launch__shared_mem_per_block_dynamic --clock-control none -s 138 '
-          '-c 138 -o /tmp/step python profiles/one_step.py 2`, then `summarize.py ncu /tmp/step.ncu-rep` there and '
-          '`summarize.py step` here.  138 consecutive launches = one full step (the window starts at the second step). '
+          f'sm__warps_active.avg.pct_of_peak_sustained_active,launch__shared_mem_per_block_dynamic --clock-control none -s {len(rows)} '
+          f'-c {len(rows)} -o /tmp/step python profiles/one_step.py 2` (profiles/capture_step.sh), then `summarize.py ncu /tmp/step.ncu-rep` there and '
+          f'`summarize.py step` here.  {len(rows)} consecutive launches = one full step (the window starts at the second step). '
           'ncu times are cold-cache and serialised: compare SHARES with `bench.py`, not absolutes.\n')
     print('| # | ' + ' | '.join(hdr) + ' |')
     print('|---:|---|---|' + '---:|' * 10)
