@@ -522,12 +522,7 @@ int conv_block_forward(rd_handle* h, ConvBlock& b, const float* src, int B, int 
 // Inference (RD_FWD_EVAL) on a tcgen05 block: BatchNorm(running stats) + activation (+ 2x2 max-pool) folded into the
 // conv epilogue -- the raw conv output z is never written
 int conv_block_forward_fused_eval(rd_handle* h, ConvBlock& b, int B, int H, int round_a, int round_p, cudaStream_t s) {
-  BnLayer L = bn_view(h, b);
-  {
-    ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
-    RD_TRY(launch_bn_finalize(L, h->partials, 0, (long long)B * H * H, 0, h->cfg.do_bn, s));
-  }
-  Epilogue e{};
+  Epilogue e{};                                          // scale / shift: bn_eval_all at the start of rd_forward
   e.mode = EPI_BNACT;
   e.out = b.a;
   e.round_tf32 = round_a;
@@ -539,6 +534,16 @@ int conv_block_forward_fused_eval(rd_handle* h, ConvBlock& b, int B, int H, int 
   const double px = (double)B * H * H;
   ProfScope ps(h, RD_PROF_CONV_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout * (b.pool ? 1.25 : 1.0)), s);
   return launch_gemm_rows_tc(b.tc_fwd, e, nullptr, s);
+}
+
+// eval-mode BatchNorm (running statistics) of every block: one launch per forward pass
+int bn_eval_all(rd_handle* h, cudaStream_t s) {
+  BnEvalJobs J;
+  for (auto& b : h->enc) RD_TRY(bn_eval_jobs_add(J, bn_view(h, b), h->cfg.do_bn));
+  RD_TRY(bn_eval_jobs_add(J, bn_view(h, h->bott), h->cfg.do_bn));
+  for (auto& b : h->dec) RD_TRY(bn_eval_jobs_add(J, bn_view(h, b), h->cfg.do_bn));
+  ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
+  return launch_bn_eval_batched(J, s);
 }
 
 // encoder level i keeps only z and the pooled tensor: its up-conv (tcgen05, transposed) applies BN + activation to z
@@ -553,8 +558,11 @@ int bn_act_forward(rd_handle* h, ConvBlock& b, int np, int B, int H, bool train,
                    bool shadows, cudaStream_t s, bool write_a = true) {
   BnLayer L = bn_view(h, b);
   {
-    ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
-    RD_TRY(launch_bn_finalize(L, h->partials, np, (long long)B * H * H, train, h->cfg.do_bn, s));
+    // running-statistics modes were finalized for all layers at once (bn_eval_all); batch statistics need this layer's sums
+    if (train) {
+      ProfScope ps(h, RD_PROF_BN_FINALIZE, 0.0, 0.0, s);
+      RD_TRY(launch_bn_finalize(L, h->partials, np, (long long)B * H * H, train, h->cfg.do_bn, s));
+    }
   }
   const double n = (double)B * H * H * b.Cout;
   ProfScope ps(h, RD_PROF_BN_ACT_POOL, 0.0, 4.0 * n * (b.pool ? (write_a ? 2.25 : 1.25) : 2.0), s);
@@ -788,6 +796,7 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
   const bool fuse_eval = mode == RD_FWD_EVAL;         // nothing is kept for a backward pass: fold BN into the convs
   h->fwd_mode = -1;
   RD_TRY(pack_weights(h, save, s));
+  if (!train) RD_TRY(bn_eval_all(h, s));
 
   int np = 0;
   for (int i = 0; i < D; ++i) {

@@ -78,6 +78,19 @@ struct BnLayer {
 // partials: [nparts][C][2] (sum, sumsq) -> mean/invstd/scale/shift (+ running stats when training)
 int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long long count, int training,
                        int do_bn, cudaStream_t s);
+// eval-mode finalize (running statistics -> scale / shift) of all layers in one launch
+static constexpr int BN_EVAL_MAX_JOBS = 24;
+struct BnEvalJob {
+  const float *gamma, *beta, *conv_bias, *running_mean, *running_var;
+  float *mean, *invstd, *scale, *shift;
+  int C, block0;
+};
+struct BnEvalJobs {
+  int n = 0, total_blocks = 0;
+  BnEvalJob job[BN_EVAL_MAX_JOBS];
+};
+int bn_eval_jobs_add(BnEvalJobs& J, const BnLayer& L, int do_bn);
+int launch_bn_eval_batched(const BnEvalJobs& J, cudaStream_t s);
 // a = act(z*scale+shift)  (+ 2x2 max-pool into p when p != null).  round_*: store TF32-rounded values.
 //   a_b / p_b (optional): bf16 copies of a / p (operands of the bf16 backward GEMMs)
 int launch_bn_act_pool(const float* z, const float* scale, const float* shift, Act act, float* a, float* p,

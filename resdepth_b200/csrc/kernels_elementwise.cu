@@ -124,6 +124,45 @@ int launch_bn_finalize(const BnLayer& L, const float* partials, int nparts, long
   return 0;
 }
 
+// Eval-mode BatchNorm of EVERY layer in one launch: scale / shift from the running statistics (no batch data involved),
+// so an inference forward pass does not pay one tiny finalize launch per layer (10 x ~7 us of 2.2 ms at batch 32).
+__global__ void __launch_bounds__(256) bn_eval_batched_kernel(const __grid_constant__ BnEvalJobs J) {
+  int j = 0;
+  while (j + 1 < J.n && (int)blockIdx.x >= J.job[j + 1].block0) ++j;
+  const BnEvalJob& L = J.job[j];
+  const int c = ((int)blockIdx.x - L.block0) * 256 + threadIdx.x;
+  if (c >= L.C) return;
+  if (!L.gamma) {                                       // no BatchNorm: identity scale, the conv bias as shift
+    L.scale[c] = 1.f;
+    L.shift[c] = L.conv_bias ? L.conv_bias[c] : 0.f;
+    return;
+  }
+  const float mean = L.running_mean[c];
+  const float invstd = 1.f / sqrtf(L.running_var[c] + BN_EPS);
+  L.mean[c] = mean;
+  L.invstd[c] = invstd;
+  const float sc = L.gamma[c] * invstd;
+  L.scale[c] = sc;
+  L.shift[c] = L.beta[c] - mean * sc;
+}
+int bn_eval_jobs_add(BnEvalJobs& J, const BnLayer& L, int do_bn) {
+  if (J.n >= BN_EVAL_MAX_JOBS) return fail("bn_eval: more than %d layers", BN_EVAL_MAX_JOBS);
+  BnEvalJob& j = J.job[J.n++];
+  j.C = L.C;
+  j.gamma = do_bn ? L.gamma : nullptr; j.beta = L.beta; j.conv_bias = L.conv_bias;
+  j.running_mean = L.running_mean; j.running_var = L.running_var;
+  j.mean = L.mean; j.invstd = L.invstd; j.scale = L.scale; j.shift = L.shift;
+  j.block0 = J.total_blocks;
+  J.total_blocks += (L.C + 255) / 256;
+  return 0;
+}
+int launch_bn_eval_batched(const BnEvalJobs& J, cudaStream_t s) {
+  if (J.n == 0) return 0;
+  bn_eval_batched_kernel<<<J.total_blocks, 256, 0, s>>>(J);
+  RD_LAUNCHED();
+  return 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // a = act(z*scale + shift), optional 2x2 max-pool (first-max-wins is irrelevant in the forward)
 // ----------------------------------------------------------------------------------------------
