@@ -7,6 +7,7 @@
 //   * linear-blend accumulation                                 (lib/evaluation.py:484-567)
 //   * weight packing / gradient un-packing for the GEMM-shaped layers
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/resdepth_b200.h"
@@ -980,7 +981,35 @@ __global__ void unpack_conv3x3_grad_kernel(const float* __restrict__ part, int S
 // (A shared-memory tiled un-pack, the mirror image of pack_conv3x3_tiled_kernel, was measured slower -- 0.31 vs 0.26 ms
 // per step: the split partials are read S times, so the element-wise kernels' full-chip parallelism on the reads matters
 // more than their scattered 4-byte stores.)
+// Tiled form for the large layers (few splits): a block sums the splits of a (9 taps x 8 ci) x 32 co tile with coalesced
+// 128-byte row reads into shared memory and writes 288 contiguous bytes per output channel -- the element-wise kernel
+// above scatters its 4-byte stores over 32 sectors per warp (0.7 TB/s on the 512 x 512 layers, ncu round 2).
+__global__ void __launch_bounds__(256)
+unpack_conv3x3_grad_tiled_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co, int Ci) {
+  __shared__ float tl[32][PK_ROW + 1];                    // [co][ci_local * 9 + t]
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * PK_CI;
+  const size_t total = (size_t)Co * Ci * 9;
+  for (int idx = threadIdx.x; idx < 32 * PK_ROW; idx += 256) {
+    const int co = idx & 31, r = idx >> 5;                // r = t * PK_CI + ci_local: consecutive rows of the packed layout
+    const int t = r / PK_CI, ci = r - t * PK_CI;
+    const float* src = part + ((size_t)t * Ci + ci0 + ci) * Co + co0 + co;
+    float a = 0.f;
+    for (int sp = 0; sp < S; ++sp) a += __ldg(src + (size_t)sp * total);
+    tl[co][ci * 9 + t] = a;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * PK_ROW; idx += 256) {
+    const int co = idx / PK_ROW, c = idx - co * PK_ROW;
+    dw[((size_t)(co0 + co) * Ci + ci0) * 9 + c] = tl[co][c];
+  }
+}
 int launch_unpack_conv_grad(const float* part, int S, float* dw, int Co, int Ci, int ntaps, cudaStream_t s) {
+  static const bool no_tiled = getenv("RESDEPTH_UNPACK_SIMPLE") != nullptr;
+  if (!no_tiled && ntaps == 9 && Co % 32 == 0 && Ci % PK_CI == 0 && S <= 8 && (long long)Co * Ci >= 128 * 128) {
+    unpack_conv3x3_grad_tiled_kernel<<<dim3(Ci / PK_CI, Co / 32), 256, 0, s>>>(part, S, dw, Co, Ci);
+    RD_LAUNCHED();
+    return 0;
+  }
   unpack_conv3x3_grad_kernel<<<ew_grid((long long)Co * Ci * ntaps), 256, 0, s>>>(part, S, dw, Co, Ci, ntaps);
   RD_LAUNCHED();
   return 0;

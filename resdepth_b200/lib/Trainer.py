@@ -559,7 +559,11 @@ class Trainer(object):
                 for param in self.model.parameters():
                     param.grad = None
 
-            host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+            # pinned landing slots for the 4-byte loss read-back: two alternate (the previous one is consumed only after
+            # this step has been enqueued); allocated once -- a pinned allocation per step costs a cudaHostAlloc each
+            if getattr(self, '_loss_slots', None) is None:
+                self._loss_slots = torch.empty(2, dtype=torch.float32, pin_memory=True)
+            host = self._loss_slots[c_iter & 1:(c_iter & 1) + 1]
             host.copy_(loss, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
