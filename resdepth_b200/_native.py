@@ -159,6 +159,7 @@ class Handle:
         self._lib = lib()
         check(self._lib.rd_create(C.byref(cfg), int(device_index), C.byref(self._h)), 'rd_create')
         self.device_index = int(device_index)
+        self.profiling = False
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:
@@ -235,6 +236,7 @@ class Handle:
 
     def profile_enable(self, on: bool):
         check(self._lib.rd_profile_enable(self._h, 1 if on else 0), 'rd_profile_enable')
+        self.profiling = bool(on)
 
     def profile_read(self):
         """Collects pending events; returns {category: dict(ms, flops, bytes, launches, calls)}."""

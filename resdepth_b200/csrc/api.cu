@@ -806,6 +806,13 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
       const double px = (double)B * H * H;
       ProfScope ps(h, RD_PROF_FIRST_FWD, 2.0 * 9.0 * b.Cin * b.Cout * px, 4.0 * px * (b.Cin + b.Cout), s);
       static const bool no_first_tc = getenv("RESDEPTH_NO_FIRST_TC") != nullptr;
+      static const bool no_first_fuse = getenv("RESDEPTH_NO_FIRST_FUSE") != nullptr;
+      if (fuse_eval && h->tf32() && !no_first_tc && !no_first_fuse && conv_first_tc_fuse_ok(b.Cin, b.Cout, H, H)) {
+        // inference: BatchNorm(running statistics) + activation + max-pool folded into the conv (z0 is never written)
+        RD_TRY(launch_conv_first_tc(x, h->P + b.w, nullptr, nullptr, &np, B, b.Cin, H, H, b.Cout, s, b.scale, b.shift,
+                                    act_view(h, b).slope, b.a, b.p, tf));
+        continue;
+      }
       if (h->tf32() && !no_first_tc && conv_first_tc_shape_ok(b.Cin, b.Cout, H, H))
         RD_TRY(launch_conv_first_tc(x, h->P + b.w, b.z, stats ? h->partials : nullptr, &np, B, b.Cin, H, H, b.Cout, s));
       else

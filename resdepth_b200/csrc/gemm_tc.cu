@@ -1492,10 +1492,22 @@ __device__ __forceinline__ uint32_t sw128_off(int row, int chunk) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-template <int N>
+// FUSE (inference, RD_FWD_EVAL): BatchNorm(running statistics) + activation + 2x2 max-pool in the epilogue -- the raw
+// conv output z is never written (at batch 32 it is 0.54 GB written here and read again by bn_act_pool).  The tile is
+// then 64 columns x 2 image rows with row r = pixel (r >> 1, r & 1), so that the four pixels of a pooling window are
+// the lanes l, l^1, l^2, l^3 of one warp; out_a = activated tensor (the additive skip), out_p = pooled tensor.
+struct FirstFuse {
+  const float* scale;
+  const float* shift;
+  const float* slope;
+  float* out_a;
+  float* out_p;
+  int round_p;
+};
+template <int N, bool FUSE = false>
 __global__ void __launch_bounds__(FIRST_THREADS, 1)
 conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ w, float* __restrict__ z,
-                     float* __restrict__ partials, int B, int Cin, int H, int W, int tw, int th) {
+                     float* __restrict__ partials, int B, int Cin, int H, int W, int tw, int th, const FirstFuse F) {
   using Cfg = FirstCfg<N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1548,7 +1560,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
   if (warp < 4) {
     // ===== builders =====
     const int r = threadIdx.x;                              // row of the tile = pixel (r % tw, r / tw)
-    const int iw = r % tw, ih = r / tw;
+    const int iw = FUSE ? (r >> 1) : r % tw, ih = FUSE ? (r & 1) : r / tw;
     int stage = 0, xs = 0;
     uint32_t phase = 0, xphase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -1636,10 +1648,16 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
     constexpr int NCH = N / 32;
     static_assert(NCH <= 2, "one 32-column chunk per epilogue warp");
     const bool has_chunk = half < NCH;
-    float s1[32], s2[32];
+    float s1[32], s2[32];                                   // FUSE: scale / shift of this warp's 32 columns
 #pragma unroll
     for (int j = 0; j < 32; ++j) s1[j] = s2[j] = 0.f;
-    const int iw = row % tw, ih = row / tw;
+    float slope = 0.f;
+    if (FUSE && has_chunk) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { s1[j] = __ldg(F.scale + half * 32 + j); s2[j] = __ldg(F.shift + half * 32 + j); }
+      slope = __ldg(F.slope);
+    }
+    const int iw = FUSE ? (row >> 1) : row % tw, ih = FUSE ? (row & 1) : row / tw;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -1655,17 +1673,33 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
       if (has_chunk) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + half * 32, v);
-        if (partials && valid) {
+        if (FUSE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+          for (int j = 0; j < 32; ++j) {
+            const float y = fmaf(v[j], s1[j], s2[j]);
+            v[j] = y > 0.f ? y : y * slope;
+          }
+          warp_store_rows(stg, lane, v, F.out_a, p * N + half * 32, valid, 0);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {                    // 2x2 window = lanes l, l^1 (other row), l^2, l^3 (next column)
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
+            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 2));
+          }
+          const long long pp = (((long long)b * (H >> 1) + (hq >> 1)) * (W >> 1) + (wq >> 1)) * N + half * 32;
+          warp_store_rows(stg, lane, v, F.out_p, pp, valid && (lane & 3) == 0, F.round_p);
+        } else {
+          if (partials && valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+          }
+          warp_store_rows(stg, lane, v, z, p * N + half * 32, valid, 0);
         }
-        warp_store_rows(stg, lane, v, z, p * N + half * 32, valid, 0);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
     }
-    if (partials && has_chunk) {
+    if (!FUSE && partials && has_chunk) {
       const float c1 = warp_colsum32(s1, lane), c2 = warp_colsum32(s2, lane);
       float* dst = partials + (size_t)(blockIdx.x * 4 + q) * N * 2;
       dst[(half * 32 + lane) * 2 + 0] = c1;
@@ -1690,24 +1724,33 @@ bool conv_first_tc_shape_ok(int Cin, int Cout, int H, int W) {
   return H >= th && (long long)H * W < (1LL << 31);
 }
 
-template <int N>
+template <int N, bool FUSE>
 static int launch_first_t(const CUtensorMap& mapX, const float* w, float* z, float* partials, int B, int Cin, int H, int W,
-                          int tw, int th, int grid, cudaStream_t s) {
+                          int tw, int th, int grid, const FirstFuse& F, cudaStream_t s) {
   using Cfg = FirstCfg<N>;
   static bool attr_set = false;
   if (!attr_set) {
-    RD_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    RD_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<N, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_first_tc_kernel<N><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(mapX, w, z, partials, B, Cin, H, W, tw, th);
+  conv_first_tc_kernel<N, FUSE><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(mapX, w, z, partials, B, Cin, H, W, tw, th, F);
   RD_LAUNCHED();
   return 0;
 }
 
+// the fused inference epilogue pools inside a 64 x 2 pixel tile
+bool conv_first_tc_fuse_ok(int Cin, int Cout, int H, int W) {
+  return conv_first_tc_shape_ok(Cin, Cout, H, W) && W >= 64 && H % 2 == 0 && W % 2 == 0;
+}
+
 int launch_conv_first_tc(const float* x, const float* w, float* z, float* partials, int* n_partials, int B, int Cin,
-                         int H, int W, int Cout, cudaStream_t s) {
+                         int H, int W, int Cout, cudaStream_t s, const float* scale, const float* shift, const float* slope,
+                         float* out_a, float* out_p, int round_p) {
   if (!conv_first_tc_shape_ok(Cin, Cout, H, W)) return fail("conv_first_tc: unsupported Cin=%d Cout=%d %dx%d", Cin, Cout, H, W);
-  const int tw = pow2_floor(W < 128 ? W : 128), th = 128 / tw;
+  const bool fuse = scale != nullptr;
+  if (fuse && !conv_first_tc_fuse_ok(Cin, Cout, H, W)) return fail("conv_first_tc: fused epilogue needs W >= 64, even H and W");
+  const FirstFuse F{scale, shift, slope, out_a, out_p, round_p};
+  const int tw = fuse ? 64 : pow2_floor(W < 128 ? W : 128), th = 128 / tw;
   // one tensor map per call: x is the caller's tensor (a different address every batch)
   CUtensorMap mapX;
   const long long dims[4] = {W, H, Cin, B};
@@ -1718,8 +1761,10 @@ int launch_conv_first_tc(const float* x, const float* w, float* z, float* partia
   const int grid = tiles < 148 ? (int)tiles : 148;
   if (n_partials) *n_partials = grid * 4;
   switch (Cout) {
-    case 32: return launch_first_t<32>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, s);
-    case 64: return launch_first_t<64>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, s);
+    case 32: return fuse ? launch_first_t<32, true>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s)
+                         : launch_first_t<32, false>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s);
+    case 64: return fuse ? launch_first_t<64, true>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s)
+                         : launch_first_t<64, false>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s);
   }
   return fail("conv_first_tc: unsupported Cout=%d", Cout);
 }

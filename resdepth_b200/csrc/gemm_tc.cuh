@@ -87,8 +87,11 @@ int tc_make_reduce_plan_wide(TcReducePlan* plan, const void* U, int Cu, const vo
 // x NCHW, w OIHW, z NHWC; partials: [n_partials][Cout][2] BatchNorm column sums (may be null)
 bool conv_first_tc_eligible(int Cin, int Cout);
 bool conv_first_tc_shape_ok(int Cin, int Cout, int H, int W);
+// scale != null: fused inference epilogue -- out_a = act(z*scale+shift), out_p = its 2x2 max-pool, z is not written
+bool conv_first_tc_fuse_ok(int Cin, int Cout, int H, int W);
 int launch_conv_first_tc(const float* x, const float* w, float* z, float* partials, int* n_partials, int B, int Cin,
-                         int H, int W, int Cout, cudaStream_t s);
+                         int H, int W, int Cout, cudaStream_t s, const float* scale = nullptr, const float* shift = nullptr,
+                         const float* slope = nullptr, float* out_a = nullptr, float* out_p = nullptr, int round_p = 0);
 
 bool tc_rows_eligible(const Gather& g, int N, int bf16 = 0);
 int tc_pick_bn(int N);

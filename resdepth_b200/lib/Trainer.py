@@ -440,6 +440,8 @@ class Trainer(object):
         """Replays (or, the second time the same device buffers are seen, captures) the CUDA graphs of a step on
         these buffers; returns None when the step should run eagerly instead."""
         tensors = (x, y, loss_mask, mean, std)
+        if self.model._rt['handle'].profiling:            # per-category timing events cannot be captured
+            return None
         if not all(t.is_cuda and t.is_contiguous() for t in tensors) or x.dtype != torch.float32 \
                 or y.dtype != torch.float32 or mean.dtype != torch.float32 or std.dtype != torch.float32:
             return None
@@ -452,7 +454,14 @@ class Trainer(object):
             self._graph_seen[key] = seen
             if seen < 2:
                 return None                      # first sight: eager (also reserves the workspace for this shape)
-            g = self._capture_step(x, y, loss_mask, mean, std, train)
+            try:
+                g = self._capture_step(x, y, loss_mask, mean, std, train)
+            except Exception as exc:                      # capture is an optimisation: fall back to eager launches
+                self.use_graphs = False
+                self._graphs.clear()
+                self.logger.warning(f'resdepth_b200: CUDA-graph capture failed ({exc}); continuing with eager launches')
+                torch.cuda.synchronize(self.device)
+                return None
             if len(self._graphs) >= _MAX_GRAPHS:
                 self._graphs.pop(next(iter(self._graphs)))
             self._graphs[key] = g
