@@ -159,3 +159,63 @@ def test_rd_config_layout_matches_header_and_integration_snippet():
     # every symbol the header declares is bound, and vice versa
     declared = set(re.findall(r'\b(rd_[a-z0-9_]+)\s*\(', header))
     assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+
+
+def test_backward_stage_ranges_tile_the_gradient_arena_for_every_depth():
+    """rd_grad_stage_range (the data-parallel slices): stage 2 | stage 1 | stage 0 are contiguous, start at 0 and end at
+    the arena size, stage 1 starts at the deepest encoder level and stage 0 at the first up-conv -- for every depth,
+    without a GPU (the layer plan is host-side)."""
+    for depth in (1, 2, 3, 5, 6):
+        cfg = _native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=depth, do_bn=1,
+                               bias_conv_layer=1, outer_skip=1, math_mode=1)
+        h = _native.Handle(cfg, 0)
+        spans = [h.grad_stage_range(s) for s in range(3)]
+        assert spans[2][0] == 0
+        assert spans[2][0] + spans[2][1] == spans[1][0]
+        assert spans[1][0] + spans[1][1] == spans[0][0]
+        assert spans[0][0] + spans[0][1] == h.param_arena_size()
+        offsets = {n: off for n, _, off in h.param_infos()}
+        assert spans[1][0] == offsets[f'encoder.{depth - 1}.0.0.weight']
+        assert spans[0][0] == offsets['decoder.0.0.weight' if depth > 1 else 'decoder.0.weight']
+        assert all(n >= 0 for _, n in spans) and (depth == 1) == (spans[2][1] == 0)
+        assert h.workspace_id() == 0 and not h.workspace_alive(1)      # no layout before the first forward call
+        h.close()
+
+
+def test_backward_math_knob_reaches_the_native_config():
+    from resdepth_b200.lib.UNet import UNet
+    m = UNet(n_input_channels=3, start_kernel=32, depth=2)
+    assert m._config().bwd_mode == _native.BWD_IDS['auto']
+    m.backward_math = 'tf32'
+    assert m._config().bwd_mode == _native.BWD_IDS['tf32']
+    m.backward_math = 'fp8'
+    with pytest.raises(ValueError, match='backward_math'):
+        m._config()
+    cfg = _native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1, bwd_mode=7)
+    with pytest.raises(RuntimeError, match='bwd_mode'):
+        _native.Handle(cfg, 0)
+    for mode, name in ((0, 'bf16'), (1, 'tf32'), (2, 'bf16')):
+        h = _native.Handle(_native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1,
+                                            math_mode=1, bwd_mode=mode), 0)
+        assert h.bwd_mode_name() == name
+        h.close()
+    h = _native.Handle(_native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=3, do_bn=1,
+                                        math_mode=0), 0)
+    assert h.bwd_mode_name() == 'fp32'
+    h.close()
+
+
+def test_trainer_shards_host_batches_before_staging():
+    """Trainer._my_shard: rank r of a data-parallel job takes tiles [r*B/N, (r+1)*B/N) of every loader batch unless the
+    loader already shards; staged (device) batches pass through untouched."""
+    from resdepth_b200.lib.Trainer import Trainer, _StagedBatch
+    tr = Trainer.__new__(Trainer)
+    tr.rank, tr.world_size = 1, 4
+    tr.shard_batches = {'train': True, 'val': False}
+    batch = {'input': torch.arange(8.).view(8, 1, 1, 1), 'dsm_std': torch.arange(8.), 'tile_size': 256}
+    mine = tr._my_shard(batch, 'train')
+    assert mine['input'].flatten().tolist() == [2.0, 3.0] and mine['dsm_std'].tolist() == [2.0, 3.0]
+    assert mine['tile_size'] == 256
+    assert tr._my_shard(batch, 'val') is batch
+    staged = _StagedBatch(batch)
+    assert tr._my_shard(staged, 'train') is staged
