@@ -1143,7 +1143,59 @@ im2col_first_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict_
     }
   }
 }
+// Compile-time form for Cin <= 3 (the tensor-core first layer): one thread per pixel gathers its 3 x 3 x Cin
+// neighbourhood with unrolled, constant tap offsets (three row and three column validity flags instead of a divide /
+// modulo chain per element -- the generic kernel above needs ~200 instructions per 16-byte chunk and was SM-bound at
+// 19 % DRAM, ncu round 2), appends the constant-one column and writes the live 16-byte chunks of its row.
+template <int CIN, int KC>
+__global__ void __launch_bounds__(256)
+im2col_first_bf16_px_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xcol, int B, int H, int W) {
+  constexpr int K = CIN * 9, CHUNKS = (K + 1 + 7) / 8;
+  const long long NP = (long long)B * H * W;
+  for (long long p = blockIdx.x * 256LL + threadIdx.x; p < NP; p += gridDim.x * 256LL) {
+    const int w = (int)(p % W);
+    const long long r_ = p / W;
+    const int h = (int)(r_ % H);
+    const long long b = r_ / H;
+    const bool rok[3] = {h > 0, true, h + 1 < H}, cok[3] = {w > 0, true, w + 1 < W};
+    float v[CHUNKS * 8];
+#pragma unroll
+    for (int k = 0; k < CHUNKS * 8; ++k) v[k] = k == K ? 1.f : 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float* xc = x + ((size_t)(b * CIN + ci) * H + h) * W + w;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (rok[r] && cok[q]) v[ci * 9 + r * 3 + q] = __ldg(xc + (r - 1) * W + (q - 1));
+    }
+    uint4* dst = reinterpret_cast<uint4*>(xcol + (size_t)p * KC);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162 bb = __floats2bfloat162_rn(v[c * 8 + 2 * j], v[c * 8 + 2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&bb);
+      }
+      dst[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  }
+}
+
 int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s) {
+  static const bool generic = getenv("RESDEPTH_IM2COL_GENERIC") != nullptr;
+  if (!generic && Kc == 64 && Cin >= 1 && Cin <= 3) {
+    const long long NP = (long long)B * H * W;
+    const int grid = (int)((NP + 255) / 256 < 148 * 8 ? (NP + 255) / 256 : 148 * 8);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xcol);
+    if (Cin == 3) im2col_first_bf16_px_kernel<3, 64><<<grid, 256, 0, s>>>(x, o, B, H, W);
+    else if (Cin == 2) im2col_first_bf16_px_kernel<2, 64><<<grid, 256, 0, s>>>(x, o, B, H, W);
+    else im2col_first_bf16_px_kernel<1, 64><<<grid, 256, 0, s>>>(x, o, B, H, W);
+    RD_LAUNCHED();
+    return 0;
+  }
   const int chunks = (Cin * 9 + 7) / 8;
   if (chunks * 8 > Kc) return fail("im2col_first_bf16: Kc=%d too small for Cin=%d", Kc, Cin);
   const int grid = B * H < 148 * 8 ? B * H : 148 * 8;

@@ -258,8 +258,8 @@ class Trainer(object):
             for n in _STEP_KEYS:
                 src = torch.flatten(batch[n]) if n.startswith('dsm_') else batch[n]
                 if use_static:
-                    if not src.is_pinned():
-                        src = src.pin_memory()
+                    # pinned batches (DataLoader(pin_memory=True), the reference's setting) copy asynchronously; pageable
+                    # ones go through the driver's staged copy -- pinning 70 MB per batch here would cost more than it saves
                     st[n].copy_(src, non_blocking=True)
                     staged[n] = st[n]
                 else:
