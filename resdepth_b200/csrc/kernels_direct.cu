@@ -449,14 +449,18 @@ conv_last_fwd_kernel(const float* __restrict__ u, const float* __restrict__ w, c
 //   pass 2 (conv_last_gather_kernel): y[q] = bias + x0[q] + sum_k t[k][q + off(k)]   (36 B per pixel, L2-resident)
 // ----------------------------------------------------------------------------------------------
 static constexpr int LTP_PIX = 256, LTP_NST = 3;
-template <int C>
-__global__ void __launch_bounds__(256, 1)
+// PPT pixels per thread (256 / PPT threads per CTA): the 9 weight loads of a channel quad are shared by the PPT pixels --
+// with one pixel per thread the kernel was bound by the shared-memory pipe (ncu round 2: stall_mio + short scoreboard
+// 48 %, 160 LDS.128 per pixel); two pixels per thread need 88 per pixel.
+template <int C, int PPT>
+__global__ void __launch_bounds__(256 / PPT, 1)
 conv_last_taps_kernel(const float* __restrict__ u, const float* __restrict__ w, float* __restrict__ taps, long long NP) {
+  constexpr int NT = 256 / PPT;
   constexpr int Q = C / 4, ROWB = C * 4 + 16, STAGE = LTP_PIX * ROWB;
   extern __shared__ __align__(16) uint8_t ltp_smem[];
   float* wq = reinterpret_cast<float*>(ltp_smem + LTP_NST * STAGE);       // [Q][36]: 4 x (k 0..7), then k = 8 of the 4 channels
   const int tid = threadIdx.x;
-  for (int i = tid; i < C * 9; i += 256) {
+  for (int i = tid; i < C * 9; i += NT) {
     const int c = i / 9, k = i - c * 9;
     wq[(c >> 2) * 36 + (k < 8 ? (c & 3) * 8 + k : 32 + (c & 3))] = w[i];
   }
@@ -467,8 +471,8 @@ conv_last_taps_kernel(const float* __restrict__ u, const float* __restrict__ w, 
       uint8_t* dst = ltp_smem + (int)(n % LTP_NST) * STAGE;
       const long long p0 = chunk * LTP_PIX;
 #pragma unroll
-      for (int j = 0; j < Q; ++j) {
-        const int idx = j * 256 + tid;
+      for (int j = 0; j < Q * PPT; ++j) {
+        const int idx = j * NT + tid;
         const int px = idx / Q, ch = idx % Q;
         const bool ok = p0 + px < NP;
         lf_cp_async16(dst + px * ROWB + ch * 16, ok ? u + (size_t)(p0 + px) * C + ch * 4 : u, ok);
@@ -484,31 +488,44 @@ conv_last_taps_kernel(const float* __restrict__ u, const float* __restrict__ w, 
     asm volatile("cp.async.wait_group %0;" ::"n"(LTP_NST - 2) : "memory");
     __syncthreads();                                   // chunk n has landed for every thread; chunk n-1's stage is free
     issue(n + LTP_NST - 1);
-    const uint8_t* row = ltp_smem + (int)(n % LTP_NST) * STAGE + tid * ROWB;
-    float2 a01 = make_float2(0.f, 0.f), a23 = a01, a45 = a01, a67 = a01, a8 = a01;
+    const uint8_t* stage = ltp_smem + (int)(n % LTP_NST) * STAGE;
+    float2 a01[PPT], a23[PPT], a45[PPT], a67[PPT], a8[PPT];
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) a01[e] = a23[e] = a45[e] = a67[e] = a8[e] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int cq = 0; cq < Q; ++cq) {
-      const float4 uv = *reinterpret_cast<const float4*>(row + cq * 16);
       const float4* wp = reinterpret_cast<const float4*>(wq + cq * 36);
-      const float uu[4] = {uv.x, uv.y, uv.z, uv.w};
+      float4 uv[PPT];
+#pragma unroll
+      for (int e = 0; e < PPT; ++e) uv[e] = *reinterpret_cast<const float4*>(stage + (tid + e * NT) * ROWB + cq * 16);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 wa = wp[2 * j], wb = wp[2 * j + 1];
-        const float2 ub = make_float2(uu[j], uu[j]);
-        a01 = ffma2(ub, make_float2(wa.x, wa.y), a01);
-        a23 = ffma2(ub, make_float2(wa.z, wa.w), a23);
-        a45 = ffma2(ub, make_float2(wb.x, wb.y), a45);
-        a67 = ffma2(ub, make_float2(wb.z, wb.w), a67);
+#pragma unroll
+        for (int e = 0; e < PPT; ++e) {
+          const float us = j == 0 ? uv[e].x : (j == 1 ? uv[e].y : (j == 2 ? uv[e].z : uv[e].w));
+          const float2 ub = make_float2(us, us);
+          a01[e] = ffma2(ub, make_float2(wa.x, wa.y), a01[e]);
+          a23[e] = ffma2(ub, make_float2(wa.z, wa.w), a23[e]);
+          a45[e] = ffma2(ub, make_float2(wb.x, wb.y), a45[e]);
+          a67[e] = ffma2(ub, make_float2(wb.z, wb.w), a67[e]);
+        }
       }
       const float4 w8 = wp[8];
-      a8 = ffma2(make_float2(uv.x, uv.y), make_float2(w8.x, w8.y), a8);
-      a8 = ffma2(make_float2(uv.z, uv.w), make_float2(w8.z, w8.w), a8);
+#pragma unroll
+      for (int e = 0; e < PPT; ++e) {
+        a8[e] = ffma2(make_float2(uv[e].x, uv[e].y), make_float2(w8.x, w8.y), a8[e]);
+        a8[e] = ffma2(make_float2(uv[e].z, uv[e].w), make_float2(w8.z, w8.w), a8[e]);
+      }
     }
-    const long long p = chunk * LTP_PIX + tid;
-    if (p < NP) {
-      taps[0 * NP + p] = a01.x; taps[1 * NP + p] = a01.y; taps[2 * NP + p] = a23.x; taps[3 * NP + p] = a23.y;
-      taps[4 * NP + p] = a45.x; taps[5 * NP + p] = a45.y; taps[6 * NP + p] = a67.x; taps[7 * NP + p] = a67.y;
-      taps[8 * NP + p] = a8.x + a8.y;
+#pragma unroll
+    for (int e = 0; e < PPT; ++e) {
+      const long long p = chunk * LTP_PIX + tid + e * NT;
+      if (p < NP) {
+        taps[0 * NP + p] = a01[e].x; taps[1 * NP + p] = a01[e].y; taps[2 * NP + p] = a23[e].x; taps[3 * NP + p] = a23[e].y;
+        taps[4 * NP + p] = a45[e].x; taps[5 * NP + p] = a45[e].y; taps[6 * NP + p] = a67[e].x; taps[7 * NP + p] = a67[e].y;
+        taps[8 * NP + p] = a8[e].x + a8[e].y;
+      }
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -550,15 +567,16 @@ int launch_conv_last_fwd(const float* u, const float* w, const float* bias, cons
     const long long NP = (long long)B * H * W;
     const long long nchunks = (NP + LTP_PIX - 1) / LTP_PIX;
     const int grid = (int)(nchunks < 148 ? nchunks : 148);
-    if (C == 64) {
-      const int smem = LTP_NST * LTP_PIX * (64 * 4 + 16) + 64 * 9 * 4;
-      RD_CUDA(cudaFuncSetAttribute(conv_last_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv_last_taps_kernel<64><<<grid, 256, smem, s>>>(u, w, tap_scratch, NP);
-    } else {
-      const int smem = LTP_NST * LTP_PIX * (32 * 4 + 16) + 32 * 9 * 4;
-      RD_CUDA(cudaFuncSetAttribute(conv_last_taps_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      conv_last_taps_kernel<32><<<grid, 256, smem, s>>>(u, w, tap_scratch, NP);
-    }
+    static const int ppt = getenv("RESDEPTH_TAPS_PPT") ? atoi(getenv("RESDEPTH_TAPS_PPT")) : 2;
+#define RD_TAPS(CC, PP)                                                                                              \
+  {                                                                                                                  \
+    const int smem = LTP_NST * LTP_PIX * (CC * 4 + 16) + CC * 9 * 4;                                                 \
+    RD_CUDA(cudaFuncSetAttribute(conv_last_taps_kernel<CC, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+    conv_last_taps_kernel<CC, PP><<<grid, 256 / PP, smem, s>>>(u, w, tap_scratch, NP);                               \
+  }
+    if (C == 64) { if (ppt == 1) RD_TAPS(64, 1) else RD_TAPS(64, 2) }
+    else { if (ppt == 1) RD_TAPS(32, 1) else RD_TAPS(32, 2) }
+#undef RD_TAPS
     RD_LAUNCHED();
     const long long blocks = (NP + 255) / 256;
     conv_last_gather_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, s>>>(tap_scratch, bias, x, x_bstride, x_affine,
