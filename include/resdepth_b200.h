@@ -105,8 +105,8 @@ int rd_backward(rd_handle* h, const float* x, const float* dy, void* stream);
 
 /* The same backward pass in three consecutive stages, so that a data-parallel caller can start the gradient
  * all-reduce of one stage (lib/Trainer.py has none: the reference is single-device) while the next
- * stage computes.  Stage 0: last_layer + decoder; 1: bottleneck + deepest encoder level; 2: remaining encoder
- * levels.  Call 0, 1, 2 in order after one saving rd_forward; when a stage returns, `stream` is ordered after
+ * stage computes.  Stage 0: last_layer + decoder; 1: bottleneck + encoder levels >= min(3, depth-1); 2: the
+ * shallower encoder levels (few parameters: the one slice that cannot overlap anything is latency-sized).  Call 0, 1, 2 in order after one saving rd_forward; when a stage returns, `stream` is ordered after
  * every gradient of that stage.  rd_grad_stage_range: the contiguous slice [offset, offset + numel) of the
  * gradient arena (floats) that stage `stage` completes. */
 int rd_backward_stage(rd_handle* h, const float* x, const float* dy, int stage, void* stream);

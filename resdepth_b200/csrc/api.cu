@@ -1072,8 +1072,14 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
 
 }  // namespace
 
-// stage 0: last_layer + decoder (down to the first up-conv); 1: bottleneck + deepest encoder level; 2: the other
-// encoder levels; -1: everything.  Stages must run in order 0, 1, 2 after one saving forward pass.
+// Encoder levels >= stage_split belong to backward stage 1, the shallower ones to stage 2.  Parameter counts shrink 4x
+// per level towards the input while the backward time per level grows: with the split at level 3 the stage-1 slice
+// (bottleneck + deep levels, ~24 MB at depth 5) has the whole shallow backward pass (> 1 ms at batch 64) to hide its
+// all-reduce, and the last slice, which nothing can hide, is 1.5 MB (latency-sized).
+static int stage_split(const rd_handle* h) { return h->depth - 1 < 3 ? h->depth - 1 : 3; }
+
+// stage 0: last_layer + decoder (down to the first up-conv); 1: bottleneck + encoder levels >= stage_split; 2: the
+// shallower encoder levels; -1: everything.  Stages must run in order 0, 1, 2 after one saving forward pass.
 static int backward_stages(rd_handle* h, const float* x, const float* dy, int stage, void* stream) {
   if (!h || !dy || !x) return fail("rd_backward: null argument");
   if (!h->G) return fail("rd_backward: gradient arena not bound (rd_bind)");
@@ -1220,7 +1226,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
                           nullptr, gp_bf16 ? h->gp_b : nullptr, s));
   }
   for (int i = D - 1; i >= 0; --i) {
-    if (!all && (stage == 1) != (i == D - 1)) continue;
+    if (!all && (stage == 1) != (i >= stage_split(h))) continue;   // stage 1: deep encoder levels; stage 2: levels below the split
     const int H = T >> i;
     const GradRef gs = skip_grad_bf16(h, i) ? GradRef(h->gs_b[i], 1) : GradRef(h->g_skip[i]);
     const GradRef gp = gp_bf16 ? GradRef(h->gp_b, 1) : GradRef(h->gp);
@@ -1246,7 +1252,8 @@ int rd_backward_stage(rd_handle* h, const float* x, const float* dy, int stage, 
 
 int rd_grad_stage_range(const rd_handle* h, int stage, int64_t* offset, int64_t* numel) {
   if (!h || stage < 0 || stage > 2 || !offset || !numel) return fail("rd_grad_stage_range: bad argument");
-  const long long e_deep = h->enc[h->depth - 1].w, d_first = h->ups[0].w;
+  // parameters are laid out encoder.0 .. encoder.D-1, bottleneck, decoder.*, last_layer (+ outer-skip BatchNorm)
+  const long long e_deep = h->enc[stage_split(h)].w, d_first = h->ups[0].w;
   const long long lo = stage == 2 ? 0 : (stage == 1 ? e_deep : d_first);
   const long long hi = stage == 2 ? e_deep : (stage == 1 ? d_first : h->param_floats);
   *offset = lo;

@@ -163,7 +163,7 @@ def test_rd_config_layout_matches_header_and_integration_snippet():
 
 def test_backward_stage_ranges_tile_the_gradient_arena_for_every_depth():
     """rd_grad_stage_range (the data-parallel slices): stage 2 | stage 1 | stage 0 are contiguous, start at 0 and end at
-    the arena size, stage 1 starts at the deepest encoder level and stage 0 at the first up-conv -- for every depth,
+    the arena size, stage 1 starts at encoder level min(3, depth-1) and stage 0 at the first up-conv -- for every depth,
     without a GPU (the layer plan is host-side)."""
     for depth in (1, 2, 3, 5, 6):
         cfg = _native.RdConfig(n_input_channels=3, start_kernel=64, max_filter_depth=512, depth=depth, do_bn=1,
@@ -175,7 +175,7 @@ def test_backward_stage_ranges_tile_the_gradient_arena_for_every_depth():
         assert spans[1][0] + spans[1][1] == spans[0][0]
         assert spans[0][0] + spans[0][1] == h.param_arena_size()
         offsets = {n: off for n, _, off in h.param_infos()}
-        assert spans[1][0] == offsets[f'encoder.{depth - 1}.0.0.weight']
+        assert spans[1][0] == offsets[f'encoder.{min(3, depth - 1)}.0.0.weight']
         assert spans[0][0] == offsets['decoder.0.0.weight' if depth > 1 else 'decoder.0.weight']
         assert all(n >= 0 for _, n in spans) and (depth == 1) == (spans[2][1] == 0)
         assert h.workspace_id() == 0 and not h.workspace_alive(1)      # no layout before the first forward call
