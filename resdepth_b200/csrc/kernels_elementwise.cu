@@ -885,6 +885,42 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const __grid_constant
       tl[r][c] = w[((size_t)(co0 + r) * Ci + ci0) * 9 + c];
     }
     __syncthreads();
+    // vector stores for the tensor-core layouts: one (co, t) pair = 8 consecutive ci of nk (2 x 16 bytes), one
+    // (ci, t, 8 co) group = 16 bytes of dnk_b / 2 x 16 bytes of dnk -- 288 items each, instead of 2304 scalar stores
+    for (int item = threadIdx.x; item < 288; item += 256) {
+      if (nk) {
+        const int co = item / 9, t = item - co * 9;
+        float v[8];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) { const float x = tl[co][ci * 9 + t]; v[ci] = rnd ? tf32_rn(x) : x; }
+        float4* dst = reinterpret_cast<float4*>(nk + (size_t)(co0 + co) * 9 * Ci + (size_t)t * Ci + ci0);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (dnk || dnk_b) {
+        const int g = item & 3, t = (item >> 2) % 9, ci = item / 36;          // 8 co per item, co fastest
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = tl[g * 8 + q][ci * 9 + (8 - t)];
+        const size_t o = (size_t)(ci0 + ci) * 9 * Co + (size_t)t * Co + co0 + g * 8;
+        if (dnk) {
+          float4* dst = reinterpret_cast<float4*>(dnk + o);
+          dst[0] = rnd ? tf32_rn4(make_float4(v[0], v[1], v[2], v[3])) : make_float4(v[0], v[1], v[2], v[3]);
+          dst[1] = rnd ? tf32_rn4(make_float4(v[4], v[5], v[6], v[7])) : make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (dnk_b) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __nv_bfloat162 bb = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+            pk[q] = *reinterpret_cast<uint32_t*>(&bb);
+          }
+          *reinterpret_cast<uint4*>(dnk_b + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+    nk = nullptr; dnk = nullptr; dnk_b = nullptr;            // done above; the loop below serves the CUDA-core layouts
+    if (!kn && !dkn) return;
     for (int idx = threadIdx.x; idx < 32 * PK_ROW; idx += 256) {
       {                                                                 // ci fastest: (ci, t, co)
         const int ci = idx % PK_CI, t = (idx / PK_CI) % 9, co = idx / PK_ROW;

@@ -407,11 +407,17 @@ class Trainer(object):
         return y_pred, self._compute_denormalized_loss(y_pred, y, loss_mask, mean, std, want_grad=train)
 
     def _set_grads(self):
+        """``param.grad`` = views of the persistent flat gradient arena (what ``loss.backward()`` leaves behind in the
+        reference).  The views are built once per arena; per step this is one attribute assignment per parameter."""
         rt = self.model._rt
-        named = dict(self.model.named_parameters())
         flat = rt['grads']
-        for name, numel, off in rt['pinfos']:
-            named[name].grad = flat[off:off + numel].view(named[name].shape)
+        cache = rt.get('grad_views')
+        if cache is None or cache[0] != flat.data_ptr():
+            named = dict(self.model.named_parameters())
+            cache = rt['grad_views'] = (flat.data_ptr(), [(named[name], flat[off:off + numel].view(named[name].shape))
+                                                          for name, numel, off in rt['pinfos']])
+        for p, g in cache[1]:
+            p.grad = g
 
     def device_step(self, x, y, loss_mask, mean, std, train, wait_before_loss=None):
         """The step on device-resident tensors: forward, fused loss (+ gradient seed), backward, gradient
