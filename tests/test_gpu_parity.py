@@ -764,3 +764,33 @@ def test_device_tile_producer_feeds_the_trainer(tmp_path):
     tr = Trainer(args)
     l0 = tr.inference_one_batch(batch, 'train')['MAE_metric']
     assert np.isfinite(l0) and l0 > 0
+
+
+def test_eval_mode_autograd_gradients_against_oracle(math_mode):
+    """model.eval() with autograd recording (RD_FWD_EVAL_SAVE): BatchNorm uses the running statistics as constants, so its
+    backward has no mean / projection terms -- also through the first block's Gram-matrix weight gradient (c1 = c2 = 0)."""
+    kwargs, B, T = CASES['kat1']
+    spec = spec_of(kwargs)
+    model = _model(kwargs)
+    batch = batch_of('kat1')
+    # non-trivial running statistics first: one oracle train-mode forward updates them
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        O.unet_forward(sd, batch['input'], spec, training=True)
+    model.load_state_dict(sd)
+    pkeys = [k for k, _ in model.named_parameters()]
+    for k in pkeys:
+        sd[k].requires_grad_(True)
+    y_ref = O.unet_forward(sd, batch['input'], spec, training=False)
+    (y_ref - batch['target']).square().mean().backward()
+    model = model.to(DEV).eval()
+    y = model(batch['input'].to(DEV))
+    assert y.requires_grad
+    (y - batch['target'].to(DEV)).square().mean().backward()
+    tight = math_mode == 'fp32'
+    assert _rel(y.detach().cpu(), y_ref.detach()) <= (5e-6 if tight else 1e-3)
+    flat = torch.cat([p.grad.cpu().flatten() for _, p in model.named_parameters()])
+    flat_ref = torch.cat([sd[k].grad.flatten() for k in pkeys])
+    assert _rel(flat, flat_ref) <= (1e-3 if tight else 1e-2), _rel(flat, flat_ref)
+    g0, g0_ref = dict(model.named_parameters())['encoder.0.0.0.weight'].grad.cpu(), sd['encoder.0.0.0.weight'].grad
+    assert _rel(g0, g0_ref) <= (5e-3 if tight else 5e-2), _rel(g0, g0_ref)
