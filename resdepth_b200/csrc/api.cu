@@ -100,7 +100,8 @@ struct Workspace {
   // HBM-bound BatchNorm backward kernels); only when every GEMM of the backward runs the bf16 tcgen05 path
   bool overlap = false;
   void* xcol_b = nullptr;
-  int xcol_b_k = 0;
+  int xcol_b_k = 0;            // operand width of the expansion in the reduce GEMMs (64 / 128)
+  int xcol_b_pitch = 0;        // stored columns per pixel: 32 when the live columns fit (the boxes zero-fill the rest)
   float *ob_mean = nullptr, *ob_invstd = nullptr, *ob_affine = nullptr;
   float* taps = nullptr;       // last-conv forward: 9 tap partial sums per pixel
   float* gram = nullptr;       // first encoder block: Gram matrix of the bf16 im2col expansion [Kc][Kc]
@@ -305,7 +306,11 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     if (bf)
       for (int i = 0; i < D; ++i) h->gs_b[i] = c.take((size_t)B * (T >> i) * (T >> i) * h->enc[i].Cout / 2 + 64);
     h->xcol_b_k = h->enc[0].Cin * 9 <= 64 ? 64 : 128;
-    h->xcol_b = bf ? c.take((size_t)B * T * T * h->xcol_b_k / 2 + 64) : nullptr;
+    {
+      static const bool xcol32 = getenv("RESDEPTH_XCOL64") == nullptr;
+      h->xcol_b_pitch = (xcol32 && h->enc[0].Cin * 9 + 1 <= 32 && h->enc[0].Cin <= 3) ? 32 : h->xcol_b_k;
+    }
+    h->xcol_b = bf ? c.take((size_t)B * T * T * h->xcol_b_pitch / 2 + 64) : nullptr;
     h->xcol_k = (h->enc[0].Cin * 9 + 31) / 32 * 32;
     h->xcol = (tf && !bf) ? c.take((size_t)B * T * T * h->xcol_k) : nullptr;
   } else {
@@ -376,13 +381,14 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     Gather gb = gather_plain(T, T, h->xcol_b_k);
     h->tc_gram.valid = false;
     if (bf && h->xcol_b && tc_reduce_eligible(gb, b0.Cout, 1)) {
-      RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, b0.gyb, b0.Cout, h->part, h->part_floats, 1));
+      const int xp = h->xcol_b_pitch != h->xcol_b_k ? h->xcol_b_pitch : 0;
+      RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, b0.gyb, b0.Cout, h->part, h->part_floats, 1, xp, 0));
       b0.bb = true;
       // Gram matrix of the expansion (same GEMM with the expansion as both operands): lets the first block's weight
       // gradient be formed from gY, without the apply pass of its BatchNorm backward (block_backward)
       static const bool no_gram = getenv("RESDEPTH_NO_GRAM") != nullptr;
       if (!no_gram && h->cfg.do_bn && b0.Cin * 9 < h->xcol_b_k && tc_reduce_eligible(gb, h->xcol_b_k, 1))
-        RD_TRY(tc_make_reduce_plan(&h->tc_gram, h->xcol_b, gb, B, h->xcol_b, h->xcol_b_k, h->part, h->part_floats, 1));
+        RD_TRY(tc_make_reduce_plan(&h->tc_gram, h->xcol_b, gb, B, h->xcol_b, h->xcol_b_k, h->part, h->part_floats, 1, xp, xp));
     } else if (h->xcol) {
       Gather g0 = gather_plain(T, T, h->xcol_k);
       if (tc_reduce_eligible(g0, b0.Cout))
@@ -760,7 +766,7 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
   const float consts[4] = {0.f, 0.01f, 1.f, 0.f};          // relu slope, LeakyReLU default slope (lib/UNet.py:30)
   RD_CUDA(cudaMemcpy(h->consts, consts, sizeof(consts), cudaMemcpyHostToDevice));
   if (h->xcol_b) {                                         // row padding of the bf16 im2col expansion stays zero
-    RD_TRY(launch_im2col_first_bf16_clear(h->xcol_b, (size_t)batch * tile * tile * h->xcol_b_k * 2, nullptr));
+    RD_TRY(launch_im2col_first_bf16_clear(h->xcol_b, (size_t)batch * tile * tile * h->xcol_b_pitch * 2, nullptr));
     RD_CUDA(cudaDeviceSynchronize());
   }
   cur.res_batch = batch; cur.res_tile = tile; cur.res_bwd = with_backward;
@@ -1003,7 +1009,7 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
       const int kc = b.bb ? h->xcol_b_k : h->xcol_k;
       if (h->xcol_early) h->xcol_early = false;           // expansion already enqueued at the start of the backward pass
       else if (b.bb) {
-        RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, kc, ws));
+        RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, h->xcol_b_pitch, ws));
         if (gy_path) RD_TRY(first_layer_gram(h, ws));
       } else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, ws));
       RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, ws));
@@ -1114,7 +1120,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
     RD_CUDA(cudaStreamWaitEvent(h->side, h->ev_main, 0));
     const double px = (double)B * T * T;
     ProfScope ps(h, RD_PROF_FIRST_WGRAD, 0.0, px * (4.0 * b0.Cin + 2.0 * b0.Cin * 9), h->side);
-    RD_TRY(launch_im2col_first_bf16(x, h->xcol_b, B, b0.Cin, T, T, h->xcol_b_k, h->side));
+    RD_TRY(launch_im2col_first_bf16(x, h->xcol_b, B, b0.Cin, T, T, h->xcol_b_pitch, h->side));
     if (h->tc_gram.valid) RD_TRY(first_layer_gram(h, h->side));
     h->xcol_early = true;
   }

@@ -1247,9 +1247,14 @@ bool tc_reduce_eligible(const Gather& g, int N, int bf16) {
   return g.C % 32 == 0 && N % 32 == 0;
 }
 
+// a_pitch / g_pitch (elements, 0 = dense): the A / G tensor stores only its first `pitch` columns per pixel (row pitch =
+// pitch elements); the tensor map declares that inner extent and the TMA unit zero-fills the rest of the 128-byte box,
+// so a 32-column bf16 expansion feeds the same 64-column operand tiles at half the HBM traffic.
 int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, int B, const void* G, int N,
-                        float* part, size_t part_floats, int bf16) {
+                        float* part, size_t part_floats, int bf16, int a_pitch, int g_pitch) {
   if (!tc_reduce_eligible(g, N, bf16)) return fail("tc reduce plan: shape not eligible (C=%d N=%d bf16=%d)", g.C, N, bf16);
+  if ((a_pitch || g_pitch) && !(bf16 && g.ups == 1 && g.ntaps == 1 && g.C == 64 && (!g_pitch || N == 64)))
+    return fail("tc reduce plan: pitched operands are supported for the bf16 1-tap 64-column case only");
   TcReduceParams& P = plan->p;
   std::memset(&P, 0, sizeof(P));
   P.bf16 = bf16;
@@ -1268,10 +1273,11 @@ int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, in
     Wg = g.Wo; Hg = g.Ho; Bg = B;
     P.coord_w = 1; P.coord_h = 2; P.coord_b = 3;
     for (int t = 0; t < g.ntaps; ++t) { P.tap_off[t][0] = 0; P.tap_off[t][1] = g.dw[t]; P.tap_off[t][2] = g.dh[t]; P.tap_off[t][3] = 0; }
-    dims[0] = g.C; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
-    strides[0] = (long long)g.C * EB; strides[1] = (long long)g.Ws * g.C * EB; strides[2] = (long long)g.Hs * g.Ws * g.C * EB;
-    gdims[0] = N; gdims[1] = Wg; gdims[2] = Hg; gdims[3] = B;
-    gstrides[0] = (long long)N * EB; gstrides[1] = (long long)Wg * N * EB; gstrides[2] = (long long)Hg * Wg * N * EB;
+    const long long ap = a_pitch ? a_pitch : g.C, gp = g_pitch ? g_pitch : N;
+    dims[0] = ap; dims[1] = g.Ws; dims[2] = g.Hs; dims[3] = B;
+    strides[0] = ap * EB; strides[1] = (long long)g.Ws * ap * EB; strides[2] = (long long)g.Hs * g.Ws * ap * EB;
+    gdims[0] = gp; gdims[1] = Wg; gdims[2] = Hg; gdims[3] = B;
+    gstrides[0] = gp * EB; gstrides[1] = (long long)Wg * gp * EB; gstrides[2] = (long long)Hg * Wg * gp * EB;
   } else {
     Wg = g.Wo; Hg = B * g.Ho; Bg = 1;
     P.coord_w = 1; P.coord_h = 3; P.coord_b = -1;
@@ -1302,10 +1308,10 @@ int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, in
     long long d5[5], s5[4], gd5[5], gs5[4];
     int b5[5], gb5[5];
     const long long csrc = g.ups == 1 ? g.C : 2LL * g.C;          // channels of one pixel row of the A tensor
-    d5[0] = CH; d5[1] = dims[1]; d5[2] = dims[2]; d5[3] = dims[3]; d5[4] = csrc / CH;
+    d5[0] = a_pitch ? a_pitch : CH; d5[1] = dims[1]; d5[2] = dims[2]; d5[3] = dims[3]; d5[4] = a_pitch ? 1 : csrc / CH;
     s5[0] = strides[0]; s5[1] = strides[1]; s5[2] = strides[2]; s5[3] = 128;
     b5[0] = CH; b5[1] = box[1]; b5[2] = box[2]; b5[3] = box[3]; b5[4] = a_nch;
-    gd5[0] = CH; gd5[1] = gdims[1]; gd5[2] = gdims[2]; gd5[3] = gdims[3]; gd5[4] = N / CH;
+    gd5[0] = g_pitch ? g_pitch : CH; gd5[1] = gdims[1]; gd5[2] = gdims[2]; gd5[3] = gdims[3]; gd5[4] = g_pitch ? 1 : N / CH;
     gs5[0] = gstrides[0]; gs5[1] = gstrides[1]; gs5[2] = gstrides[2]; gs5[3] = 128;
     gb5[0] = CH; gb5[1] = box[1]; gb5[2] = box[2]; gb5[3] = box[3]; gb5[4] = plan->BN / CH;
     // fp32 MN-major operands need the 32-byte-atom swizzle; bf16 the standard 128-byte swizzle

@@ -75,7 +75,7 @@ bool tc_reduce_eligible(const Gather& g, int N, int bf16 = 0);
 // src: tensor the gather reads (rows of the result); G: [pixels][N] matrix; part_floats: capacity of the split buffer
 // bf16 != 0: src and G point to bf16 tensors
 int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, int B, const void* G, int N,
-                        float* part, size_t part_floats, int bf16 = 0);
+                        float* part, size_t part_floats, int bf16 = 0, int a_pitch = 0, int g_pitch = 0);
 int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s);
 // wide 3x3 weight gradient (bf16): D[cu][(tap, cs)] = sum_p U[p][cu] * S[p + sign*off(tap)][cs]; U, S: bf16 NHWC
 // [B,H,W,Cu] / [B,H,W,Cs], Cu % 128 == 0, Cs in {64, 128}.  part: [splits][Cu][ntiles*BN] (see plan->p.N)

@@ -1222,13 +1222,18 @@ im2col_first_bf16_px_kernel(const float* __restrict__ x, __nv_bfloat16* __restri
 
 int launch_im2col_first_bf16(const float* x, void* xcol, int B, int Cin, int H, int W, int Kc, cudaStream_t s) {
   static const bool generic = getenv("RESDEPTH_IM2COL_GENERIC") != nullptr;
-  if (!generic && Kc == 64 && Cin >= 1 && Cin <= 3) {
+  if ((!generic || Kc == 32) && (Kc == 64 || Kc == 32) && Cin >= 1 && Cin <= 3) {
+    // Kc = 32: rows of 32 bf16 (64 bytes) -- the reduce GEMMs read them through tensor maps whose boxes are 64 wide
     const long long NP = (long long)B * H * W;
     const int grid = (int)((NP + 255) / 256 < 148 * 8 ? (NP + 255) / 256 : 148 * 8);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(xcol);
-    if (Cin == 3) im2col_first_bf16_px_kernel<3, 64><<<grid, 256, 0, s>>>(x, o, B, H, W);
-    else if (Cin == 2) im2col_first_bf16_px_kernel<2, 64><<<grid, 256, 0, s>>>(x, o, B, H, W);
-    else im2col_first_bf16_px_kernel<1, 64><<<grid, 256, 0, s>>>(x, o, B, H, W);
+#define RD_IM2COL(CI)                                                                     \
+  {                                                                                       \
+    if (Kc == 64) im2col_first_bf16_px_kernel<CI, 64><<<grid, 256, 0, s>>>(x, o, B, H, W); \
+    else im2col_first_bf16_px_kernel<CI, 32><<<grid, 256, 0, s>>>(x, o, B, H, W);          \
+  }
+    if (Cin == 3) RD_IM2COL(3) else if (Cin == 2) RD_IM2COL(2) else RD_IM2COL(1)
+#undef RD_IM2COL
     RD_LAUNCHED();
     return 0;
   }
