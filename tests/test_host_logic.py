@@ -219,3 +219,35 @@ def test_trainer_shards_host_batches_before_staging():
     assert tr._my_shard(batch, 'val') is batch
     staged = _StagedBatch(batch)
     assert tr._my_shard(staged, 'train') is staged
+
+
+def test_first_block_weight_gradient_identity_used_by_the_cuda_path():
+    """DESIGN.md 4.7, checked against PyTorch autograd in float64 on the CPU: for conv(bias-free) -> BatchNorm(train) ->
+    ReLU, the weight gradient equals  cs * ( X^T gY - c1 * cx - c2 * (G W - cx * mean) )  with X the im2col expansion,
+    G = X^T X, cx = X^T 1, gY the gradient at the BatchNorm output times the ReLU mask, c1 = mean(gY),
+    c2 = mean(gY * xhat) / sigma, cs = gamma / sigma -- no second pass over z."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    B, Cin, Co, H = 3, 3, 8, 10
+    x = torch.randn(B, Cin, H, H, generator=g, dtype=torch.float64)
+    w = (0.3 * torch.randn(Co, Cin, 3, 3, generator=g, dtype=torch.float64)).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(Co, generator=g, dtype=torch.float64))
+    beta = 0.1 * torch.randn(Co, generator=g, dtype=torch.float64)
+    z = F.conv2d(x, w, padding=1)
+    y = F.batch_norm(z, None, None, gamma, beta, True, 0.1, 1e-5)
+    a = F.relu(y)
+    up = torch.randn(a.shape, generator=g, dtype=torch.float64)            # gradient arriving at the activation
+    (a * up).sum().backward()
+    # the pieces the CUDA path has: X (im2col), gY, batch statistics
+    X = F.unfold(x, 3, padding=1).transpose(1, 2).reshape(-1, Cin * 9)      # [pixels][27], k = ci*9 + r*3 + s
+    n = X.shape[0]
+    zc = z.detach().permute(0, 2, 3, 1).reshape(n, Co)
+    mean, var = zc.mean(0), zc.var(0, unbiased=False)
+    sigma = torch.sqrt(var + 1e-5)
+    gY = (up * (y.detach() > 0)).permute(0, 2, 3, 1).reshape(n, Co)
+    xhat = (zc - mean) / sigma
+    cs, c1, c2 = gamma / sigma, gY.mean(0), (gY * xhat).mean(0) / sigma
+    G, cx, A = X.T @ X, X.sum(0), X.T @ gY                                   # [27][27], [27], [27][Co]
+    W2 = w.detach().reshape(Co, Cin * 9)
+    dW = cs[:, None] * (A.T - c1[:, None] * cx[None, :] - c2[:, None] * (W2 @ G - mean[:, None] * cx[None, :]))
+    assert torch.allclose(dW.reshape(w.shape), w.grad, rtol=1e-9, atol=1e-10)
