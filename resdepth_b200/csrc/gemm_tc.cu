@@ -123,6 +123,80 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
   __syncwarp();
 }
 
+// Inference epilogue of one warp's 32 rows x 32 columns: BatchNorm(running statistics) + activation (+ 2x2 max-pool), all
+// in the TRANSPOSED domain (lane -> rows i*4 + lane/8, columns 4*(lane%8)..+3): the per-channel constants are two float4
+// per lane (requested before the accumulator load) instead of sixteen row-domain loads behind it, one staging round trip
+// serves both outputs, and the pooling partners of a row are a register (row ^ tw: same lane for tw >= 4) and lane ^ 8
+// (row ^ 1).  ncu (round 2): the row-domain version held the 64-channel inference convs at 41 % tensor pipe.
+__device__ __forceinline__ void warp_bnact_store_rows(float* stg, int lane, const float (&v)[32], float4 sc, float4 sh,
+                                                      float slope, float* __restrict__ out, long long off, bool ok, int rnd,
+                                                      float* __restrict__ pool_out, long long poff, bool pok, int rnd_pool,
+                                                      int tw) {
+  const uint32_t stg_s = smem_u32(stg);
+#pragma unroll
+  for (int c4 = 0; c4 < 8; ++c4)
+    sts128(stg_s + (lane * 32 + ((c4 ^ (lane & 7)) << 2)) * 4, make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
+  __syncwarp();
+  const int c4 = lane & 7;
+  const unsigned off_lo = (unsigned)(off & 0xffffffffu), off_hi = (unsigned)((unsigned long long)off >> 32);
+  const unsigned pof_lo = (unsigned)(poff & 0xffffffffu), pof_hi = (unsigned)((unsigned long long)poff >> 32);
+  float4 val[8];
+  unsigned okm = 0, pokm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    float4 a = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
+    a.x = fmaf(a.x, sc.x, sh.x); a.y = fmaf(a.y, sc.y, sh.y); a.z = fmaf(a.z, sc.z, sh.z); a.w = fmaf(a.w, sc.w, sh.w);
+    a.x = a.x > 0.f ? a.x : a.x * slope; a.y = a.y > 0.f ? a.y : a.y * slope;
+    a.z = a.z > 0.f ? a.z : a.z * slope; a.w = a.w > 0.f ? a.w : a.w * slope;
+    val[i] = a;
+    const unsigned lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
+    const bool okr = __shfl_sync(0xffffffffu, (int)ok, r) != 0;
+    okm |= (unsigned)okr << i;
+    if (okr) {
+      float4 w4 = a;
+      if (rnd) { w4.x = tf32_round(w4.x); w4.y = tf32_round(w4.y); w4.z = tf32_round(w4.z); w4.w = tf32_round(w4.w); }
+      *reinterpret_cast<float4*>(out + (long long)(((unsigned long long)hi << 32) | lo) + c4 * 4) = w4;
+    }
+  }
+  if (pool_out) {
+    // vertical partner: row ^ tw
+    float4 m[8];
+    if (tw >= 4) {
+      const int k = tw >> 2;                              // 1, 2 or 4: register index bit
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 o = k == 1 ? val[i ^ 1] : (k == 2 ? val[i ^ 2] : val[i ^ 4]);
+        m[i] = make_float4(fmaxf(val[i].x, o.x), fmaxf(val[i].y, o.y), fmaxf(val[i].z, o.z), fmaxf(val[i].w, o.w));
+      }
+    } else {                                              // tw == 2: row bit 1 = lane bit 4
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        m[i] = make_float4(fmaxf(val[i].x, __shfl_xor_sync(0xffffffffu, val[i].x, 16)),
+                           fmaxf(val[i].y, __shfl_xor_sync(0xffffffffu, val[i].y, 16)),
+                           fmaxf(val[i].z, __shfl_xor_sync(0xffffffffu, val[i].z, 16)),
+                           fmaxf(val[i].w, __shfl_xor_sync(0xffffffffu, val[i].w, 16)));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3);
+      float4 p4 = make_float4(fmaxf(m[i].x, __shfl_xor_sync(0xffffffffu, m[i].x, 8)),      // horizontal partner: row ^ 1
+                              fmaxf(m[i].y, __shfl_xor_sync(0xffffffffu, m[i].y, 8)),
+                              fmaxf(m[i].z, __shfl_xor_sync(0xffffffffu, m[i].z, 8)),
+                              fmaxf(m[i].w, __shfl_xor_sync(0xffffffffu, m[i].w, 8)));
+      const unsigned lo = __shfl_sync(0xffffffffu, pof_lo, r), hi = __shfl_sync(0xffffffffu, pof_hi, r);
+      const bool pk = __shfl_sync(0xffffffffu, (int)pok, r) != 0;
+      pokm |= (unsigned)pk << i;
+      if (pk) {
+        if (rnd_pool) { p4.x = tf32_round(p4.x); p4.y = tf32_round(p4.y); p4.z = tf32_round(p4.z); p4.w = tf32_round(p4.w); }
+        *reinterpret_cast<float4*>(pool_out + (long long)(((unsigned long long)hi << 32) | lo) + c4 * 4) = p4;
+      }
+    }
+  }
+  (void)okm; (void)pokm;
+  __syncwarp();
+}
+
 // Transposed-conv epilogue of one warp for one 128-row (sub-)tile: + bias, + additive skip (optionally BatchNorm +
 // activation of the raw encoder output on the fly), scatter to the 2x2 output sites, optional TF32 rounding and
 // bf16 copy.  The layer is HBM-bound and the skip read sits on the critical path of every store, so the skip rows
@@ -601,36 +675,21 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       for (int ci = 0; ci < NCH2; ++ci) {
         const int ch = 2 * ci + half;
         if (ch >= NCH) break;
+        const int n = nt * BN + ch * 32;
+        float4 bn_sc = make_float4(1.f, 1.f, 1.f, 1.f), bn_sh = make_float4(0.f, 0.f, 0.f, 0.f);
+        float bn_slope = 0.f;
+        if (P.epi_mode == EPI_BNACT) {                     // this lane's four channels of the transposed domain
+          bn_sc = __ldg(reinterpret_cast<const float4*>(P.scale + n) + (lane & 7));
+          bn_sh = __ldg(reinterpret_cast<const float4*>(P.shift + n) + (lane & 7));
+          bn_slope = __ldg(P.slope);
+        }
         float v[32];
         tmem_ld32(t_row + ch * 32, v);
-        const int n = nt * BN + ch * 32;
         if (P.epi_mode == EPI_BNACT) {
           // eval-mode BatchNorm folded into the conv: a = act(acc*scale + shift); optional fused 2x2 max-pool
-          // (the 2x2 window of a pixel lives in lanes l, l^1, l^tw, l^tw^1 of this warp)
-          const float slope = __ldg(P.slope);
-          const float4* scp = reinterpret_cast<const float4*>(P.scale + n);
-          const float4* shp = reinterpret_cast<const float4*>(P.shift + n);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 sc = __ldg(scp + j), sh = __ldg(shp + j);
-            float y0 = fmaf(v[4 * j], sc.x, sh.x), y1 = fmaf(v[4 * j + 1], sc.y, sh.y);
-            float y2 = fmaf(v[4 * j + 2], sc.z, sh.z), y3 = fmaf(v[4 * j + 3], sc.w, sh.w);
-            v[4 * j] = y0 > 0.f ? y0 : y0 * slope;
-            v[4 * j + 1] = y1 > 0.f ? y1 : y1 * slope;
-            v[4 * j + 2] = y2 > 0.f ? y2 : y2 * slope;
-            v[4 * j + 3] = y3 > 0.f ? y3 : y3 * slope;
-          }
-          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32);
-          if (P.pool_out) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float m = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-              v[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, P.tw));
-            }
-            const size_t pp = ((size_t)b * (P.Ho >> 1) + (h >> 1)) * (P.Wo >> 1) + (w >> 1);
-            warp_store_rows(stg, lane, v, P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1),
-                            P.round_pool);
-          }
+          const size_t pp = ((size_t)b * (P.Ho >> 1) + (h >> 1)) * (P.Wo >> 1) + (w >> 1);
+          warp_bnact_store_rows(stg, lane, v, bn_sc, bn_sh, bn_slope, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
+                                P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1), P.round_pool, P.tw);
         } else {
           if (P.epi_mode == EPI_STATS) {
             float sv[32], sq[32];
