@@ -252,6 +252,8 @@ def roofline_of(prof, K, pk, math_name, traffic_key_prefix=''):
                 'frac': achieved / pk['bf16_tflops_sustained'], 'traffic': None,
                 'peak_note': f"bf16 cuBLAS sustained ({pk['source']}); this kernel computes in "
                              f"{math_name.split(' ')[0]}: the tf32 tensor ceiling is half of it"}
+        if 'tf32' in math_name and dom_name.endswith('_fwd'):
+            roof['frac_of_tf32_ceiling'] = achieved / (0.5 * pk['bf16_tflops_sustained'])
     else:
         achieved = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
         roof = {'bound': 'hbm', 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
