@@ -510,8 +510,56 @@ def run_native(args):
             ib = max(nums['inference_fp32']['value'], nums['inference_bf16_channels_last']['value'])
             extras['vs_cudnn']['inference_vs_best'] = extras['inference']['value'] / ib
 
+    def blend_block():
+        """test.py's inference loop (predict_linear_blend): a 4096 x 4096 raster in 256 x 256 tiles with stride 128 (961
+        tiles in batches of 32 from pinned host memory), forward + de-normalise + ramp-weighted accumulation on the
+        device, the float64 raster read back once."""
+        from types import SimpleNamespace
+
+        from resdepth_b200.lib.evaluation import predict_linear_blend
+        from resdepth_b200.lib.UNet import UNet
+        R, tile, stride, bs = 4096, 256, 128, 32
+        starts = list(range(0, R - tile + 1, stride))
+        pos = [(y, x) for y in starts for x in starts]
+        box = []
+        for (y, x) in pos:                                   # non-overlapping boxes of a regular grid (rasterutils)
+            box.append((0 if y == 0 else tile - stride, 0 if x == 0 else tile - stride,
+                        tile - 1 if y == starts[-1] else stride - 1, tile - 1 if x == starts[-1] else stride - 1))
+        g = torch.Generator().manual_seed(5)
+        pool = [torch.randn(bs, 3, tile, tile, generator=g).pin_memory() for _ in range(4)]
+        batches = []
+        for i in range(0, len(pos), bs):
+            sl = slice(i, min(i + bs, len(pos)))
+            n = sl.stop - sl.start
+            batches.append({'input': pool[(i // bs) % 4][:n], 'dsm_mean': torch.full((n,), 400.0), 'dsm_std': torch.full((n,), 3.5),
+                            'patch_offset_y': torch.tensor([p[0] for p in pos[sl]]), 'patch_offset_x': torch.tensor([p[1] for p in pos[sl]]),
+                            'patch_valid_pixels_uly': torch.tensor([b[0] for b in box[sl]]),
+                            'patch_valid_pixels_ulx': torch.tensor([b[1] for b in box[sl]]),
+                            'patch_valid_pixels_lry': torch.tensor([b[2] for b in box[sl]]),
+                            'patch_valid_pixels_lrx': torch.tensor([b[3] for b in box[sl]])})
+
+        class Loader(list):
+            pass
+        loader = Loader(batches)
+        loader.dataset = SimpleNamespace(dsm_input_gdal=SimpleNamespace(RasterXSize=R, RasterYSize=R), tile_size=tile, stride=stride)
+        torch.manual_seed(0)
+        net = UNet(**CONFIGS['cfg3'][0]).to(dev)
+        predict_linear_blend(loader, net)                    # warm-up (workspace, plans)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = predict_linear_blend(loader, net)
+        dt = time.perf_counter() - t0
+        extras['predict_linear_blend'] = {
+            'workload': f'{R}x{R} raster, {len(pos)} tiles of {tile}x{tile} (stride {stride}), batches of {bs} from pinned host '
+                        'memory; wall clock incl. the H2D copies and the D2H of the float64 raster',
+            'value': len(pos) / dt, 'unit': UNIT, 'seconds': dt, 'raster_mean': float(out.mean())}
+        net._rt['handle'].close()
+        net._rt.clear()
+
     if args.config == 'cfg3' and not args.quick:
         main.close()
+        if world == 1:
+            guarded('predict_linear_blend', blend_block)
         guarded('value_tf32_bwd', tf32_block)
         for other in ('cfg5', 'cfg1'):
             guarded(other, lambda o=other: other_config(o))

@@ -4,8 +4,8 @@ Same signature and return value (a float64 ``numpy`` raster with the extent of t
 runs one forward per DataLoader batch, copies the prediction to the host, de-normalises it in numpy and
 accumulates ``tile * weights`` tile by tile in Python; here the forward (``rd_forward``), the de-normalisation
 (``denormalize_numpy``, lib/data_normalization.py:41-53), the per-tile ramp weights (``_get_blend_weights``,
-lib/evaluation.py:516-567) and the accumulation all stay on the device (``rd_blend_accumulate``), and the raster
-crosses PCIe once at the end.
+lib/evaluation.py:516-567) and the accumulation all stay on the device (``rd_blend_accumulate``), the input tiles of
+batch i+1 are copied while batch i computes, and the raster crosses PCIe once at the end.
 """
 from __future__ import annotations
 
@@ -51,22 +51,41 @@ def predict_linear_blend(dataloader, model):
     raster = torch.zeros((rows, cols), dtype=torch.float64, device=device)
 
     rank, world_size = world()          # one process per GPU: every rank blends its share of the batches
-    with torch.no_grad():
-        for bi, batch in enumerate(dataloader):
-            if not owns_batch(bi, rank, world_size):
-                continue
-            x = batch['input']
+    main = torch.cuda.current_stream(device)
+    copy = torch.cuda.Stream(device)
+
+    def stage(batch):
+        """H2D copies of one batch on the copy stream (one batch ahead of the forward pass that consumes it)."""
+        x = batch['input']
+        n = x.shape[0]
+        geom = np.stack([_as_int_array(batch[k]).reshape(n) for k in (
+            'patch_offset_y', 'patch_offset_x', 'patch_valid_pixels_uly', 'patch_valid_pixels_ulx',
+            'patch_valid_pixels_lry', 'patch_valid_pixels_lrx')], axis=1).astype(np.int32)
+        if x.is_cuda:
+            copy.wait_stream(main)
+        with torch.cuda.stream(copy):
             if not x.is_cuda and not x.is_pinned():
                 x = x.pin_memory()
-            x = x.to(device, dtype=torch.float32, non_blocking=True)
-            n = x.shape[0]
-            geom = np.stack([_as_int_array(batch[k]).reshape(n) for k in (
-                'patch_offset_y', 'patch_offset_x', 'patch_valid_pixels_uly', 'patch_valid_pixels_ulx',
-                'patch_valid_pixels_lry', 'patch_valid_pixels_lrx')], axis=1).astype(np.int32)
+            xd = x.to(device, dtype=torch.float32, non_blocking=True)
             geom_d = torch.from_numpy(np.ascontiguousarray(geom)).to(device, non_blocking=True)
             mean = torch.flatten(batch['dsm_mean']).to(device, dtype=torch.float32, non_blocking=True)
             std = torch.flatten(batch['dsm_std']).to(device, dtype=torch.float32, non_blocking=True)
-            y_pred = model(x)
+            ready = torch.cuda.Event()
+            ready.record(copy)
+        for t in (xd, geom_d, mean, std):
+            t.record_stream(main)
+        return xd, geom_d, mean, std, ready
+
+    mine = (batch for bi, batch in enumerate(dataloader) if owns_batch(bi, rank, world_size))
+    with torch.no_grad():
+        nxt = next(mine, None)
+        nxt = stage(nxt) if nxt is not None else None
+        while nxt is not None:
+            xd, geom_d, mean, std, ready = nxt
+            following = next(mine, None)
+            nxt = stage(following) if following is not None else None     # in flight while this batch computes
+            main.wait_event(ready)
+            y_pred = model(xd)
             blend_tiles_into(raster, y_pred, mean, std, geom_d, tile_size, stride)
     return sum_partial_rasters(raster).cpu().numpy()
 
