@@ -89,6 +89,7 @@ struct Workspace {
   std::vector<float*> g_skip;
   float *gy = nullptr, *gh = nullptr, *gp = nullptr;
   void* gp_b = nullptr;        // bf16 gradient at a pooled tensor (bf16 backward)
+  void* gh_b = nullptr;        // bf16 gradient at an up-conv input (= output of the block before it), bf16 backward
   float* xcol = nullptr;       // im2col expansion of the input for the first layer's tensor-core wgrad
   int xcol_k = 0;
   float* gt = nullptr;         // bilinear up-mode: gradient at the low-resolution 1x1-conv output
@@ -133,7 +134,7 @@ struct rd_handle : rd::Workspace {
   int fwd_batch = 0, fwd_tile = 0, fwd_mode = -1;
   // staged backward (rd_backward_stage): next expected stage, and whether the pooled-tensor gradient is in gp_b
   int bw_next_stage = 0;
-  bool bw_gp_bf16 = false;
+  bool bw_gp_bf16 = false, bw_gh_bf16 = false;
   bool xcol_early = false;     // the first layer's im2col expansion was enqueued at the start of this backward pass
   bool tf32() const { return cfg.math_mode == RD_MATH_TF32; }
 
@@ -302,6 +303,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
     h->gy_b = bf ? c.take(max_out / 2 + 64) : nullptr;
     h->gy_b2 = bf ? c.take(max_out / 2 + 64) : nullptr;
     h->gp_b = bf ? c.take(max_pool / 2 + 64) : nullptr;
+    h->gh_b = bf ? c.take(max_out / 2 + 64) : nullptr;
     h->gs_b.assign(D, nullptr);
     if (bf)
       for (int i = 0; i < D; ++i) h->gs_b[i] = c.take((size_t)B * (T >> i) * (T >> i) * h->enc[i].Cout / 2 + 64);
@@ -316,7 +318,7 @@ size_t carve(rd_handle* h, void* base, int B, int T, int bwd) {
   } else {
     h->xcol = nullptr;
     h->gt = nullptr;
-    h->gy_b = nullptr; h->gy_b2 = nullptr; h->xcol_b = nullptr; h->gp_b = nullptr;
+    h->gy_b = nullptr; h->gy_b2 = nullptr; h->xcol_b = nullptr; h->gp_b = nullptr; h->gh_b = nullptr;
     h->gs_b.assign(D, nullptr);
     h->part = nullptr; h->part_floats = 0;
     h->g_skip.assign(D, nullptr);
@@ -1099,6 +1101,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
   if (!all && stage != h->bw_next_stage)
     return fail("rd_backward_stage: stage %d out of order (expected %d)", stage, h->bw_next_stage);
   bool& gp_bf16 = h->bw_gp_bf16;                         // is the gradient at the current pooled tensor held in gp_b?
+  bool& gh_bf16 = h->bw_gh_bf16;                         // is the gradient at the last up-conv's input held in gh_b?
   auto join = [&]() -> int {                             // the caller's stream continues only after every weight gradient
     if (h->overlap && h->overlap_allowed) {
       RD_CUDA(cudaEventRecord(h->ev_join, h->side));
@@ -1146,6 +1149,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
     const float* Gu = h->g_skip[D - 1 - j];                  // gradient at u_j (and at skip a_{D-1-j})
     const float* X = j == 0 ? h->bott.a : h->dec[j - 1].a;   // input of the transposed conv
     const double px = (double)B * Hin * Hin, cc = (double)u.C * u.C;
+    gh_bf16 = false;
     // bias gradient = per-channel sum of du_j: produced by the kernel that wrote du_j (last-conv backward for the
     // last level, the decoder conv's dgrad epilogue for the others)
     if (u.bilinear) {
@@ -1199,7 +1203,11 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
     auto up_dgrad = [&]() -> int {
       Epilogue e{};
       e.mode = EPI_PLAIN;
-      e.out = h->gh;
+      // bf16 backward on tcgen05: the gradient at the up-conv's input is only read by the BatchNorm backward of the
+      // block that produced that input -- keep it in bf16 only, like the skip and pooled-tensor gradients
+      gh_bf16 = u.bb && u.tc && h->gh_b != nullptr;
+      e.out = gh_bf16 ? nullptr : h->gh;
+      e.out_b = gh_bf16 ? h->gh_b : nullptr;
       ProfScope ps(h, RD_PROF_CONVT_DGRAD, 2.0 * 4.0 * cc * px, 4.0 * px * u.C * 5.0, s);
       if (u.tc) RD_TRY(launch_gemm_rows_tc(u.tc_dgrad, e, nullptr, s));
       else RD_TRY(launch_gemm_rows_simt(Gu, g4, u.w_nk, B, u.C, e, nullptr, s));
@@ -1219,7 +1227,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
       // du_{j-1} is also the A operand of the next transposed-conv dgrad / wgrad: store it TF32-rounded (fp32
       // backward) or only as bf16 (bf16 backward)
       const bool only_b = skip_grad_bf16(h, D - j);
-      RD_TRY(block_backward(h, h->dec[j - 1], h->gh, GradRef(), B, Hin, h->ups[j - 1].u, false,
+      RD_TRY(block_backward(h, h->dec[j - 1], gh_bf16 ? GradRef(h->gh_b, 1) : GradRef(h->gh), GradRef(), B, Hin, h->ups[j - 1].u, false,
                             only_b ? nullptr : h->g_skip[D - j], h->tf32() && h->ups[j - 1].tc,
                             h->G + h->ups[j - 1].bias, only_b ? h->gs_b[D - j] : nullptr, s));
     }
@@ -1228,7 +1236,7 @@ static int backward_stages(rd_handle* h, const float* x, const float* dy, int st
   }
   if (all || stage == 1) {
     gp_bf16 = h->gp_b && h->bott.tc;
-    RD_TRY(block_backward(h, h->bott, h->gh, GradRef(), B, T >> D, h->enc[D - 1].p, false, gp_bf16 ? nullptr : h->gp, 0,
+    RD_TRY(block_backward(h, h->bott, h->bw_gh_bf16 ? GradRef(h->gh_b, 1) : GradRef(h->gh), GradRef(), B, T >> D, h->enc[D - 1].p, false, gp_bf16 ? nullptr : h->gp, 0,
                           nullptr, gp_bf16 ? h->gp_b : nullptr, s));
   }
   for (int i = D - 1; i >= 0; --i) {
