@@ -416,14 +416,19 @@ def run_native(args):
             model.eval()
             with torch.no_grad():
                 return model(infer_x)
-        infer_ms, _, _, _, _ = timed(infer_step, K, W)
-        _, _, infer_prof, _, _ = timed(infer_step, K, 2, arm=main, profile=True)
+        infer_repack_ms, _, _, _, _ = timed(infer_step, K, W)        # a bare model(x): weights re-packed every call
+        with model.constant_weights(dev):                           # what predict_linear_blend's tile loop runs
+            infer_ms, _, _, _, _ = timed(infer_step, K, W)
+            _, _, infer_prof, _, _ = timed(infer_step, K, 2, arm=main, profile=True)
         model.train()
         if rank == 0:
             iroof, ibreak, itotal, _ = roofline_of(infer_prof, K, peaks(), math_name, 'inference:')
             extras['inference'] = {
                 'workload': 'BASELINE configs[1]: eval-mode forward, 3-ch 256x256, depth 5, batch 32/GPU',
                 'value': 32 * world * K / (infer_ms * 1e-3), 'unit': UNIT, 'ms_per_call': infer_ms / K,
+                'note': 'inside model.constant_weights() (rd_freeze_params), as in predict_linear_blend; a bare '
+                        'model(x) re-packs the weights on every call',
+                'ms_per_call_repacking': infer_repack_ms / K,
                 'gflop_per_tile': 19.797, 'tflops': 32 * K / (infer_ms * 1e-3) * 19.797 / 1e3,
                 'roofline': iroof, 'kernel_ms_per_call': ibreak, 'kernel_ms_total_per_call': itotal / K}
         # tier-next figure: the on-device tile producer that feeds the step

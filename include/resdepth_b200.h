@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RD_ABI_VERSION 3
+#define RD_ABI_VERSION 4
 
 typedef struct rd_handle rd_handle;
 
@@ -168,6 +168,14 @@ int rd_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n
  * returns control of `stream`) when every GEMM of the backward pass takes the bf16 tcgen05 path.  on = 0 serialises
  * everything on the caller's stream (used by the per-kernel profile of bench.py); default 1. */
 int rd_set_overlap(rd_handle* h, int on);
+
+/* Inference with constant weights (test.py's tile loop, lib/evaluation.py:38-76; validation, lib/Trainer.py:269-300):
+ * while on, the caller promises that the parameter and BatchNorm-buffer arenas do not change, and RD_FWD_EVAL forwards
+ * re-use the packed GEMM copies of the weights and the BatchNorm scale / shift vectors of the first such forward after
+ * the switch-on instead of rebuilding them every call (one launch over all parameters + one over all BatchNorm
+ * layers).  Every switch-on starts a new generation (the next forward packs again), as do rd_bind, a training-mode
+ * forward on the same workspace layout and a new workspace layout.  on = 0 (default): every forward re-packs. */
+int rd_freeze_params(rd_handle* h, int on);
 
 /* Per-category device timing (CUDA events on the launching stream around the library's own launches).
  * rd_profile_enable(h, 1) starts recording; rd_profile_collect synchronises the recorded events and folds

@@ -15,7 +15,7 @@ ACT_IDS = {'relu': 0, 'lrelu': 1, 'prelu': 2}          # RD_ACT_*
 MATH_FP32, MATH_TF32 = 0, 1                             # RD_MATH_*
 FWD_EVAL, FWD_TRAIN, FWD_EVAL_SAVE = 0, 1, 2            # RD_FWD_*
 UP_IDS = {'transpose': 0, 'bilinear': 1}                # RD_UP_*
-ABI_VERSION = 3
+ABI_VERSION = 4
 BWD_IDS = {'auto': 0, 'tf32': 1, 'bf16': 2}                  # RD_BWD_*
 
 # every symbol include/resdepth_b200.h declares
@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     'rd_workspace_bytes', 'rd_forward', 'rd_loss', 'rd_backward', 'rd_adam_step', 'rd_sgd_step',
     'rd_blend_accumulate', 'rd_launch_count', 'rd_math_mode_name', 'rd_profile_enable', 'rd_profile_collect',
     'rd_profile_read', 'rd_debug_rows', 'rd_debug_reduce', 'rd_make_tiles', 'rd_residuals', 'rd_residual_stats',
-    'rd_tile_stds', 'rd_set_overlap', 'rd_backward_stage', 'rd_grad_stage_range', 'rd_bwd_mode_name',
+    'rd_tile_stds', 'rd_set_overlap', 'rd_freeze_params', 'rd_backward_stage', 'rd_grad_stage_range', 'rd_bwd_mode_name',
     'rd_workspace_id', 'rd_workspace_alive',
 )
 PROF_NUM = 18                                           # RD_PROF_NUM
@@ -115,6 +115,8 @@ def _declare(lib):
     lib.rd_tile_stds.argtypes = [vp, i32, i32, vp, i32, i32, f32, vp, vp]
     lib.rd_set_overlap.restype = i32
     lib.rd_set_overlap.argtypes = [vp, i32]
+    lib.rd_freeze_params.restype = i32
+    lib.rd_freeze_params.argtypes = [vp, i32]
     lib.rd_launch_count.restype = i64
     lib.rd_launch_count.argtypes = [i32]
     lib.rd_math_mode_name.restype = C.c_char_p
@@ -160,6 +162,7 @@ class Handle:
         check(self._lib.rd_create(C.byref(cfg), int(device_index), C.byref(self._h)), 'rd_create')
         self.device_index = int(device_index)
         self.profiling = False
+        self.frozen = False
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:
@@ -233,6 +236,11 @@ class Handle:
     def set_overlap(self, on: bool):
         """Side-stream weight gradients in rd_backward on (default) / off (everything on the caller's stream)."""
         check(self._lib.rd_set_overlap(self._h, 1 if on else 0), 'rd_set_overlap')
+
+    def freeze_params(self, on: bool):
+        """Constant-weight inference: while on, eval-mode forwards re-use the packed weights (rd_freeze_params)."""
+        check(self._lib.rd_freeze_params(self._h, 1 if on else 0), 'rd_freeze_params')
+        self.frozen = bool(on)
 
     def profile_enable(self, on: bool):
         check(self._lib.rd_profile_enable(self._h, 1 if on else 0), 'rd_profile_enable')

@@ -107,6 +107,7 @@ struct Workspace {
   float* taps = nullptr;       // last-conv forward: 9 tap partial sums per pixel
   float* gram = nullptr;       // first encoder block: Gram matrix of the bf16 im2col expansion [Kc][Kc]
   TcReducePlan tc_gram;        // reduce GEMM (xcol, xcol) that produces it
+  long long eval_pack_gen = 0; // rd_freeze_params generation whose weights / BatchNorm vectors this layout's packs hold
 };
 }  // namespace rd
 
@@ -116,6 +117,8 @@ struct rd_handle : rd::Workspace {
   int depth = 0;
   std::vector<int> widths;
   long long last_w = -1, last_b = -1;
+  long long freeze_gen = 0;    // rd_freeze_params: generation counter, bumped by every switch-on and by rd_bind
+  bool frozen = false;
   std::vector<ParamInfo> params, buffers;
   long long param_floats = 0, buffer_floats = 0;
   float *P = nullptr, *G = nullptr, *BUF = nullptr;   // bound arenas
@@ -697,6 +700,7 @@ int rd_bind(rd_handle* h, float* params, float* grads, float* bn_buffers) {
   if (!params) return fail("rd_bind: null parameter arena");
   if (((uintptr_t)params | (uintptr_t)grads | (uintptr_t)bn_buffers) & 15) return fail("rd_bind: arenas must be 16-byte aligned");
   h->P = params; h->G = grads; h->BUF = bn_buffers;
+  ++h->freeze_gen;                               // packs built from the previous arenas are stale
   return 0;
 }
 
@@ -772,6 +776,7 @@ int rd_reserve(rd_handle* h, int batch, int tile, int with_backward) {
     RD_CUDA(cudaDeviceSynchronize());
   }
   cur.res_batch = batch; cur.res_tile = tile; cur.res_bwd = with_backward;
+  cur.eval_pack_gen = 0;
   cur.ws_id = h->ws_next_id++;
   return 0;
 }
@@ -803,8 +808,13 @@ int rd_forward(rd_handle* h, const float* x, float* y, int batch, int tile, int 
   const int tf = h->tf32() ? 1 : 0;
   const bool fuse_eval = mode == RD_FWD_EVAL;         // nothing is kept for a backward pass: fold BN into the convs
   h->fwd_mode = -1;
-  RD_TRY(pack_weights(h, save, s));
-  if (!train) RD_TRY(bn_eval_all(h, s));
+  // constant-weight inference (rd_freeze_params): this layout's packs were built from the frozen arenas already
+  const bool reuse_packs = fuse_eval && h->frozen && h->eval_pack_gen == h->freeze_gen;
+  if (!reuse_packs) {
+    RD_TRY(pack_weights(h, save, s));
+    if (!train) RD_TRY(bn_eval_all(h, s));
+  }
+  h->eval_pack_gen = (fuse_eval && h->frozen) ? h->freeze_gen : 0;
 
   int np = 0;
   for (int i = 0; i < D; ++i) {
@@ -1361,6 +1371,13 @@ int rd_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n
                  void* stream) {
   if (!dsm || !pos || !stds || n < 0 || tile <= 0 || tile > rows || tile > cols) return fail("rd_tile_stds: bad argument");
   return launch_tile_stds(dsm, rows, cols, pos, n, tile, nodata, stds, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int rd_freeze_params(rd_handle* h, int on) {
+  if (!h) return fail("rd_freeze_params: null handle");
+  if (on) ++h->freeze_gen;
+  h->frozen = on != 0;
+  return 0;
 }
 
 int rd_set_overlap(rd_handle* h, int on) {

@@ -1545,8 +1545,8 @@ struct FirstCfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES;           // hi + lo
   static constexpr int B_BYTES = N * 128;
   static constexpr int B_OFF = FIRST_STAGES * STAGE_BYTES;  // B_hi, then B_lo
-  static constexpr int STG_OFF = B_OFF + 2 * B_BYTES;       // 8 x 4 KB epilogue staging
-  static constexpr int X_OFF = STG_OFF + 8 * 4096;          // FIRST_XS input halo patches
+  static constexpr int STG_OFF = B_OFF + 2 * B_BYTES;       // 8 warps x 2 x 4 KB epilogue staging (TMA-store sources)
+  static constexpr int X_OFF = STG_OFF + 8 * 8192;          // FIRST_XS input halo patches
   static constexpr int BAR_OFF = X_OFF + FIRST_XS * FIRST_X_BYTES;
   static constexpr int SMEM_BYTES = BAR_OFF + 256 + 1024;
   static constexpr int TMEM_COLS = 2 * N <= 32 ? 32 : (2 * N <= 64 ? 64 : (2 * N <= 128 ? 128 : (2 * N <= 256 ? 256 : 512)));
@@ -1571,8 +1571,9 @@ struct FirstFuse {
 };
 template <int N, bool FUSE = false>
 __global__ void __launch_bounds__(FIRST_THREADS, 1)
-conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __restrict__ w, float* __restrict__ z,
-                     float* __restrict__ partials, int B, int Cin, int H, int W, int tw, int th, const FirstFuse F) {
+conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapZ,
+                     const float* __restrict__ w, float* __restrict__ partials, int B, int Cin, int H, int W, int tw,
+                     int th, const FirstFuse F) {
   using Cfg = FirstCfg<N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1597,6 +1598,7 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
     for (int i = 0; i < FIRST_XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 128); }
     fence_mbar_init();
     prefetch_tmap(&mapX);
+    prefetch_tmap(&mapZ);
   }
   if (warp == 4) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   // weights [N][K] (OIHW flattening) -> B_hi / B_lo operand tiles, zero-padded to K = 32
@@ -1709,7 +1711,13 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
     const int q = warp & 3;
     const int half = (warp - 5) >> 2;
     const int row = q * 32 + lane;
-    float* stg = reinterpret_cast<float*>(smem + Cfg::STG_OFF) + (warp - 5) * 1024;
+    // Full-resolution output rows leave through TMA stores: a lane writes ITS row (32 channels = 128 bytes) into a
+    // SWIZZLE_128B box [32 pixels][128 B] (conflict-free STS.128), one lane issues the bulk store.  The transposing
+    // round trip this replaces (STS + LDS + STG per 16 bytes) was two thirds of the epilogue's L1 wavefronts in a
+    // kernel ncu showed at 81 % l1tex throughput and 42 % DRAM.  Box = (32 ch, bw, 32 / bw, 1) pixels of one image;
+    // pixels outside the image are clipped by the TMA unit.
+    uint8_t* stg_raw = smem + Cfg::STG_OFF + (warp - 5) * 8192;
+    float* stg = reinterpret_cast<float*>(stg_raw + 4096);  // FUSE: transposing buffer of the pooled tensor
     constexpr int NCH = N / 32;
     static_assert(NCH <= 2, "one 32-column chunk per epilogue warp");
     const bool has_chunk = half < NCH;
@@ -1723,6 +1731,9 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
       slope = __ldg(F.slope);
     }
     const int iw = FUSE ? (row >> 1) : row % tw, ih = FUSE ? (row & 1) : row / tw;
+    // first pixel of the warp's box inside the tile and this lane's row inside the box (w fastest, then h)
+    const int bw0 = FUSE ? q * 16 : (q * 32) % tw, bh0 = FUSE ? 0 : (q * 32) / tw;
+    const int srow = FUSE ? (lane & 1) * 16 + (lane >> 1) : lane;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -1732,19 +1743,38 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
       const int b = t / tiles_h;
       const int wq = tw_i * tw + iw, hq = th_i * th + ih;
       const bool valid = wq < W && hq < H;
-      const long long p = ((long long)b * H + hq) * W + wq;
       mbar_wait(&t_full[acc], (it >> 1) & 1);
       tc_fence_after();
       if (has_chunk) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + half * 32, v);
+        // the bulk store that last read this staging buffer must have finished reading it
+        uint8_t* sbuf = stg_raw + (FUSE ? 0 : (it & 1) * 4096);
+        if (lane == 0) {
+          if (FUSE) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
+        }
+        __syncwarp();
         if (FUSE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float y = fmaf(v[j], s1[j], s2[j]);
             v[j] = y > 0.f ? y : y * slope;
           }
-          warp_store_rows(stg, lane, v, F.out_a, p * N + half * 32, valid, 0);
+        } else if (partials && valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
+        }
+        const uint32_t sb = smem_u32(sbuf);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          sts128(sb + sw128_off(srow, c), make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+        fence_proxy_async();                                // generic-proxy stores -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&mapZ, sbuf, half * 32, tw_i * tw + bw0, th_i * th + bh0, b);
+          bulk_commit_group();
+        }
+        if (FUSE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {                    // 2x2 window = lanes l, l^1 (other row), l^2, l^3 (next column)
             v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
@@ -1752,18 +1782,13 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const float* __re
           }
           const long long pp = (((long long)b * (H >> 1) + (hq >> 1)) * (W >> 1) + (wq >> 1)) * N + half * 32;
           warp_store_rows(stg, lane, v, F.out_p, pp, valid && (lane & 3) == 0, F.round_p);
-        } else {
-          if (partials && valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { s1[j] += v[j]; s2[j] = fmaf(v[j], v[j], s2[j]); }
-          }
-          warp_store_rows(stg, lane, v, z, p * N + half * 32, valid, 0);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
     }
+    if (has_chunk && lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the reads of the last stores
     if (!FUSE && partials && has_chunk) {
       const float c1 = warp_colsum32(s1, lane), c2 = warp_colsum32(s2, lane);
       float* dst = partials + (size_t)(blockIdx.x * 4 + q) * N * 2;
@@ -1790,15 +1815,15 @@ bool conv_first_tc_shape_ok(int Cin, int Cout, int H, int W) {
 }
 
 template <int N, bool FUSE>
-static int launch_first_t(const CUtensorMap& mapX, const float* w, float* z, float* partials, int B, int Cin, int H, int W,
-                          int tw, int th, int grid, const FirstFuse& F, cudaStream_t s) {
+static int launch_first_t(const CUtensorMap& mapX, const CUtensorMap& mapZ, const float* w, float* partials, int B, int Cin,
+                          int H, int W, int tw, int th, int grid, const FirstFuse& F, cudaStream_t s) {
   using Cfg = FirstCfg<N>;
   static bool attr_set = false;
   if (!attr_set) {
     RD_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<N, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  conv_first_tc_kernel<N, FUSE><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(mapX, w, z, partials, B, Cin, H, W, tw, th, F);
+  conv_first_tc_kernel<N, FUSE><<<grid, FIRST_THREADS, Cfg::SMEM_BYTES, s>>>(mapX, mapZ, w, partials, B, Cin, H, W, tw, th, F);
   RD_LAUNCHED();
   return 0;
 }
@@ -1822,14 +1847,21 @@ int launch_conv_first_tc(const float* x, const float* w, float* z, float* partia
   const long long strides[3] = {(long long)W * 4, (long long)H * W * 4, (long long)Cin * H * W * 4};
   const int box[4] = {tw + 8, th + 2, Cin, 1};
   RD_TRY(tc_encode_map(&mapX, x, 4, dims, strides, box, 2));
+  // output rows (z, or the activated tensor of the fused inference epilogue) as NHWC boxes of 32 channels x 32 pixels
+  CUtensorMap mapZ;
+  const int bw = fuse ? 16 : (tw < 32 ? tw : 32);
+  const long long zdims[4] = {Cout, W, H, B};
+  const long long zstrides[3] = {(long long)Cout * 4, (long long)W * Cout * 4, (long long)H * W * Cout * 4};
+  const int zbox[4] = {32, bw, 32 / bw, 1};
+  RD_TRY(tc_encode_map(&mapZ, fuse ? out_a : z, 4, zdims, zstrides, zbox, 0));
   const long long tiles = (long long)cdiv(W, tw) * cdiv(H, th) * B;
   const int grid = tiles < 148 ? (int)tiles : 148;
   if (n_partials) *n_partials = grid * 4;
   switch (Cout) {
-    case 32: return fuse ? launch_first_t<32, true>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s)
-                         : launch_first_t<32, false>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s);
-    case 64: return fuse ? launch_first_t<64, true>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s)
-                         : launch_first_t<64, false>(mapX, w, z, partials, B, Cin, H, W, tw, th, grid, F, s);
+    case 32: return fuse ? launch_first_t<32, true>(mapX, mapZ, w, partials, B, Cin, H, W, tw, th, grid, F, s)
+                         : launch_first_t<32, false>(mapX, mapZ, w, partials, B, Cin, H, W, tw, th, grid, F, s);
+    case 64: return fuse ? launch_first_t<64, true>(mapX, mapZ, w, partials, B, Cin, H, W, tw, th, grid, F, s)
+                         : launch_first_t<64, false>(mapX, mapZ, w, partials, B, Cin, H, W, tw, th, grid, F, s);
   }
   return fail("conv_first_tc: unsupported Cout=%d", Cout);
 }

@@ -446,8 +446,9 @@ class Trainer(object):
         """Replays (or, the second time the same device buffers are seen, captures) the CUDA graphs of a step on
         these buffers; returns None when the step should run eagerly instead."""
         tensors = (x, y, loss_mask, mean, std)
-        if self.model._rt['handle'].profiling:            # per-category timing events cannot be captured
-            return None
+        handle = self.model._rt['handle']
+        if handle.profiling or handle.frozen:             # timing events cannot be captured; a graph must not depend
+            return None                                   # on packs that outlive a constant_weights() block
         if not all(t.is_cuda and t.is_contiguous() for t in tensors) or x.dtype != torch.float32 \
                 or y.dtype != torch.float32 or mean.dtype != torch.float32 or std.dtype != torch.float32:
             return None

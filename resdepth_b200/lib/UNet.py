@@ -9,6 +9,7 @@ hand-written sm_100a kernels.  There is no PyTorch/CPU fallback: a CPU tensor or
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import List, Optional
 
@@ -215,6 +216,8 @@ class UNet(nn.Module):
                 view = arena[off:off + numel].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
+                if rt['handle'].frozen:                       # constant_weights(): the packed copies are stale now
+                    rt['handle'].freeze_params(True)
         named_b = dict(self.named_buffers())
         bbase = bufs.data_ptr()
         for name, numel, off in rt['binfos']:
@@ -296,6 +299,20 @@ class UNet(nn.Module):
         if device is None:
             device = next(self.parameters()).device
         return self._runtime(torch.device(device))['handle']
+
+    @contextlib.contextmanager
+    def constant_weights(self, device: Optional[torch.device] = None):
+        """Inference with weights that do not change inside the block (the tile loop of ``test.py``): eval-mode
+        forwards re-use the packed GEMM copies of the weights and the BatchNorm scale / shift vectors instead of
+        rebuilding them on every call (``rd_freeze_params``).  The caller promises not to modify parameters or
+        buffers inside the block; ``load_state_dict`` / optimizer steps belong outside it."""
+        handle = self.native_handle(device)
+        handle.freeze_params(True)
+        try:
+            yield self
+        finally:
+            if handle._h:                                   # the handle may have been replaced (math-mode change)
+                handle.freeze_params(False)
 
     # -- public API -------------------------------------------------------------------------------
     def forward(self, x):

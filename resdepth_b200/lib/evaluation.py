@@ -77,7 +77,7 @@ def predict_linear_blend(dataloader, model):
         return xd, geom_d, mean, std, ready
 
     mine = (batch for bi, batch in enumerate(dataloader) if owns_batch(bi, rank, world_size))
-    with torch.no_grad():
+    with torch.no_grad(), model.constant_weights(device):     # nothing in the loop touches the weights: pack once
         nxt = next(mine, None)
         nxt = stage(nxt) if nxt is not None else None
         while nxt is not None:

@@ -618,6 +618,45 @@ def test_workspace_layouts_are_kept_across_shape_changes():
     assert torch.equal(y1, y4)
 
 
+def test_constant_weights_block_reuses_packs_and_sees_new_weights_afterwards(math_mode):
+    """model.constant_weights() (rd_freeze_params): eval forwards inside the block skip the weight pack / BatchNorm
+    finalize launches and return bit-identical outputs, on every workspace layout the block touches; a weight change
+    between two blocks is seen by the second one; a training forward inside a block invalidates that layout's packs."""
+    from resdepth_b200 import _native
+    kwargs, B, T = CASES['kat1']
+    model = _model(kwargs).to(DEV)
+    a = O.synthetic_batch(4, 1, 64, seed=1)['input'].to(DEV)
+    b = O.synthetic_batch(2, 1, 64, seed=2)['input'].to(DEV)
+    _train_step(model, O.synthetic_batch(4, 1, 64, seed=3))          # non-trivial running statistics
+    model.eval()
+    lib = _native.lib()
+    with torch.no_grad():
+        ya, yb = model(a), model(b)
+        lib.rd_launch_count(1)
+        model(a)
+        plain = lib.rd_launch_count(1)
+        with model.constant_weights():
+            assert torch.equal(model(a), ya)                          # first call of the block packs
+            lib.rd_launch_count(1)
+            y2 = model(a)
+            frozen = lib.rd_launch_count(1)
+            assert torch.equal(y2, ya)
+            assert frozen < plain                                     # no pack, no BatchNorm finalize launch
+            assert torch.equal(model(b), yb) and torch.equal(model(b), yb)        # another layout packs once, too
+            assert torch.equal(model(a), ya)
+            model.train()
+            model._forward_native(a, _native.FWD_TRAIN)               # overwrites the layout's BatchNorm vectors
+            model.eval()
+            y_after_train = model(a)
+        assert torch.equal(y_after_train, model(a))                   # the block re-packed after the training forward
+        for p in model.parameters():
+            p.mul_(1.01)
+        y_new = model(a)
+        assert not torch.equal(y_new, y_after_train)
+        with model.constant_weights():
+            assert torch.equal(model(a), y_new) and torch.equal(model(a), y_new)
+
+
 def test_staged_backward_equals_the_single_call():
     """rd_backward_stage 0,1,2 (the data-parallel schedule) writes bit-identical gradients to rd_backward, the stage
     ranges tile the gradient arena, and stages out of order are refused."""
