@@ -1717,7 +1717,6 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
     // kernel ncu showed at 81 % l1tex throughput and 42 % DRAM.  Box = (32 ch, bw, 32 / bw, 1) pixels of one image;
     // pixels outside the image are clipped by the TMA unit.
     uint8_t* stg_raw = smem + Cfg::STG_OFF + (warp - 5) * 8192;
-    float* stg = reinterpret_cast<float*>(stg_raw + 4096);  // FUSE: transposing buffer of the pooled tensor
     constexpr int NCH = N / 32;
     static_assert(NCH <= 2, "one 32-column chunk per epilogue warp");
     const bool has_chunk = half < NCH;
@@ -1749,10 +1748,8 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * N + half * 32, v);
         // the bulk store that last read this staging buffer must have finished reading it
-        uint8_t* sbuf = stg_raw + (FUSE ? 0 : (it & 1) * 4096);
-        if (lane == 0) {
-          if (FUSE) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
-        }
+        uint8_t* sbuf = stg_raw + (it & 1) * 4096;
+        if (lane == 0) bulk_wait_group_read<1>();
         __syncwarp();
         if (FUSE) {
 #pragma unroll
@@ -1775,13 +1772,28 @@ conv_first_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_cons
           bulk_commit_group();
         }
         if (FUSE) {
+          // 2x2 max-pool straight from the staged rows (the TMA store only reads them): the box holds image rows 0 / 1 of
+          // 16 columns, pooled pixel pc = rows {2pc, 2pc+1, 16+2pc, 17+2pc}.  Lane -> (pc = lane / 4, two 16-byte channel
+          // groups); the group order alternates with pc so that the eight lanes of a shared-memory phase hit eight
+          // different swizzled chunk positions, and four lanes write 64 contiguous bytes of a pooled pixel.
+          // (Round 2: the 64-shuffle butterfly + transposing store this replaces made the epilogue warps the
+          // bottleneck of the kernel -- ncu: MMA warp 69 % of its samples waiting for a free accumulator.)
+          const int pc = lane >> 2, jq = lane & 3;
+          const int pw = ((tw_i * tw + bw0) >> 1) + pc, ph = th_i;               // th == 2: one pooled row per tile
+          const bool pvalid = (tw_i * tw + bw0 + 2 * pc) < W && th_i * 2 < H;
+          float* prow = F.out_p + (((long long)b * (H >> 1) + ph) * (W >> 1) + pw) * N + half * 32;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {                    // 2x2 window = lanes l, l^1 (other row), l^2, l^3 (next column)
-            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 1));
-            v[j] = fmaxf(v[j], __shfl_xor_sync(0xffffffffu, v[j], 2));
+          for (int g = 0; g < 2; ++g) {
+            const int j = jq + 4 * ((pc & 1) ^ g);
+            float4 m = lds128(sb + sw128_off(2 * pc, j));
+            const float4 m1 = lds128(sb + sw128_off(2 * pc + 1, j));
+            const float4 m2 = lds128(sb + sw128_off(16 + 2 * pc, j));
+            const float4 m3 = lds128(sb + sw128_off(17 + 2 * pc, j));
+            m.x = fmaxf(fmaxf(m.x, m1.x), fmaxf(m2.x, m3.x)); m.y = fmaxf(fmaxf(m.y, m1.y), fmaxf(m2.y, m3.y));
+            m.z = fmaxf(fmaxf(m.z, m1.z), fmaxf(m2.z, m3.z)); m.w = fmaxf(fmaxf(m.w, m1.w), fmaxf(m2.w, m3.w));
+            if (F.round_p) { m.x = tf32_round(m.x); m.y = tf32_round(m.y); m.z = tf32_round(m.z); m.w = tf32_round(m.w); }
+            if (pvalid) *reinterpret_cast<float4*>(prow + 4 * j) = m;
           }
-          const long long pp = (((long long)b * (H >> 1) + (hq >> 1)) * (W >> 1) + (wq >> 1)) * N + half * 32;
-          warp_store_rows(stg, lane, v, F.out_p, pp, valid && (lane & 3) == 0, F.round_p);
         }
       }
       tc_fence_before();
