@@ -107,6 +107,7 @@ struct Workspace {
   float* taps = nullptr;       // last-conv forward: 9 tap partial sums per pixel
   float* gram = nullptr;       // first encoder block: Gram matrix of the bf16 im2col expansion [Kc][Kc]
   TcReducePlan tc_gram;        // reduce GEMM (xcol, xcol) that produces it
+  bool gram_fused = false;     // the first layer's weight-gradient GEMM also produces the Gram matrix (one pass over xcol)
   long long eval_pack_gen = 0; // rd_freeze_params generation whose weights / BatchNorm vectors this layout's packs hold
 };
 }  // namespace rd
@@ -385,6 +386,7 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
     ConvBlock& b0 = h->enc[0];
     Gather gb = gather_plain(T, T, h->xcol_b_k);
     h->tc_gram.valid = false;
+    h->gram_fused = false;
     if (bf && h->xcol_b && tc_reduce_eligible(gb, b0.Cout, 1)) {
       const int xp = h->xcol_b_pitch != h->xcol_b_k ? h->xcol_b_pitch : 0;
       RD_TRY(tc_make_reduce_plan(&b0.tc_wgrad, h->xcol_b, gb, B, b0.gyb, b0.Cout, h->part, h->part_floats, 1, xp, 0));
@@ -392,8 +394,18 @@ int build_tc_plans(rd_handle* h, int B, int T, int bwd) {
       // Gram matrix of the expansion (same GEMM with the expansion as both operands): lets the first block's weight
       // gradient be formed from gY, without the apply pass of its BatchNorm backward (block_backward)
       static const bool no_gram = getenv("RESDEPTH_NO_GRAM") != nullptr;
-      if (!no_gram && h->cfg.do_bn && b0.Cin * 9 < h->xcol_b_k && tc_reduce_eligible(gb, h->xcol_b_k, 1))
-        RD_TRY(tc_make_reduce_plan(&h->tc_gram, h->xcol_b, gb, B, h->xcol_b, h->xcol_b_k, h->part, h->part_floats, 1, xp, xp));
+      // ... and since both GEMMs have the expansion as their M operand, ONE GEMM with the N tile [xcol | gY] (the xcol box
+      // in shared memory is both operands) yields G and X^T gY from a single pass over xcol: tc_reduce_plan_add_gram
+      static const bool gram_separate = getenv("RESDEPTH_GRAM_SEPARATE") != nullptr;
+      if (!no_gram && h->cfg.do_bn && b0.Cin * 9 < h->xcol_b_k && tc_reduce_eligible(gb, h->xcol_b_k, 1)) {
+        if (!gram_separate && h->xcol_b_k == 64 && b0.Cout == 64 && b0.tc_wgrad.BN == 64 &&
+            (size_t)b0.tc_wgrad.splits * 64 * 128 <= h->part_floats) {
+          RD_TRY(tc_reduce_plan_add_gram(&b0.tc_wgrad, h->part_floats));
+          h->gram_fused = true;
+        } else {
+          RD_TRY(tc_make_reduce_plan(&h->tc_gram, h->xcol_b, gb, B, h->xcol_b, h->xcol_b_k, h->part, h->part_floats, 1, xp, xp));
+        }
+      }
     } else if (h->xcol) {
       Gather g0 = gather_plain(T, T, h->xcol_k);
       if (tc_reduce_eligible(g0, b0.Cout))
@@ -977,7 +989,7 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
   // First encoder block on the bf16 tcgen05 path: its dz feeds only the weight gradient, which is rebuilt from gY, the
   // Gram matrix of the input expansion and the BatchNorm coefficients (launch_first_grad_correct) -- the reduce pass
   // stores gY and the apply pass (a second sweep over z, the largest tensor of the network) is skipped.
-  const bool gy_path = first && b.bb && b.tc_wgrad.valid && h->tc_gram.valid && g_pool.p && do_bn;
+  const bool gy_path = first && b.bb && b.tc_wgrad.valid && (h->tc_gram.valid || h->gram_fused) && g_pool.p && do_bn;
   const bool ov0 = h->overlap && h->overlap_allowed;
   if (gy_path && ov0 && h->wg_pending[b.par]) {           // gY goes into this block's dz buffer: wait for its last reader
     RD_CUDA(cudaStreamWaitEvent(s, h->ev_wg[b.par], 0));
@@ -1022,11 +1034,18 @@ int block_backward(rd_handle* h, ConvBlock& b, GradRef g_full, GradRef g_pool, i
       if (h->xcol_early) h->xcol_early = false;           // expansion already enqueued at the start of the backward pass
       else if (b.bb) {
         RD_TRY(launch_im2col_first_bf16(src_in, h->xcol_b, B, b.Cin, H, H, h->xcol_b_pitch, ws));
-        if (gy_path) RD_TRY(first_layer_gram(h, ws));
+        if (gy_path && !h->gram_fused) RD_TRY(first_layer_gram(h, ws));
       } else RD_TRY(launch_im2col_first(src_in, h->xcol, B, b.Cin, H, H, kc, 1, ws));
       RD_TRY(launch_gemm_reduce_tc(b.tc_wgrad, ws));
-      RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, kc, ws));
-      if (gy_path) RD_TRY(launch_first_grad_correct(h->G + b.w, h->P + b.w, h->gram, h->coef, b.Cout, b.Cin * 9, kc, ws));
+      if (h->gram_fused && b.bb) {
+        // partials [split][kc][2 kc] -> h->gram [kc][2 kc]: columns 0..kc-1 = Gram matrix, kc..2kc-1 = X^T gY
+        RD_TRY(launch_sum_partials(h->part, b.tc_wgrad.splits, kc * 2 * kc, kc * 2 * kc, 1, h->gram, ws));
+        RD_TRY(launch_unpack_first_grad(h->gram + kc, 1, h->G + b.w, b.Cout, b.Cin * 9, kc, ws, 2 * kc));
+        if (gy_path) RD_TRY(launch_first_grad_correct(h->G + b.w, h->P + b.w, h->gram, h->coef, b.Cout, b.Cin * 9, 2 * kc, ws));
+      } else {
+        RD_TRY(launch_unpack_first_grad(h->part, b.tc_wgrad.splits, h->G + b.w, b.Cout, b.Cin * 9, kc, ws));
+        if (gy_path) RD_TRY(launch_first_grad_correct(h->G + b.w, h->P + b.w, h->gram, h->coef, b.Cout, b.Cin * 9, kc, ws));
+      }
     } else {
       RD_TRY(launch_conv_first_wgrad(src_in, h->gy, h->G + b.w, h->scratch, h->scratch_floats, B, b.Cin, H, H, b.Cout, s));
     }

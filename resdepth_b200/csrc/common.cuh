@@ -187,7 +187,7 @@ int residual_statistics(const double* res, const uint8_t* valid, long long n, do
 int launch_tile_stds(const float* dsm, int rows, int cols, const int32_t* pos, int n, int tile, float nodata,
                      double* stds, cudaStream_t s);
 int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s);
-int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s);
+int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s, int pitch = 0);
 // column sums: out[c] = sum over pixels of g[p][c]   (bias gradient of the transposed convs)
 int launch_channel_sum(const float* g, long long npix, int C, float* out, float* scratch, size_t scratch_floats,
                        cudaStream_t s);

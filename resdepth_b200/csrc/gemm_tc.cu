@@ -1220,10 +1220,12 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
     } else {
       active = lane == 4;
       chunk0 = n0 / 64;
+      if (P.g_self) { chunk0 = 0; g_slot = 1; }         // [A chunk | G chunk]: G lands right behind the (single) A box
     }
     int live_chunks = 0;
     for (int gI = 0; gI < groups; ++gI)
       if (m0 + gI * P.a_nch * 64 < P.Mrows) live_chunks += P.a_nch;
+    const int g_boxes = P.g_self ? 1 : Cfg::NB;
     const CUtensorMap* map = is_a ? &mapA : &mapG;
     const bool up2 = P.coord_b < 0;
     int stage = 0;
@@ -1236,7 +1238,7 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
       const int w0 = tw_i * P.tw, h0 = th_i * P.th, b0 = tb_i * P.tb;
       if (lane == 0) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], (live_chunks + Cfg::NB) * Cfg::BOX_BYTES);
+        mbar_arrive_expect_tx(&full_bar[stage], (live_chunks + g_boxes) * Cfg::BOX_BYTES);
       }
       __syncwarp();
       if (active) {
@@ -1254,7 +1256,7 @@ gemm_reduce_bf16_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_c
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sg = sa + 2 * Cfg::BOX_BYTES;
+        const uint32_t sg = P.g_self ? sa : sa + 2 * Cfg::BOX_BYTES;     // self mode: N operand = [A box | G box]
         const uint64_t da0 = smem_desc_sw128(sa, Cfg::BOX_BYTES, 1024), dg0 = smem_desc_sw128(sg, Cfg::BOX_BYTES, 1024);
         if (elect_one()) {
 #pragma unroll
@@ -1399,6 +1401,18 @@ int tc_make_reduce_plan(TcReducePlan* plan, const void* src, const Gather& g, in
   P.boxes_per_split = cdiv(total_boxes, S);
   plan->splits = cdiv(total_boxes, P.boxes_per_split);
   plan->valid = true;
+  return 0;
+}
+
+int tc_reduce_plan_add_gram(TcReducePlan* plan, size_t part_floats) {
+  TcReduceParams& P = plan->p;
+  if (!plan->valid || !P.bf16 || P.ntaps != 1 || P.Ca != 64 || P.Mrows != 64 || P.N != 64 || plan->BN != 64 || P.g_taps)
+    return fail("tc reduce plan: the Gram-fused form needs a bf16 1-tap plan with 64-channel operands");
+  const size_t per = (size_t)P.Mrows * 128;
+  if ((size_t)plan->splits * per > part_floats) return fail("tc reduce plan: partial buffer too small for the Gram-fused form");
+  P.g_self = 1;
+  P.N = 128;
+  plan->BN = 128;
   return 0;
 }
 

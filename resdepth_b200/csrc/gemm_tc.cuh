@@ -62,6 +62,9 @@ struct TcReduceParams {
   int g_taps;            // taps per N tile (0: normal mode)
   int g_nch;             // 64-channel chunks per tap (Cs / 64)
   int g_off[9][2];       // per tap: (w, h) shift of the N operand
+  // "self" mode (bf16, 64-row M operand, 64-column G): the N tile is [A chunk | G chunk] = 128 columns, the A box in shared
+  // memory serving as both operands -- D = A^T [A | G]: the Gram matrix of A and A^T G from ONE pass over both tensors
+  int g_self;
 };
 
 struct TcReducePlan {
@@ -80,6 +83,9 @@ int launch_gemm_reduce_tc(const TcReducePlan& plan, cudaStream_t s);
 // wide 3x3 weight gradient (bf16): D[cu][(tap, cs)] = sum_p U[p][cu] * S[p + sign*off(tap)][cs]; U, S: bf16 NHWC
 // [B,H,W,Cu] / [B,H,W,Cs], Cu % 128 == 0, Cs in {64, 128}.  part: [splits][Cu][ntiles*BN] (see plan->p.N)
 bool tc_reduce_wide_eligible(int Cu, int Cs, int H, int W);
+// turns a bf16 1-tap plan with a 64-channel A operand and N = 64 into the "self" form (TcReduceParams::g_self): output
+// [64][128] per split, columns 0..63 = A^T A, columns 64..127 = A^T G
+int tc_reduce_plan_add_gram(TcReducePlan* plan, size_t part_floats);
 int tc_make_reduce_plan_wide(TcReducePlan* plan, const void* U, int Cu, const void* S, int Cs, int sign, int B, int H,
                              int W, float* part, size_t part_floats);
 

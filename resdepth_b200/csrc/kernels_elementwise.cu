@@ -1256,14 +1256,14 @@ int launch_im2col_first_bf16_clear(void* xcol, size_t bytes, cudaStream_t s) {
 // 32 consecutive outputs per block (coalesced 128-byte reads of every split), the splits spread over the 8 warps and
 // combined in a fixed order: the one-wave reduce GEMM of this layer produces ~148 splits of only Co*K values each
 __global__ void __launch_bounds__(256)
-unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co, int K, int Kc) {
+unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restrict__ dw, int Co, int K, int Kc, int pitch) {
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane, total = Co * K;
   const int co = i % Co, k = i / Co;
   float a = 0.f;
   if (i < total)
-    for (int sp = w; sp < S; sp += 8) a += part[((size_t)sp * Kc + k) * Co + co];
+    for (int sp = w; sp < S; sp += 8) a += part[((size_t)sp * Kc + k) * pitch + co];
   red[w][lane] = a;
   __syncthreads();
   if (w == 0 && i < total) {
@@ -1272,8 +1272,8 @@ unpack_first_grad_kernel(const float* __restrict__ part, int S, float* __restric
     dw[(size_t)co * K + k] = a;
   }
 }
-int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s) {
-  unpack_first_grad_kernel<<<cdiv(Co * K, 32), 256, 0, s>>>(part, S, dw, Co, K, Kc);
+int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K, int Kc, cudaStream_t s, int pitch) {
+  unpack_first_grad_kernel<<<cdiv(Co * K, 32), 256, 0, s>>>(part, S, dw, Co, K, Kc, pitch ? pitch : Co);
   RD_LAUNCHED();
   return 0;
 }
@@ -1286,7 +1286,7 @@ int launch_unpack_first_grad(const float* part, int S, float* dw, int Co, int K,
 // im2col kernel writes a constant-one column there).  One thread per (co, k); K <= 27.
 __global__ void __launch_bounds__(256)
 first_grad_correct_kernel(float* __restrict__ dw, const float* __restrict__ w, const float* __restrict__ gram,
-                          const BwdCoef* __restrict__ coef, int Co, int K, int Kc) {
+                          const BwdCoef* __restrict__ coef, int Co, int K, int Kc) {   // Kc: row pitch of gram
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= Co * K) return;
   const int co = i / K, k = i - co * K;
