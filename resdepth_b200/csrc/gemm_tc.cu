@@ -1546,8 +1546,11 @@ bool tc_available() { return encode_fn() != nullptr; }
 //   warps 0-3: builders -- thread r reads the 27 input values of pixel r from the patch in shared memory, splits
 //              them and writes row r of the K-major SWIZZLE_128B operand tiles A_hi / A_lo (+ proxy fence)
 //   warp 4   : TMEM allocator, MMA issuer (12 tcgen05.mma of K = 8 per 128-pixel tile)
-//   warps 5-8: epilogue (TMEM lane quarter = warp % 4... see q below): z rows through the transposing staging
-//              buffer, BatchNorm column sums kept in registers across the CTA's tiles
+//   warps 5-12: epilogue (TMEM lane quarter = warp % 4, even / odd 32-column chunk = (warp - 5) / 4): a lane owns one
+//              output row (pixel); it writes its 128 bytes into a SWIZZLE_128B staging box and one lane issues a TMA
+//              store of the box (32 channels x 32 pixels) -- no transposition, no STG; BatchNorm column sums are kept
+//              per lane in registers across the CTA's tiles.  Fused inference form: BatchNorm + activation before the
+//              store, 2x2 max-pool read back from the staged rows.
 // ---------------------------------------------------------------------------------------------
 static constexpr int FIRST_THREADS = 448;         // 4 builder warps, MMA warp, 8 epilogue warps, input-TMA warp
 static constexpr int FIRST_XS = 4;                // input halo patches in flight
