@@ -84,9 +84,11 @@ struct RowsCfg {
 // cover one row: each warp-level access then touches 4 rows x 128 contiguous bytes (4 wavefronts).  `off` is the
 // element offset of the lane's row.  (The transposed-conv epilogues, which also add the skip tensor, have their own
 // versions of this: convt_epilogue / convt_ring_epilogue.)
+template <bool SUMS = false>
 __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const float (&v)[32], float* __restrict__ out,
                                                 long long off, bool ok, int rnd,
-                                                __nv_bfloat16* __restrict__ outb = nullptr) {
+                                                __nv_bfloat16* __restrict__ outb = nullptr, float4* s1 = nullptr,
+                                                float4* s2 = nullptr) {
   const uint32_t stg_s = smem_u32(stg);
 #pragma unroll
   for (int c4 = 0; c4 < 8; ++c4)
@@ -108,6 +110,13 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3);
     float4 val = lds128(stg_s + (r * 32 + ((c4 ^ (r & 7)) << 2)) * 4);
+    if (SUMS && ((okm >> i) & 1)) {
+      // column sums (BatchNorm statistics / bias gradient) of the valid rows, per lane: this lane's four channels over its
+      // eight rows -- the cross-lane part (four lane groups) is done ONCE per kernel, not with a 31-shuffle butterfly per chunk
+      s1->x += val.x; s1->y += val.y; s1->z += val.z; s1->w += val.w;
+      s2->x = fmaf(val.x, val.x, s2->x); s2->y = fmaf(val.y, val.y, s2->y);
+      s2->z = fmaf(val.z, val.z, s2->z); s2->w = fmaf(val.w, val.w, s2->w);
+    }
     if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
     if ((okm >> i) & 1) {
       if (out) *reinterpret_cast<float4*>(out + o[i]) = val;
@@ -647,9 +656,9 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                               tfull_bar, tempty_bar, num_tiles, n_tiles);
     } else {
     constexpr int NCH = BN / 32, NCH2 = (NCH + 1) / 2;
-    float cs1[NCH2], cs2[NCH2];
+    float4 cs1[NCH2], cs2[NCH2];                        // transposed-domain column sums: channels 4*(lane%8)..+3 of chunk ci
 #pragma unroll
-    for (int i = 0; i < NCH2; ++i) cs1[i] = cs2[i] = 0.f;
+    for (int i = 0; i < NCH2; ++i) cs1[i] = cs2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int iw = row % P.tw, ih = (row / P.tw) % P.th, ib = row / (P.tw * P.th);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -691,18 +700,12 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           warp_bnact_store_rows(stg, lane, v, bn_sc, bn_sh, bn_slope, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
                                 P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1), P.round_pool, P.tw);
         } else {
-          if (P.epi_mode == EPI_STATS) {
-            float sv[32], sq[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sv[j] = valid ? v[j] : 0.f;
-              sq[j] = sv[j] * sv[j];
-            }
-            cs1[ci] += warp_colsum32(sv, lane);
-            cs2[ci] += warp_colsum32(sq, lane);
-          }
-          warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
-                          reinterpret_cast<__nv_bfloat16*>(P.out_b));
+          if (P.epi_mode == EPI_STATS)
+            warp_store_rows<true>(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
+                                  reinterpret_cast<__nv_bfloat16*>(P.out_b), &cs1[ci], &cs2[ci]);
+          else
+            warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
+                            reinterpret_cast<__nv_bfloat16*>(P.out_b));
         }
       }
       }   // sub-tiles
@@ -711,7 +714,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if (P.epi_mode == EPI_STATS) {
-      // lane c holds the sums of column (chunk*32 + c) over this warp's rows of all tiles of this CTA
+      // lane holds the sums of its four channels over the rows it handled (all tiles of this CTA); the four lane groups
+      // (lane / 8) cover disjoint rows: two xor steps complete the warp's column sums in lanes 0..7.
       // partial row = (CTA group, warp); the n_tiles CTAs of a group (fixed N tile each: gridDim.x is a multiple
       // of n_tiles) fill disjoint column ranges of the same partial rows
       const int nt = blockIdx.x % n_tiles;
@@ -721,9 +725,20 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       for (int ci = 0; ci < NCH2; ++ci) {
         const int ch = 2 * ci + half;
         if (ch >= NCH) break;
-        const int col = ch * 32 + lane;
-        dst[col * 2 + 0] = had_tiles ? cs1[ci] : 0.f;
-        dst[col * 2 + 1] = had_tiles ? cs2[ci] : 0.f;
+        float a[8] = {cs1[ci].x, cs1[ci].y, cs1[ci].z, cs1[ci].w, cs2[ci].x, cs2[ci].y, cs2[ci].z, cs2[ci].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+          a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int col = ch * 32 + lane * 4 + e;
+            dst[col * 2 + 0] = had_tiles ? a[e] : 0.f;
+            dst[col * 2 + 1] = had_tiles ? a[4 + e] : 0.f;
+          }
+        }
       }
     }
     }   // !RING
