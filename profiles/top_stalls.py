@@ -56,3 +56,23 @@ for k, r in enumerate(kernels):
         stalls = {c: f(x, c) for c in h if c.startswith('stall_') and 'Not' not in c}
         top = sorted(stalls.items(), key=lambda kv: -kv[1])[:2]
         print('   ', x[si['Address']][-5:], x[si['Source']][:90].ljust(90), int(f(x, '# Samples')), top)
+    # samples per code region (64 instructions), in address order, with the marker opcodes the region contains: tells the
+    # warp roles apart (UTMALDG = TMA producer, UTCHMMA = MMA issuer, LDTM = epilogue) when the kernel is warp-specialised
+    if len(sys.argv) > 4 and sys.argv[4] == 'regions':
+        marks = ('UTMALDG', 'UTMASTG', 'UTCHMMA', 'UTCBAR', 'LDTM', 'SYNCS', 'SHFL', 'STS', 'LDS', 'STG', 'LDG', 'BAR')
+        ordered = sorted(body, key=lambda x: x[si['Address']])
+        print('   regions (64 instructions each): start address, samples, share, two dominant stalls, marker opcodes')
+        for b0 in range(0, len(ordered), 64):
+            blk = ordered[b0:b0 + 64]
+            smp = sum(f(x, '# Samples') for x in blk)
+            if smp < 0.004 * total:
+                continue
+            st = {}
+            for x in blk:
+                for c in h:
+                    if c.startswith('stall_') and 'Not' not in c:
+                        st[c] = st.get(c, 0.0) + f(x, c)
+            top = sorted(st.items(), key=lambda kv: -kv[1])[:2]
+            present = [m for m in marks if any(m in x[si['Source']] for x in blk)]
+            print(f'    {blk[0][si["Address"]][-5:]}  {int(smp):6d}  {100 * smp / total:5.1f}%  '
+                  f'{[(c[6:], int(v)) for c, v in top]}  {" ".join(present)}')

@@ -462,6 +462,8 @@ __device__ __forceinline__ void convt_ring_epilogue(const TcRowsParams& P, uint8
   cp_async_wait<0>();
 }
 
+#define RD_REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 72;")
+#define RD_REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 216;")
 template <int BN, bool HALO, bool BF16, bool RING = false>
 __global__ void __launch_bounds__(ROWS_THREADS, 1)
 gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
@@ -492,6 +494,10 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Warp-specialised register budget: the producer / MMA-issuer warpgroup (warps 0-3) gives registers back, the two
+  // epilogue warpgroups (warps 4-11) take them: 128 x 72 + 256 x 216 = 64 512 <= 65 536.  The epilogue is the
+  // instruction- and latency-bound part of every HBM-bound layer (ncu round 2) and was held at 168 registers with spills.
+  // (the instructions sit at the top of each role's branch: ptxas bounds the registers of the code a setmaxnreg dominates)
 
   const int n_tiles = P.N / BN;
   const int m_tiles = P.tiles_w * P.tiles_h * P.tiles_b;
@@ -501,6 +507,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   if (HALO && (warp == 0 || warp == 2)) {
     // ===== halo variant: warp 0 streams the halo patches (one per 32-channel chunk), warp 2 the weight tiles
     // (one per chunk and tap); the two rings advance independently =====
+    RD_REG_DEC();
     if (lane == 0) {
       int slot = 0;
       uint32_t phase = 0;
@@ -532,6 +539,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   } else if (HALO && warp == 1) {
     // ===== halo variant MMA issuer: the whole warp walks the loop, one elected lane issues =====
+    RD_REG_DEC();
     {
       constexpr uint32_t idesc = BF16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int aslot = 0, bslot = 0;
@@ -584,6 +592,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (!HALO && warp == 0) {
     // ===== TMA producer: lane 0 waits for the slot and arms the barrier, then lane 0 issues the A box and
     // lane 1 the B box (coordinates in registers, no indexed arrays) =====
+    RD_REG_DEC();
     const bool up2 = P.coord_b < 0;                   // (c, w, a, b*h) view of the 2x-upsampled tensor; else (c, w, h, b)
     int stage = 0;
     uint32_t phase = 0;
@@ -613,6 +622,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     }
   } else if (!HALO && warp == 1) {
     // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
+    RD_REG_DEC();
     {
       constexpr uint32_t idesc = BF16 ? idesc_bf16(128, BN, 0, 0) : idesc_tf32(128, BN, 0, 0);
       int stage = 0;
@@ -647,6 +657,7 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   } else if (warp >= 4) {
     // ===== 8 epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter take the even / odd
     // 32-column chunks, doubling the loads and stores in flight for the HBM-bound layers =====
+    RD_REG_INC();
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
@@ -742,6 +753,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       }
     }
     }   // !RING
+  } else {
+    RD_REG_DEC();                                       // idle warps of the first warpgroup: the whole group must release
   }
   tc_fence_before();
   __syncthreads();
@@ -750,6 +763,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
+#undef RD_REG_DEC
+#undef RD_REG_INC
 
 // ---------------------------------------------------------------------------------------------
 // host side
