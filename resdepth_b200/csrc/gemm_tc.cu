@@ -84,9 +84,21 @@ struct RowsCfg {
 // cover one row: each warp-level access then touches 4 rows x 128 contiguous bytes (4 wavefronts).  `off` is the
 // element offset of the lane's row.  (The transposed-conv epilogues, which also add the skip tensor, have their own
 // versions of this: convt_epilogue / convt_ring_epilogue.)
+// Row offsets of a (sub-)tile in the transposed domain (lane -> rows i*4 + lane/8): shuffled ONCE per 128-row tile, not
+// per 32-column chunk.  32-bit element offsets: the launcher rejects outputs of 2^32 elements or more.
+__device__ __forceinline__ void rows_to_transposed(int lane, unsigned row_off, bool ok, unsigned (&R)[8], unsigned& okm) {
+  okm = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3);
+    R[i] = __shfl_sync(0xffffffffu, row_off, r);
+    okm |= (unsigned)__shfl_sync(0xffffffffu, (int)ok, r) << i;
+  }
+}
+// `col` = element offset of the chunk inside a row + this lane's 4-channel group (n + 4 * (lane % 8)).
 template <bool SUMS = false>
 __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const float (&v)[32], float* __restrict__ out,
-                                                long long off, bool ok, int rnd,
+                                                const unsigned (&R)[8], unsigned okm, unsigned col, int rnd,
                                                 __nv_bfloat16* __restrict__ outb = nullptr, float4* s1 = nullptr,
                                                 float4* s2 = nullptr) {
   const uint32_t stg_s = smem_u32(stg);
@@ -96,16 +108,6 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
              make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]));
   __syncwarp();
   const int c4 = lane & 7;
-  const unsigned off_lo = (unsigned)(off & 0xffffffffu), off_hi = (unsigned)((unsigned long long)off >> 32);
-  long long o[8];
-  unsigned okm = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + (lane >> 3);
-    const unsigned lo = __shfl_sync(0xffffffffu, off_lo, r), hi = __shfl_sync(0xffffffffu, off_hi, r);
-    okm |= (unsigned)__shfl_sync(0xffffffffu, (int)ok, r) << i;
-    o[i] = (long long)(((unsigned long long)hi << 32) | lo) + c4 * 4;
-  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = i * 4 + (lane >> 3);
@@ -119,13 +121,14 @@ __device__ __forceinline__ void warp_store_rows(float* stg, int lane, const floa
     }
     if (rnd) { val.x = tf32_round(val.x); val.y = tf32_round(val.y); val.z = tf32_round(val.z); val.w = tf32_round(val.w); }
     if ((okm >> i) & 1) {
-      if (out) *reinterpret_cast<float4*>(out + o[i]) = val;
+      const size_t o = (size_t)(R[i] + col);
+      if (out) *reinterpret_cast<float4*>(out + o) = val;
       if (outb) {
         __nv_bfloat162 lo2 = __floats2bfloat162_rn(val.x, val.y), hi2 = __floats2bfloat162_rn(val.z, val.w);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo2);
         pk.y = *reinterpret_cast<uint32_t*>(&hi2);
-        *reinterpret_cast<uint2*>(outb + o[i]) = pk;
+        *reinterpret_cast<uint2*>(outb + o) = pk;
       }
     }
   }
@@ -691,6 +694,8 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         convt_epilogue<BN>(P, stg, lane, half, t_row, nt, b, h, w, valid);
         continue;
       }
+      unsigned Rt[8], okt = 0;                           // PLAIN / STATS: transposed-domain row offsets of this sub-tile
+      if (P.epi_mode != EPI_BNACT) rows_to_transposed(lane, (unsigned)(pix * P.N), valid, Rt, okt);
 #pragma unroll
       for (int ci = 0; ci < NCH2; ++ci) {
         const int ch = 2 * ci + half;
@@ -712,10 +717,10 @@ gemm_rows_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
                                 P.pool_out, (long long)(pp * P.N + n), valid && !(w & 1) && !(h & 1), P.round_pool, P.tw);
         } else {
           if (P.epi_mode == EPI_STATS)
-            warp_store_rows<true>(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
+            warp_store_rows<true>(stg, lane, v, P.out, Rt, okt, (unsigned)(n + 4 * (lane & 7)), P.round_tf32,
                                   reinterpret_cast<__nv_bfloat16*>(P.out_b), &cs1[ci], &cs2[ci]);
           else
-            warp_store_rows(stg, lane, v, P.out, (long long)(pix * P.N + n), valid, P.round_tf32,
+            warp_store_rows(stg, lane, v, P.out, Rt, okt, (unsigned)(n + 4 * (lane & 7)), P.round_tf32,
                             reinterpret_cast<__nv_bfloat16*>(P.out_b));
         }
       }
@@ -945,8 +950,8 @@ int launch_gemm_rows_tc(const TcRowsPlan& plan, const Epilogue& e, int* n_partia
   P.pool_out = e.pool_out;
   P.round_pool = e.round_pool;
   P.out_b = e.out_b;
-  if (e.mode == EPI_CONVT && (double)P.Bo * P.Ho * P.Wo * P.N >= 4294967296.0)
-    return fail("tc rows: transposed-conv output of 2^32 elements or more (reduce the batch)");
+  if (e.mode != EPI_BNACT && (double)P.Bo * P.Ho * P.Wo * P.N >= 4294967296.0)
+    return fail("tc rows: output of 2^32 elements or more (32-bit element offsets in the epilogue: reduce the batch)");
   if (e.mode == EPI_BNACT && e.pool_out && (P.tw < 2 || P.th < 2 || (P.Wo & 1) || (P.Ho & 1)))
     return fail("tc rows: fused pooling needs even image sizes and a tile of at least 2x2 pixels");
   const int n_tiles = P.N / plan.BN;
