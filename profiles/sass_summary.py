@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'resdepth_b200', '_lib', 'libresdepth_b200.so')
-KEYS = ['UTCHMMA', 'UTCQMMA', 'UTCIMMA', 'UTCOMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UTCBAR', 'UTCATOMSWS',
+KEYS = ['UTCHMMA', 'UTCQMMA', 'UTCIMMA', 'UTCOMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'UTCBAR', 'UTCATOMSWS', 'USETMAXREG',
         'SYNCS', 'LDGSTS', 'FFMA2', 'HMMA', 'STG', 'LDG', 'STS', 'LDS', 'SHFL']
 
 
