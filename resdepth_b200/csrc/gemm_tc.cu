@@ -10,13 +10,16 @@
 //     accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   * warp roles (384 threads): warp 0 = activation-TMA producer, warp 1 = TMEM allocator + MMA issuer, warp 2 =
 //     weight-TMA producer of the halo variant, warps 4..11 = epilogue (tcgen05.ld 32 lanes x 32 columns -> registers ->
-//     fused epilogue -> transposition through swizzled shared memory -> 128-byte row stores).
+//     fused epilogue -> transposition through swizzled shared memory -> 128-byte row stores).  Register budget by
+//     role (setmaxnreg): the first warpgroup releases down to 72 registers per thread, the two epilogue warpgroups
+//     take 216 -- the epilogue is the instruction- and latency-bound part of every layer with short K.
 //   * variants: HALO (3x3 layers with N <= 128: one 18 x 18 halo patch per channel chunk serves all nine taps and two
 //     sub-tiles; weight tiles of three taps per slot), RING (HBM-bound up-convs: skip rows by per-warp cp.async rings),
 //     BF16 (backward GEMMs, kind::f16).  The file also holds the reduce kernels (weight gradients, incl. the wide-N
 //     formulation) and the first-conv kernel (software im2col producer, 3xTF32).
 //   * persistent CTAs, static tile schedule with a fixed N tile per CTA so BatchNorm column sums accumulate in
-//     registers across all of a CTA's tiles (one partial row per CTA-warp instead of one per tile).
+//     registers across all of a CTA's tiles (one partial row per CTA-warp instead of one per tile); they are taken in
+//     the transposed domain of the store path (a lane's four channels over its rows), with one cross-lane step per kernel.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
